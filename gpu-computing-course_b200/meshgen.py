@@ -1,0 +1,86 @@
+"""Synthetic workloads (BASELINE.json configs C1..C5) — ctypes view of csrc/meshgen.c.
+
+Host-side workload utilities only; the collision library never calls these.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "lib", "libb200cd_meshgen.so")
+_LIB = None
+
+# the reference's hard-coded Morton normalisation box (reference morton.h:45,51,57)
+REF_ORIGIN = (0.004501, -0.476622, -0.381965)
+REF_EXTENT = (3.08, 0.76, 2.36)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_PATH):
+            raise RuntimeError(f"{_PATH} missing - run __graft_entry__.build() / make -C gpu-computing-course_b200/csrc")
+        _LIB = C.CDLL(_PATH)
+        _LIB.mg_grid_num_verts.restype = C.c_uint64
+        _LIB.mg_grid_num_tris.restype = C.c_uint64
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def soup(n, h=None, seed=1234, origin=(0.0, 0.0, 0.0), extent=(1.0, 1.0, 1.0), out=None):
+    """C4: n private triangles, centroids uniform in the box, vertex jitter +-h.
+
+    Default h keeps SURVEY §8(d)'s density: h = 0.68 * (box volume / n)^(1/3)."""
+    if h is None:
+        h = 0.68 * (extent[0] * extent[1] * extent[2] / n) ** (1.0 / 3.0)
+    if out is None:
+        xyz = np.empty((3 * n, 3), np.float32)
+        idx = np.empty((n, 3), np.uint32)
+    else:
+        xyz, idx = out
+    o = (C.c_double * 3)(*origin)
+    e = (C.c_double * 3)(*extent)
+    lib().mg_soup(C.c_uint32(n), C.c_double(h), C.c_uint64(seed), o, e, _p(xyz, C.c_float), _p(idx, C.c_uint32))
+    return xyz, idx
+
+
+def _grid_alloc(nx, ny, sheets=1):
+    nv = (nx + 1) * (ny + 1) * sheets
+    nt = 2 * nx * ny * sheets
+    return np.empty((nv, 3), np.float32), np.empty((nt, 3), np.uint32)
+
+
+def cloth_fold(nx=708, ny=708, layers=8, gap_edges=0.5, amp=1.5, wl_edges=12.0, seed=1):
+    """C3: accordion-folded sheet inside the reference Morton box, dense contacts."""
+    xyz, idx = _grid_alloc(nx, ny)
+    lib().mg_cloth_fold(C.c_uint32(nx), C.c_uint32(ny), C.c_uint32(layers), C.c_double(gap_edges), C.c_double(amp),
+                        C.c_double(wl_edges), C.c_uint64(seed), _p(xyz, C.c_float), _p(idx, C.c_uint32))
+    return xyz, idx
+
+
+def two_sheets(nq=4096, seed=7):
+    """C5: two nq x nq-quad sheets intersecting along curves, unit cube."""
+    xyz, idx = _grid_alloc(nq, nq, 2)
+    lib().mg_two_sheets(C.c_uint32(nq), C.c_uint64(seed), _p(xyz, C.c_float), _p(idx, C.c_uint32))
+    return xyz, idx
+
+
+def flag(nx=795, nz=794, nfold=3, seed=2021):
+    """C1/C2 stand-in for the missing flag-2000-changed.obj (1 262 460 triangles by default)."""
+    xyz, idx = _grid_alloc(nx, nz)
+    lib().mg_flag(C.c_uint32(nx), C.c_uint32(nz), C.c_uint32(nfold), C.c_uint64(seed), _p(xyz, C.c_float),
+                  _p(idx, C.c_uint32))
+    return xyz, idx
+
+
+def write_obj(path, xyz, idx):
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    idx = np.ascontiguousarray(idx, np.uint32)
+    rc = lib().mg_write_obj(os.fsencode(path), _p(xyz, C.c_float), C.c_uint32(xyz.shape[0]), _p(idx, C.c_uint32),
+                            C.c_uint32(idx.shape[0]))
+    if rc != 0:
+        raise OSError(f"mg_write_obj({path}) failed: {rc}")

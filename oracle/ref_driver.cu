@@ -1,0 +1,207 @@
+/*
+ * ref_driver.cu — thin driver around the REFERENCE'S OWN host functions.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/README.md). Built by oracle/Makefile into
+ * oracle/_ref/libref_cd.so, *including the reference headers from where they lie*
+ * (-I/root/reference/CollisionDetection); no reference source is copied into this
+ * repository. It exists to (1) pin the CPU restatement oracle/cd_oracle.c against
+ * the real reference code, (2) generate tests/golden/ fixtures, (3) serve as the
+ * "reference" CPU baseline bench.py times on the GPU box's host cores.
+ *
+ * What is the reference's and what is ours:
+ *   reference (called unmodified): loadObj (load_obj.h:24), morton3D (morton.h:70),
+ *     thrust::sort_by_key as load_obj.h:107 uses it, fillLeafNodesCpu (cpu.cuh:89),
+ *     generateHierarchyParallelCpu (cpu.cuh:110), calBoundingBoxCpu (cpu.cuh:167),
+ *     findCollisionIterativeCpu (cpu.cuh:196), determineRangeCpu / findSplitCpu
+ *     (cpu.cuh:65,22), checkTriangleContact (tri_contact.cuh:19), checkBoxOverlap
+ *     (box.cuh:40).
+ *   ours: this driver (the reference's cpu_main.cu is entirely commented out,
+ *     cpu_main.cu:1-117); clzll() — the reference's cpu_math.cpp:12-27 is broken
+ *     (never terminates for 0, wrong mask), so we supply device-__clzll semantics,
+ *     which is what the reference's GPU path uses (bvh.cuh:48); zeroed node storage
+ *     (Node() leaves isLeaf/idx/childCount uninitialised, bvh.cuh:38-42); a pair
+ *     buffer that grows (main.cu:81 fixes it at 500 pairs).
+ *   not linked: findCollisionsCpu (cpu.cuh:247-271) reads threadIdx in host code;
+ *     it is dropped by -fvisibility=hidden + --gc-sections.
+ */
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "load_obj.h"
+#include "cpu.cuh"
+
+int clzll(unsigned long long x, int) { return x ? __builtin_clzll(x) : 64; }
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+struct RefMesh {
+    std::vector<vec3f> verts;
+    std::vector<Triangle> tris;   // sorted by Morton code after load (load_obj.h:107)
+    std::vector<unsigned long long> mortons;
+    Node* leaves = nullptr;
+    Node* inner = nullptr;
+    unsigned int wrong_parent = 0;
+    std::vector<unsigned int> pairs;
+    unsigned int npairs = 0;
+    double ms_load = 0, ms_fill = 0, ms_hier = 0, ms_refit = 0, ms_query = 0;
+    ~RefMesh() { free(leaves); free(inner); }
+};
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+REF_API void* ref_load_obj(const char* path) {
+    auto* m = new RefMesh;
+    double t0 = now_ms();
+    loadObj(std::string(path), m->verts, m->tris, m->mortons);
+    m->ms_load = now_ms() - t0;
+    return m;
+}
+
+/* Same steps as the face branch of loadObj (load_obj.h:76-107) — push vertices,
+ * then for each face compute centroid + morton3D with the reference's own
+ * function, then the reference's thrust::sort_by_key call — but fed from arrays
+ * so multi-million-triangle meshes do not need to go through OBJ text. */
+REF_API void* ref_from_arrays(const float* xyz, uint32_t nverts, const uint32_t* idx, uint32_t ntris) {
+    auto* m = new RefMesh;
+    double t0 = now_ms();
+    m->verts.reserve(nverts);
+    for (uint32_t i = 0; i < nverts; ++i) m->verts.push_back(vec3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+    m->tris.reserve(ntris);
+    m->mortons.reserve(ntris);
+    for (uint32_t t = 0; t < ntris; ++t) {
+        Triangle f;
+        f.vIdx[0] = idx[3 * t]; f.vIdx[1] = idx[3 * t + 1]; f.vIdx[2] = idx[3 * t + 2];
+        vec3f *p1 = &m->verts[f.vIdx[0]], *p2 = &m->verts[f.vIdx[1]], *p3 = &m->verts[f.vIdx[2]];
+        double xAvg = (p1->x + p2->x + p3->x) / 3, yAvg = (p1->y + p2->y + p3->y) / 3,
+               zAvg = (p1->z + p2->z + p3->z) / 3;
+        f.ID = (unsigned int)m->tris.size();
+        f.morton = morton3D(xAvg, yAvg, zAvg);
+        f.ax = xAvg; f.ay = yAvg; f.az = zAvg;
+        m->tris.push_back(f);
+        m->mortons.push_back(f.morton);
+    }
+    thrust::sort_by_key(m->mortons.begin(), m->mortons.end(), m->tris.begin());
+    m->ms_load = now_ms() - t0;
+    return m;
+}
+
+REF_API void ref_free(void* h) { delete static_cast<RefMesh*>(h); }
+REF_API uint32_t ref_num_verts(void* h) { return (uint32_t) static_cast<RefMesh*>(h)->verts.size(); }
+REF_API uint32_t ref_num_tris(void* h) { return (uint32_t) static_cast<RefMesh*>(h)->tris.size(); }
+
+/* vertices as the floats they were parsed as; triangle indices in ID (face) order */
+REF_API void ref_get_mesh(void* h, float* xyz, uint32_t* idx) {
+    auto* m = static_cast<RefMesh*>(h);
+    for (size_t i = 0; i < m->verts.size(); ++i) {
+        xyz[3 * i] = (float)m->verts[i].x; xyz[3 * i + 1] = (float)m->verts[i].y; xyz[3 * i + 2] = (float)m->verts[i].z;
+    }
+    for (const Triangle& t : m->tris)
+        for (int k = 0; k < 3; ++k) idx[3 * (size_t)t.ID + k] = t.vIdx[k];
+}
+
+REF_API void ref_get_sorted(void* h, uint64_t* keys, uint32_t* ids) {
+    auto* m = static_cast<RefMesh*>(h);
+    for (size_t i = 0; i < m->tris.size(); ++i) { keys[i] = m->mortons[i]; ids[i] = m->tris[i].ID; }
+}
+
+/* cpu_main.cu:55-90 equivalent */
+REF_API unsigned int ref_build(void* h) {
+    auto* m = static_cast<RefMesh*>(h);
+    const int n = (int)m->tris.size();
+    free(m->leaves); free(m->inner);
+    m->leaves = static_cast<Node*>(calloc((size_t)n, sizeof(Node)));
+    m->inner = static_cast<Node*>(calloc((size_t)(n > 1 ? n - 1 : 1), sizeof(Node)));
+    m->wrong_parent = 0;
+    double t0 = now_ms();
+    fillLeafNodesCpu(m->tris.data(), n, m->leaves);
+    double t1 = now_ms();
+    generateHierarchyParallelCpu(m->mortons.data(), n, m->leaves, m->inner, &m->wrong_parent);
+    double t2 = now_ms();
+    calBoundingBoxCpu(m->leaves, m->verts.data(), (unsigned int)n);
+    double t3 = now_ms();
+    m->ms_fill = t1 - t0; m->ms_hier = t2 - t1; m->ms_refit = t3 - t2;
+    return m->wrong_parent;
+}
+
+/* unified numbering: internal i -> i, leaf j -> (n-1)+j */
+REF_API void ref_get_nodes(void* h, int32_t* left, int32_t* right, int32_t* parent, uint32_t* bounded,
+                           double* bounds) {
+    auto* m = static_cast<RefMesh*>(h);
+    const int n = (int)m->tris.size();
+    auto number = [&](Node* p) -> int32_t {
+        if (!p) return -1;
+        if (p >= m->leaves && p < m->leaves + n) return (int32_t)((n - 1) + (p - m->leaves));
+        return (int32_t)(p - m->inner);
+    };
+    for (int i = 0; i < 2 * n - 1; ++i) {
+        Node* nd = i < n - 1 ? &m->inner[i] : &m->leaves[i - (n - 1)];
+        if (i < n - 1) { left[i] = number(nd->childA); right[i] = number(nd->childB); bounded[i] = nd->bounded; }
+        parent[i] = number(nd->parent);
+        double* b = bounds + 6 * (size_t)i;
+        b[0] = nd->box.x1; b[1] = nd->box.y1; b[2] = nd->box.z1;
+        b[3] = nd->box.x2; b[4] = nd->box.y2; b[5] = nd->box.z2;
+    }
+}
+
+/* the loop of findCollisionsCpu (cpu.cuh:268-270) around the reference's
+ * findCollisionIterativeCpu, with a pair buffer that cannot overflow */
+REF_API uint64_t ref_collide(void* h) {
+    auto* m = static_cast<RefMesh*>(h);
+    const int n = (int)m->tris.size();
+    m->npairs = 0;
+    m->pairs.assign(1 << 20, 0u);
+    double t0 = now_ms();
+    for (int i = 0; i < n; ++i) {
+        if (m->pairs.size() / 2 - m->npairs < (size_t)n + 16) m->pairs.resize(m->pairs.size() * 2 + 2 * (size_t)n);
+        findCollisionIterativeCpu(&m->inner[0], m->leaves[i].triangle, &m->leaves[i].box, m->verts.data(),
+                                  &m->npairs, m->pairs.data());
+    }
+    m->ms_query = now_ms() - t0;
+    return m->npairs;
+}
+
+REF_API void ref_get_pairs(void* h, uint32_t* out) {
+    auto* m = static_cast<RefMesh*>(h);
+    memcpy(out, m->pairs.data(), (size_t)m->npairs * 8);
+}
+
+REF_API void ref_get_timing(void* h, double* ms5) {
+    auto* m = static_cast<RefMesh*>(h);
+    ms5[0] = m->ms_load; ms5[1] = m->ms_fill; ms5[2] = m->ms_hier; ms5[3] = m->ms_refit; ms5[4] = m->ms_query;
+}
+
+/* ---- unit hooks on the reference predicates ---- */
+REF_API uint64_t ref_morton3D(double x, double y, double z) { return morton3D(x, y, z); }
+
+REF_API int ref_tri_contact(const double* t) {
+    vec3f P1(t[0], t[1], t[2]), P2(t[3], t[4], t[5]), P3(t[6], t[7], t[8]);
+    vec3f Q1(t[9], t[10], t[11]), Q2(t[12], t[13], t[14]), Q3(t[15], t[16], t[17]);
+    return checkTriangleContact(P1, P2, P3, Q1, Q2, Q3);
+}
+
+/* boxes as lo xyz, hi xyz */
+REF_API int ref_box_overlap(const double* a, const double* b) {
+    Box A, B;
+    A.x1 = a[0]; A.y1 = a[1]; A.z1 = a[2]; A.x2 = a[3]; A.y2 = a[4]; A.z2 = a[5];
+    B.x1 = b[0]; B.y1 = b[1]; B.z1 = b[2]; B.x2 = b[3]; B.y2 = b[4]; B.z2 = b[5];
+    return checkBoxOverlap(&A, &B);
+}
+
+/* check.cuh:19-27 known-answer hook, host twins */
+REF_API void ref_range_split(const uint64_t* keys, int n, int i, int* out3) {
+    std::vector<unsigned long long> k(keys, keys + n);
+    Range r = determineRangeCpu(k.data(), n, i);
+    out3[0] = r.x; out3[1] = r.y;
+    out3[2] = findSplitCpu(k.data(), r.x, r.y);
+}
