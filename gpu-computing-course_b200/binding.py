@@ -1,0 +1,338 @@
+"""ctypes binding of libb200cd.so (include/b200cd.h) — the call a Python user makes.
+
+Mirrors the reference's entry-point sequence (reference CollisionDetection/main.cu:47-174):
+
+    ctx  = Context(device)                      # device 0 / default stream in main.cu
+    mesh = ctx.mesh_load_obj(path)              # loadObj, load_obj.h:24   (or mesh_from_arrays)
+    bvh  = ctx.bvh_build(mesh, params)          # Morton + sort + fillLeafNodes + hierarchy + refit
+    pairs = ctx.self_collide(bvh, sorted=True)  # findCollisions, collision.cuh:73 -> (count, 2) uint32
+
+There is no CPU fallback: if the library or a B200 is missing this module raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200cd.so")
+_LIB = None
+
+OK, E_INVALID, E_CUDA, E_NOMEM, E_IO, E_PARSE, E_CAPACITY, E_DEPTH, E_NODEVICE, E_TOOBIG = range(10)
+
+# every symbol include/b200cd.h declares (tests check the .so exports exactly these)
+SYMBOLS = [
+    "b200cd_create", "b200cd_destroy", "b200cd_set_stream", "b200cd_synchronize", "b200cd_get_stats",
+    "b200cd_strerror", "b200cd_last_error", "b200cd_abi_version", "b200cd_default_params", "b200cd_host_alloc",
+    "b200cd_host_free", "b200cd_mesh_load_obj", "b200cd_mesh_from_arrays", "b200cd_mesh_from_device",
+    "b200cd_mesh_update", "b200cd_mesh_info", "b200cd_mesh_download", "b200cd_mesh_destroy",
+    "b200cd_bvh_build", "b200cd_bvh_rebuild", "b200cd_bvh_refit", "b200cd_bvh_download", "b200cd_bvh_validate",
+    "b200cd_bvh_destroy", "b200cd_self_collide", "b200cd_self_collide_shard", "b200cd_self_collide_device",
+    "b200cd_sort_pairs_device", "b200cd_bvh_view_get", "b200cd_bvh_alloc_like",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("morton_origin", C.c_double * 3), ("morton_extent", C.c_double * 3), ("key_bits", C.c_int32),
+                ("auto_box", C.c_int32), ("pair_capacity_hint", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("ms_upload", "ms_morton", "ms_sort", "ms_hierarchy", "ms_refit", "ms_build",
+                                         "ms_traverse", "ms_narrow", "ms_pair_sort", "ms_query", "ms_download")] + \
+               [("ntris", C.c_uint32), ("nverts", C.c_uint32), ("candidates", C.c_uint64), ("pairs", C.c_uint64),
+                ("sort_passes", C.c_uint32), ("query_retries", C.c_uint32), ("kernel_launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Checks(C.Structure):
+    _fields_ = [(k, C.c_uint32) for k in ("null_parent_internal", "wrong_bound_count", "null_child",
+                                          "uninit_box_internal", "null_parent_leaf", "bad_triangle",
+                                          "uninit_box_leaf", "unsorted_keys", "box_not_enclosing")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class BvhView(C.Structure):
+    _fields_ = [("d_nodes", C.c_void_p), ("nodes_bytes", C.c_uint64), ("d_leaves", C.c_void_p),
+                ("leaves_bytes", C.c_uint64), ("d_ids", C.c_void_p), ("ids_bytes", C.c_uint64), ("ntris", C.c_uint32)]
+
+
+NODE32 = np.dtype([("lo", np.float32, 3), ("hi", np.float32, 3), ("left", np.int32), ("right", np.int32)])
+
+
+class B200cdError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        msg = lib().b200cd_strerror(status).decode()
+        super().__init__(f"{where}: {msg}" + (f" ({detail})" if detail else ""))
+
+
+def lib():
+    """Load libb200cd.so; fail loudly if it has not been built (no fallback path exists)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                               f"(make -C gpu-computing-course_b200/csrc). There is no CPU fallback.")
+        _LIB = C.CDLL(LIB_PATH)
+        _LIB.b200cd_strerror.restype = C.c_char_p
+        _LIB.b200cd_last_error.restype = C.c_char_p
+        _LIB.b200cd_last_error.argtypes = [C.c_void_p]
+    return _LIB
+
+
+def default_params(key_bits=63):
+    p = Params()
+    lib().b200cd_default_params(C.byref(p))
+    p.key_bits = key_bits
+    return p
+
+
+def make_params(origin=None, extent=None, key_bits=63, auto_box=False, pair_capacity_hint=0):
+    p = default_params(key_bits)
+    if origin is not None:
+        p.morton_origin[:] = list(origin)
+    if extent is not None:
+        p.morton_extent[:] = list(extent)
+    p.auto_box = 1 if auto_box else 0
+    p.pair_capacity_hint = pair_capacity_hint
+    return p
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Mesh:
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        nv, nt = C.c_uint32(), C.c_uint32()
+        lib().b200cd_mesh_info(self.h, C.byref(nv), C.byref(nt))
+        self.nverts, self.ntris = nv.value, nt.value
+
+    def update(self, xyz=None, idx=None):
+        """overwrite vertices and/or indices in place from host arrays (same sizes)"""
+        if xyz is not None:
+            xyz = np.ascontiguousarray(xyz, np.float32)
+            assert xyz.shape == (self.nverts, 3)
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, np.uint32)
+            assert idx.shape == (self.ntris, 3)
+        self.ctx._chk(lib().b200cd_mesh_update(self.ctx.h, self.h, _ptr(xyz, C.c_float) if xyz is not None else None,
+                                               _ptr(idx, C.c_uint32) if idx is not None else None, C.c_int(0)),
+                      "mesh_update")
+
+    def update_from_ptr(self, xyz_ptr, idx_ptr, on_device=False):
+        """raw pointers (pinned host buffers or device memory); either may be 0/None"""
+        self.ctx._chk(lib().b200cd_mesh_update(self.ctx.h, self.h, C.c_void_p(xyz_ptr or None),
+                                               C.c_void_p(idx_ptr or None), C.c_int(1 if on_device else 0)),
+                      "mesh_update")
+
+    def download(self):
+        xyz = np.empty((self.nverts, 3), np.float32)
+        idx = np.empty((self.ntris, 3), np.uint32)
+        self.ctx._chk(lib().b200cd_mesh_download(self.ctx.h, self.h, _ptr(xyz, C.c_float), _ptr(idx, C.c_uint32)), "mesh_download")
+        return xyz, idx
+
+    def destroy(self):
+        if self.h:
+            lib().b200cd_mesh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Bvh:
+    def __init__(self, ctx, handle, ntris):
+        self.ctx, self.h, self.ntris = ctx, handle, ntris
+
+    def download(self, nodes=True, keys=True, ids=True):
+        """parity hooks: (nodes[2n-1] NODE32, sorted_keys[n] u64, sorted_ids[n] u32)"""
+        n = self.ntris
+        a_nodes = np.empty(max(2 * n - 1, 0), NODE32) if nodes else None
+        a_keys = np.empty(n, np.uint64) if keys else None
+        a_ids = np.empty(n, np.uint32) if ids else None
+        self.ctx._chk(lib().b200cd_bvh_download(
+            self.ctx.h, self.h,
+            a_nodes.ctypes.data_as(C.c_void_p) if nodes else None,
+            _ptr(a_keys, C.c_uint64) if keys else None,
+            _ptr(a_ids, C.c_uint32) if ids else None), "bvh_download")
+        return a_nodes, a_keys, a_ids
+
+    def validate(self, mesh=None):
+        out = Checks()
+        self.ctx._chk(lib().b200cd_bvh_validate(self.ctx.h, self.h, mesh.h if mesh else None, C.byref(out)), "bvh_validate")
+        return out.as_dict()
+
+    def view(self):
+        v = BvhView()
+        self.ctx._chk(lib().b200cd_bvh_view_get(self.ctx.h, self.h, C.byref(v)), "bvh_view_get")
+        return v
+
+    def destroy(self):
+        if self.h:
+            lib().b200cd_bvh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU. Not thread-safe (same contract as the C ABI)."""
+
+    def __init__(self, device=0, stream=None):
+        self.h = C.c_void_p()
+        rc = lib().b200cd_create(C.c_int(device), C.byref(self.h))
+        if rc != OK:
+            self.h = None
+            raise B200cdError(rc, "b200cd_create")
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def _chk(self, rc, where):
+        if rc != OK:
+            raise B200cdError(rc, where, lib().b200cd_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_handle):
+        self._chk(lib().b200cd_set_stream(self.h, C.c_void_p(cuda_stream_handle)), "set_stream")
+
+    def synchronize(self):
+        self._chk(lib().b200cd_synchronize(self.h), "synchronize")
+
+    def stats(self):
+        s = Stats()
+        self._chk(lib().b200cd_get_stats(self.h, C.byref(s)), "get_stats")
+        return s.as_dict()
+
+    # ---- mesh in
+    def mesh_load_obj(self, path):
+        m = C.c_void_p()
+        self._chk(lib().b200cd_mesh_load_obj(self.h, os.fsencode(path), C.byref(m)), "mesh_load_obj")
+        return Mesh(self, m)
+
+    def mesh_from_arrays(self, xyz, idx):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, np.uint32).reshape(-1, 3)
+        m = C.c_void_p()
+        self._chk(lib().b200cd_mesh_from_arrays(self.h, _ptr(xyz, C.c_float), C.c_uint32(xyz.shape[0]),
+                                                _ptr(idx, C.c_uint32), C.c_uint32(idx.shape[0]), C.byref(m)),
+                  "mesh_from_arrays")
+        return Mesh(self, m)
+
+    def mesh_from_host_ptr(self, xyz_ptr, nverts, idx_ptr, ntris):
+        """raw host pointers (e.g. pinned buffers from host_alloc)"""
+        m = C.c_void_p()
+        self._chk(lib().b200cd_mesh_from_arrays(self.h, C.c_void_p(xyz_ptr), C.c_uint32(nverts), C.c_void_p(idx_ptr),
+                                                C.c_uint32(ntris), C.byref(m)), "mesh_from_arrays")
+        return Mesh(self, m)
+
+    def mesh_from_device(self, d_xyz_ptr, nverts, d_idx_ptr, ntris):
+        m = C.c_void_p()
+        self._chk(lib().b200cd_mesh_from_device(self.h, C.c_void_p(d_xyz_ptr), C.c_uint32(nverts),
+                                                C.c_void_p(d_idx_ptr), C.c_uint32(ntris), C.byref(m)),
+                  "mesh_from_device")
+        return Mesh(self, m)
+
+    # ---- build
+    def bvh_build(self, mesh, params=None):
+        params = params or default_params()
+        b = C.c_void_p()
+        self._chk(lib().b200cd_bvh_build(self.h, mesh.h, C.byref(params), C.byref(b)), "bvh_build")
+        return Bvh(self, b, mesh.ntris)
+
+    def bvh_rebuild(self, bvh, mesh, params=None):
+        params = params or default_params()
+        self._chk(lib().b200cd_bvh_rebuild(self.h, bvh.h, mesh.h, C.byref(params)), "bvh_rebuild")
+
+    def bvh_refit(self, bvh, mesh):
+        self._chk(lib().b200cd_bvh_refit(self.h, bvh.h, mesh.h), "bvh_refit")
+
+    def bvh_alloc_like(self, ntris):
+        b = C.c_void_p()
+        self._chk(lib().b200cd_bvh_alloc_like(self.h, C.c_uint32(ntris), C.byref(b)), "bvh_alloc_like")
+        return Bvh(self, b, ntris)
+
+    # ---- query
+    def self_collide(self, bvh, sorted=True, shard=0, nshards=1, chunk=0, cap=None):
+        """-> (count, 2) uint32 array, lower ID first. Grows the host buffer on E_CAPACITY."""
+        cnt = C.c_uint64()
+        if cap is None:
+            cap = 1 << 16
+        while True:
+            out = np.empty((cap, 2), np.uint32)
+            rc = lib().b200cd_self_collide_shard(self.h, bvh.h, C.c_uint32(shard), C.c_uint32(nshards),
+                                                 C.c_uint32(chunk), _ptr(out, C.c_uint32), C.c_uint64(cap),
+                                                 C.byref(cnt), C.c_int(1 if sorted else 0))
+            if rc == E_CAPACITY:
+                cap = int(cnt.value)
+                continue
+            self._chk(rc, "self_collide")
+            return out[:cnt.value]
+
+    def self_collide_into(self, bvh, out_ptr, cap, sorted=True, shard=0, nshards=1, chunk=0):
+        """result straight into a caller-owned host buffer (raw pointer); returns the pair count"""
+        cnt = C.c_uint64()
+        rc = lib().b200cd_self_collide_shard(self.h, bvh.h, C.c_uint32(shard), C.c_uint32(nshards), C.c_uint32(chunk),
+                                             C.c_void_p(out_ptr), C.c_uint64(cap), C.byref(cnt),
+                                             C.c_int(1 if sorted else 0))
+        self._chk(rc, "self_collide")
+        return int(cnt.value)
+
+    def self_collide_device(self, bvh, sorted=True, shard=0, nshards=1, chunk=0):
+        """-> (device pointer, count); the buffer is owned by the BVH until its next query"""
+        cnt = C.c_uint64()
+        ptr = C.c_void_p()
+        self._chk(lib().b200cd_self_collide_device(self.h, bvh.h, C.c_uint32(shard), C.c_uint32(nshards),
+                                                   C.c_uint32(chunk), C.c_int(1 if sorted else 0), C.byref(ptr),
+                                                   C.byref(cnt)), "self_collide_device")
+        return ptr.value, int(cnt.value)
+
+    def sort_pairs_device(self, d_ptr, count, id_bits=0):
+        self._chk(lib().b200cd_sort_pairs_device(self.h, C.c_void_p(d_ptr), C.c_uint64(count), C.c_uint32(id_bits)),
+                  "sort_pairs_device")
+
+    def destroy(self):
+        if self.h:
+            lib().b200cd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def host_alloc(nbytes):
+    p = C.c_void_p()
+    rc = lib().b200cd_host_alloc(C.byref(p), C.c_uint64(nbytes))
+    if rc != OK:
+        raise B200cdError(rc, "host_alloc")
+    return p.value
+
+
+def host_free(ptr):
+    lib().b200cd_host_free(C.c_void_p(ptr))
+
+
+def pinned_array(shape, dtype):
+    """numpy array over page-locked memory (kept alive by the returned object)"""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    ptr = host_alloc(max(n * dtype.itemsize, 1))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    return arr, ptr

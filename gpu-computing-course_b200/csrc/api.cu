@@ -1,0 +1,760 @@
+// api.cu — the C ABI of libb200cd.so (include/b200cd.h): contexts, meshes, the
+// build pipeline K1..K4 and the query pipeline K5..K6, error handling, stage timers.
+//
+// Host-side mirror of the reference driver main() (reference
+// CollisionDetection/main.cu:47-174): load -> alloc/H2D -> build stages -> query ->
+// D2H. Differences: handles instead of raw cudaMalloc'ed structs, status codes
+// instead of HANDLE_ERROR/exit (common/book.h:21-31), one stream with no
+// per-kernel cudaEventSynchronize (main.cu:93,100,109,143), buffers that grow
+// instead of the fixed 500-pair list (main.cu:81).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace b200cd;
+
+#define API extern "C" __attribute__((visibility("default")))
+
+namespace b200cd {
+unsigned long long g_kernel_launches = 0;
+}
+
+namespace {
+
+enum Ev { EV_B0, EV_B1, EV_B2, EV_B3, EV_B4, EV_Q0, EV_Q1, EV_Q2, EV_Q3, EV_U0, EV_U1, EV_D0, EV_D1, EV_COUNT };
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+float ev_ms(b200cd_ctx* ctx, int a, int b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+template <typename T>
+int dev_alloc(b200cd_ctx* ctx, T** p, uint64_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+    return B200CD_OK;
+}
+
+void free_bvh_buffers(b200cd_bvh* b) {
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(b->d_keys[i]);
+        cudaFree(b->d_ids[i]);
+    }
+    cudaFree(b->d_hist);
+    cudaFree(b->d_tile_status);
+    cudaFree(b->d_parent);
+    cudaFree(b->d_flags);
+    cudaFree(b->d_pairs);
+    cudaFree(b->d_leaves);
+    cudaFree(b->d_root_box);
+    cudaFree(b->d_cand);
+    cudaFree(b->d_out);
+    cudaFree(b->d_out_tmp);
+    cudaFree(b->d_counters);
+    if (b->h_counters) cudaFreeHost(b->h_counters);
+}
+
+int id_bits_for(uint32_t n) {
+    int b = 1;
+    while (b < 32 && (n - 1) >> b) ++b;
+    return n <= 1 ? 1 : b;
+}
+
+int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200cd_bvh** out) {
+    b200cd_bvh* b = new (std::nothrow) b200cd_bvh;
+    if (!b) return set_error(ctx, B200CD_E_NOMEM, "host allocation failed");
+    b->ctx = ctx;
+    b->n = n;
+    b->nverts = nverts;
+    int rc = B200CD_OK;
+    auto A = [&](int r) { if (rc == B200CD_OK) rc = r; };
+    if (with_sort) {
+        A(dev_alloc(ctx, &b->d_keys[0], n));
+        A(dev_alloc(ctx, &b->d_keys[1], n));
+        A(dev_alloc(ctx, &b->d_ids[1], n));
+        A(dev_alloc(ctx, &b->d_parent, 2ull * n));
+        A(dev_alloc(ctx, &b->d_flags, n));
+    }
+    A(dev_alloc(ctx, &b->d_ids[0], n));
+    // radix scratch is sized for the larger of the key sort and an n-pair result sort; grown on demand
+    b->tile_status_words = radix_tile_status_words(std::max<uint32_t>(n, 1u), 8);
+    A(dev_alloc(ctx, &b->d_hist, radix_hist_words(8)));
+    A(dev_alloc(ctx, &b->d_tile_status, b->tile_status_words));
+    A(dev_alloc(ctx, &b->d_pairs, n));
+    A(dev_alloc(ctx, &b->d_leaves, n));
+    A(dev_alloc(ctx, &b->d_root_box, 8));
+    A(dev_alloc(ctx, &b->d_counters, 4));
+    if (rc == B200CD_OK && cudaMallocHost(reinterpret_cast<void**>(&b->h_counters), 4 * sizeof(unsigned long long)) != cudaSuccess)
+        rc = set_error(ctx, B200CD_E_NOMEM, "cudaMallocHost failed");
+    if (rc != B200CD_OK) {
+        free_bvh_buffers(b);
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return B200CD_OK;
+}
+
+int check_params(b200cd_ctx* ctx, const b200cd_params* p) {
+    if (!p) return set_error(ctx, B200CD_E_INVALID, "params is NULL");
+    if (p->key_bits != 63 && p->key_bits != 30) return set_error(ctx, B200CD_E_INVALID, "key_bits must be 63 or 30");
+    if (!p->auto_box)
+        for (int a = 0; a < 3; ++a)
+            if (!(p->morton_extent[a] > 0.0)) return set_error(ctx, B200CD_E_INVALID, "morton_extent must be > 0");
+    return B200CD_OK;
+}
+
+int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd_params* p) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = b->n;
+    b->params = *p;
+    b->built = false;
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
+    int npass = 0;
+    if (n) {
+        // K1
+        uint32_t* d_bbox = nullptr;
+        if (p->auto_box) {
+            d_bbox = ctx->d_scalars;
+            launch_bbox(m->d_verts, m->nverts, d_bbox, ctx->sm_count, s);
+        }
+        launch_morton(m->d_verts, m->d_idx, n, *p, d_bbox, b->d_keys[0], s);
+    }
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
+    if (n) {
+        // K2: 8-bit digits over the significant key bits (60 of 63: morton.h:15 masks 21 bits
+        // per axis but the 2^20 scale leaves bit 20 clear for in-box meshes; we still sort all
+        // 63 so out-of-box meshes order exactly like the host sort)
+        RadixPass passes[8];
+        const int total_bits = (p->key_bits == 30) ? 30 : 63;
+        for (int sh = 0; sh < total_bits; sh += 8) passes[npass++] = {sh, std::min(8, total_bits - sh)};
+        b->cur = radix_sort(b->d_keys, b->d_ids, n, passes, npass, /*iota*/ true, b->d_hist, b->d_tile_status,
+                            b->tile_status_words, ctx->sm_count, s);
+    }
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
+    launch_hierarchy(b->d_keys[b->cur], n, b->d_parent, s);  // K3
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));
+    launch_refit(m->d_verts, m->d_idx, b->d_ids[b->cur], n, b->d_parent, b->d_flags, b->d_pairs, b->d_leaves,
+                 b->d_root_box, s);  // K4
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
+    CD_CUDA(ctx, cudaGetLastError());
+    ctx->stats.sort_passes = (uint32_t)npass;
+    ctx->stats.ntris = n;
+    ctx->stats.nverts = m->nverts;
+    ctx->stats.ms_build = -1.f;  // resolved lazily by b200cd_get_stats (build is asynchronous)
+    b->built = true;
+    return B200CD_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ context
+
+API int b200cd_abi_version(void) { return B200CD_ABI_VERSION; }
+
+API const char* b200cd_strerror(int status) {
+    switch (status) {
+        case B200CD_OK: return "ok";
+        case B200CD_E_INVALID: return "invalid argument";
+        case B200CD_E_CUDA: return "CUDA runtime error";
+        case B200CD_E_NOMEM: return "out of memory";
+        case B200CD_E_IO: return "file could not be read";
+        case B200CD_E_PARSE: return "OBJ line not in the accepted dialect";
+        case B200CD_E_CAPACITY: return "pair buffer too small";
+        case B200CD_E_DEPTH: return "BVH traversal stack exhausted";
+        case B200CD_E_NODEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+        case B200CD_E_TOOBIG: return "mesh too large";
+        default: return "unknown status";
+    }
+}
+
+API const char* b200cd_last_error(const b200cd_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+API int b200cd_create(int device, b200cd_ctx** out) {
+    if (!out) return B200CD_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return B200CD_E_NODEVICE;
+    }
+    if (device < 0 || device >= ndev) return B200CD_E_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B200CD_E_CUDA;
+    if (prop.major != 10) return B200CD_E_NODEVICE;  // the only code in this library is sm_100a SASS
+    b200cd_ctx* ctx = new (std::nothrow) b200cd_ctx;
+    if (!ctx) return B200CD_E_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    DeviceGuard g(device);
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < EV_COUNT; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&ctx->d_scalars), 64 * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), 64 * sizeof(uint32_t)) == cudaSuccess;
+    if (!ok) {
+        b200cd_destroy(ctx);
+        return B200CD_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return B200CD_OK;
+}
+
+API int b200cd_destroy(b200cd_ctx* ctx) {
+    if (!ctx) return B200CD_OK;
+    DeviceGuard g(ctx->device);
+    if (ctx->own_stream) {
+        cudaStreamSynchronize(ctx->own_stream);
+        cudaStreamDestroy(ctx->own_stream);
+    }
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    cudaFree(ctx->d_scalars);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    delete ctx;
+    return B200CD_OK;
+}
+
+API int b200cd_set_stream(b200cd_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return B200CD_E_INVALID;
+    DeviceGuard g(ctx->device);
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return B200CD_OK;
+}
+
+API int b200cd_synchronize(b200cd_ctx* ctx) {
+    if (!ctx) return B200CD_E_INVALID;
+    DeviceGuard g(ctx->device);
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200CD_OK;
+}
+
+API int b200cd_get_stats(const b200cd_ctx* cctx, b200cd_stats* out) {
+    if (!cctx || !out) return B200CD_E_INVALID;
+    b200cd_ctx* ctx = const_cast<b200cd_ctx*>(cctx);
+    DeviceGuard g(ctx->device);
+    if (ctx->stats.ms_build < 0.f) {
+        CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.ms_morton = ev_ms(ctx, EV_B0, EV_B1);
+        ctx->stats.ms_sort = ev_ms(ctx, EV_B1, EV_B2);
+        ctx->stats.ms_hierarchy = ev_ms(ctx, EV_B2, EV_B3);
+        ctx->stats.ms_refit = ev_ms(ctx, EV_B3, EV_B4);
+        ctx->stats.ms_build = ev_ms(ctx, EV_B0, EV_B4);
+    }
+    ctx->stats.kernel_launches = g_kernel_launches;
+    *out = ctx->stats;
+    return B200CD_OK;
+}
+
+API void b200cd_default_params(b200cd_params* p) {
+    if (!p) return;
+    // reference morton.h:45,51,57
+    p->morton_origin[0] = 0.004501;  p->morton_extent[0] = 3.08;
+    p->morton_origin[1] = -0.476622; p->morton_extent[1] = 0.76;
+    p->morton_origin[2] = -0.381965; p->morton_extent[2] = 2.36;
+    p->key_bits = 63;
+    p->auto_box = 0;
+    p->pair_capacity_hint = 0;
+}
+
+API int b200cd_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return B200CD_E_INVALID;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? B200CD_OK : B200CD_E_NOMEM;
+}
+API int b200cd_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? B200CD_OK : B200CD_E_CUDA; }
+
+// ------------------------------------------------------------------ mesh
+
+namespace {
+int new_mesh(b200cd_ctx* ctx, uint32_t nverts, uint32_t ntris, b200cd_mesh** out) {
+    if (nverts > (1u << 30) || ntris > (1u << 30)) return set_error(ctx, B200CD_E_TOOBIG, "more than 2^30 vertices or triangles");
+    b200cd_mesh* m = new (std::nothrow) b200cd_mesh;
+    if (!m) return set_error(ctx, B200CD_E_NOMEM, "host allocation failed");
+    m->ctx = ctx;
+    m->nverts = nverts;
+    m->ntris = ntris;
+    int rc = dev_alloc(ctx, &m->d_verts, nverts);
+    if (rc == B200CD_OK) rc = dev_alloc(ctx, &m->d_idx, 3ull * ntris);
+    if (rc != B200CD_OK) {
+        cudaFree(m->d_verts);
+        cudaFree(m->d_idx);
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return B200CD_OK;
+}
+
+int upload(b200cd_ctx* ctx, b200cd_mesh* m, const float* xyz, const uint32_t* idx, bool on_device) {
+    cudaStream_t s = ctx->stream;
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_U0], s));
+    if (xyz && m->nverts) {
+        const float* src = xyz;
+        float* staging = nullptr;
+        if (!on_device) {
+            CD_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&staging), 12ull * m->nverts, s));
+            CD_CUDA(ctx, cudaMemcpyAsync(staging, xyz, 12ull * m->nverts, cudaMemcpyHostToDevice, s));
+            src = staging;
+        }
+        launch_expand_verts(src, m->d_verts, m->nverts, s);
+        if (staging) CD_CUDA(ctx, cudaFreeAsync(staging, s));
+    }
+    if (idx && m->ntris)
+        CD_CUDA(ctx, cudaMemcpyAsync(m->d_idx, idx, 12ull * m->ntris, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (idx) {  // every index must name an existing vertex (the reference only prints a warning, load_obj.h:77-79)
+        launch_check_idx(m->d_idx, m->ntris, m->nverts, ctx->d_scalars + 32, ctx->sm_count, s);
+        CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 32, ctx->d_scalars + 32, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_U1], s));
+    CD_CUDA(ctx, cudaStreamSynchronize(s));  // the caller may free / reuse its buffers on return
+    CD_CUDA(ctx, cudaGetLastError());
+    ctx->stats.ms_upload = ev_ms(ctx, EV_U0, EV_U1);
+    if (idx && ctx->h_scalars[32]) return set_error(ctx, B200CD_E_INVALID, "triangle references a vertex index >= nverts");
+    return B200CD_OK;
+}
+}  // namespace
+
+API int b200cd_mesh_from_arrays(b200cd_ctx* ctx, const float* xyz, uint32_t nverts, const uint32_t* tri_idx,
+                                uint32_t ntris, b200cd_mesh** out) {
+    if (!ctx || !out || (nverts && !xyz) || (ntris && !tri_idx)) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    b200cd_mesh* m = nullptr;
+    int rc = new_mesh(ctx, nverts, ntris, &m);
+    if (rc != B200CD_OK) return rc;
+    rc = upload(ctx, m, xyz, tri_idx, false);
+    if (rc != B200CD_OK) {
+        b200cd_mesh_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return B200CD_OK;
+}
+
+API int b200cd_mesh_from_device(b200cd_ctx* ctx, const void* d_xyz, uint32_t nverts, const void* d_tri_idx,
+                                uint32_t ntris, b200cd_mesh** out) {
+    if (!ctx || !out || (nverts && !d_xyz) || (ntris && !d_tri_idx)) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    b200cd_mesh* m = nullptr;
+    int rc = new_mesh(ctx, nverts, ntris, &m);
+    if (rc != B200CD_OK) return rc;
+    rc = upload(ctx, m, static_cast<const float*>(d_xyz), static_cast<const uint32_t*>(d_tri_idx), true);
+    if (rc != B200CD_OK) {
+        b200cd_mesh_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return B200CD_OK;
+}
+
+API int b200cd_mesh_update(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, const uint32_t* tri_idx, int on_device) {
+    if (!ctx || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    DeviceGuard g(ctx->device);
+    return upload(ctx, mesh, xyz, tri_idx, on_device != 0);
+}
+
+API int b200cd_mesh_info(const b200cd_mesh* mesh, uint32_t* nverts, uint32_t* ntris) {
+    if (!mesh) return B200CD_E_INVALID;
+    if (nverts) *nverts = mesh->nverts;
+    if (ntris) *ntris = mesh->ntris;
+    return B200CD_OK;
+}
+
+API int b200cd_mesh_download(b200cd_ctx* ctx, const b200cd_mesh* mesh, float* xyz, uint32_t* tri_idx) {
+    if (!ctx || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    DeviceGuard g(ctx->device);
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (xyz && mesh->nverts) {
+        std::vector<float4> tmp(mesh->nverts);
+        CD_CUDA(ctx, cudaMemcpy(tmp.data(), mesh->d_verts, sizeof(float4) * mesh->nverts, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < mesh->nverts; ++i) {
+            xyz[3 * (size_t)i] = tmp[i].x; xyz[3 * (size_t)i + 1] = tmp[i].y; xyz[3 * (size_t)i + 2] = tmp[i].z;
+        }
+    }
+    if (tri_idx && mesh->ntris)
+        CD_CUDA(ctx, cudaMemcpy(tri_idx, mesh->d_idx, 12ull * mesh->ntris, cudaMemcpyDeviceToHost));
+    return B200CD_OK;
+}
+
+API int b200cd_mesh_destroy(b200cd_mesh* mesh) {
+    if (!mesh) return B200CD_OK;
+    DeviceGuard g(mesh->ctx->device);
+    cudaStreamSynchronize(mesh->ctx->stream);
+    cudaFree(mesh->d_verts);
+    cudaFree(mesh->d_idx);
+    delete mesh;
+    return B200CD_OK;
+}
+
+// OBJ ingest with the reference parser's dialect (load_obj.h:41-103).
+API int b200cd_mesh_load_obj(b200cd_ctx* ctx, const char* path, b200cd_mesh** out) {
+    if (!ctx || !path || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    *out = nullptr;
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return set_error(ctx, B200CD_E_IO, std::string("cannot open ") + path);  // load_obj.h:31-35
+    std::vector<char> text;
+    {
+        char chunk[1 << 16];
+        size_t got;
+        while ((got = fread(chunk, 1, sizeof chunk, fp)) > 0) text.insert(text.end(), chunk, chunk + got);
+        bool bad = ferror(fp) != 0;
+        fclose(fp);
+        if (bad) return set_error(ctx, B200CD_E_IO, std::string("read error on ") + path);
+    }
+    std::vector<float> xyz;
+    std::vector<uint32_t> idx;
+    size_t pos = 0, line_no = 0;
+    char buffer[256];
+    while (pos < text.size()) {
+        const char* nl = static_cast<const char*>(memchr(text.data() + pos, '\n', text.size() - pos));
+        if (!nl) break;  // last line without '\n' is dropped: load_obj.h:41 tests eof() after getline
+        size_t len = (size_t)(nl - (text.data() + pos));
+        ++line_no;
+        if (len >= 255)  // getline(buffer, 255) would set failbit and the reference never terminates
+            return set_error(ctx, B200CD_E_PARSE, "line " + std::to_string(line_no) + ": longer than 254 characters");
+        memcpy(buffer, text.data() + pos, len);
+        buffer[len] = '\0';
+        pos += len + 1;
+        if (buffer[0] == 'v' && buffer[1] == ' ') {  // load_obj.h:48-61
+            float f1, f2, f3;
+            if (sscanf(buffer, "v %f %f %f", &f1, &f2, &f3) != 3)
+                return set_error(ctx, B200CD_E_PARSE, "line " + std::to_string(line_no) + ": vertex not in 'v x y z' format");
+            xyz.push_back(f1); xyz.push_back(f2); xyz.push_back(f3);
+        } else if (buffer[0] == 'f' && buffer[1] == ' ') {  // load_obj.h:64-102
+            int v1, v2, v3, t1, t2, t3;
+            if (sscanf(buffer, "f %d/%d %d/%d %d/%d", &v1, &t1, &v2, &t2, &v3, &t3) != 6)
+                return set_error(ctx, B200CD_E_PARSE, "line " + std::to_string(line_no) + ": face not in 'f v/vt v/vt v/vt' format");
+            const int v_size = (int)(xyz.size() / 3) + 1;  // load_obj.h:76-79; faces must follow their vertices (:89)
+            if (v1 < 1 || v2 < 1 || v3 < 1 || v1 >= v_size || v2 >= v_size || v3 >= v_size)
+                return set_error(ctx, B200CD_E_PARSE, "line " + std::to_string(line_no) + ": face references a vertex not yet defined");
+            idx.push_back((uint32_t)(v1 - 1)); idx.push_back((uint32_t)(v2 - 1)); idx.push_back((uint32_t)(v3 - 1));
+        }
+    }
+    return b200cd_mesh_from_arrays(ctx, xyz.data(), (uint32_t)(xyz.size() / 3), idx.data(), (uint32_t)(idx.size() / 3), out);
+}
+
+// ------------------------------------------------------------------ build
+
+API int b200cd_bvh_build(b200cd_ctx* ctx, const b200cd_mesh* mesh, const b200cd_params* params, b200cd_bvh** out) {
+    if (!ctx || !mesh || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    *out = nullptr;
+    int rc = check_params(ctx, params);
+    if (rc != B200CD_OK) return rc;
+    DeviceGuard g(ctx->device);
+    b200cd_bvh* b = nullptr;
+    rc = alloc_bvh(ctx, mesh->ntris, mesh->nverts, true, &b);
+    if (rc != B200CD_OK) return rc;
+    rc = run_build(ctx, b, mesh, params);
+    if (rc != B200CD_OK) {
+        b200cd_bvh_destroy(b);
+        return rc;
+    }
+    *out = b;
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_rebuild(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh, const b200cd_params* params) {
+    if (!ctx || !bvh || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (bvh->n != mesh->ntris || !bvh->d_keys[0]) return set_error(ctx, B200CD_E_INVALID, "BVH was not built for a mesh of this size");
+    int rc = check_params(ctx, params);
+    if (rc != B200CD_OK) return rc;
+    DeviceGuard g(ctx->device);
+    bvh->nverts = mesh->nverts;
+    return run_build(ctx, bvh, mesh, params);
+}
+
+API int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh) {
+    if (!ctx || !bvh || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (!bvh->built || bvh->n != mesh->ntris || !bvh->d_parent) return set_error(ctx, B200CD_E_INVALID, "BVH not built for this mesh");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));
+    launch_refit(mesh->d_verts, mesh->d_idx, bvh->d_ids[bvh->cur], bvh->n, bvh->d_parent, bvh->d_flags, bvh->d_pairs,
+                 bvh->d_leaves, bvh->d_root_box, s);
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
+    CD_CUDA(ctx, cudaGetLastError());
+    ctx->stats.ms_build = -1.f;
+    ctx->stats.sort_passes = 0;
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_download(b200cd_ctx* ctx, const b200cd_bvh* bvh, b200cd_node32* nodes, uint64_t* sorted_keys,
+                            uint32_t* sorted_ids) {
+    if (!ctx || !bvh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (!bvh->built) return set_error(ctx, B200CD_E_INVALID, "BVH not built");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = bvh->n;
+    if (!n) return B200CD_OK;
+    if (nodes) {
+        b200cd_node32* d_nodes = nullptr;
+        const uint64_t cnt = 2ull * n - 1;
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_nodes), cnt * sizeof(b200cd_node32)));
+        cudaMemsetAsync(d_nodes, 0xff, cnt * sizeof(b200cd_node32), s);
+        launch_export_nodes(bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, n, d_nodes, s);
+        cudaError_t e = cudaMemcpyAsync(nodes, d_nodes, cnt * sizeof(b200cd_node32), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_nodes);
+        CD_CUDA(ctx, e);
+    }
+    if (sorted_keys) {
+        if (!bvh->d_keys[0]) return set_error(ctx, B200CD_E_INVALID, "this BVH was received, not built: no keys");
+        CD_CUDA(ctx, cudaMemcpyAsync(sorted_keys, bvh->d_keys[bvh->cur], 8ull * n, cudaMemcpyDeviceToHost, s));
+    }
+    if (sorted_ids) CD_CUDA(ctx, cudaMemcpyAsync(sorted_ids, bvh->d_ids[bvh->cur], 4ull * n, cudaMemcpyDeviceToHost, s));
+    CD_CUDA(ctx, cudaStreamSynchronize(s));
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_validate(b200cd_ctx* ctx, const b200cd_bvh* bvh, const b200cd_mesh* mesh, b200cd_checks* out) {
+    if (!ctx || !bvh || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (!bvh->built || !bvh->d_parent) return set_error(ctx, B200CD_E_INVALID, "BVH not built on this context");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    uint32_t* d_chk = ctx->d_scalars + 16;
+    launch_validate(bvh->d_pairs, bvh->d_leaves, bvh->d_parent, bvh->d_flags, bvh->d_keys[bvh->cur], bvh->n,
+                    mesh ? mesh->nverts : bvh->nverts, d_chk, s);
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 16, d_chk, 9 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CD_CUDA(ctx, cudaStreamSynchronize(s));
+    CD_CUDA(ctx, cudaGetLastError());
+    memcpy(out, ctx->h_scalars + 16, 9 * sizeof(uint32_t));
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_destroy(b200cd_bvh* bvh) {
+    if (!bvh) return B200CD_OK;
+    DeviceGuard g(bvh->ctx->device);
+    cudaStreamSynchronize(bvh->ctx->stream);
+    free_bvh_buffers(bvh);
+    delete bvh;
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_view_get(b200cd_ctx* ctx, b200cd_bvh* bvh, b200cd_bvh_view* out) {
+    if (!ctx || !bvh || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    out->d_nodes = bvh->d_pairs;   out->nodes_bytes = bvh->n > 1 ? sizeof(NodePair) * (uint64_t)(bvh->n - 1) : 0;
+    out->d_leaves = bvh->d_leaves; out->leaves_bytes = sizeof(LeafRec) * (uint64_t)bvh->n;
+    out->d_ids = bvh->d_ids[bvh->cur]; out->ids_bytes = 4ull * bvh->n;
+    out->ntris = bvh->n;
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_alloc_like(b200cd_ctx* ctx, uint32_t ntris, b200cd_bvh** out) {
+    if (!ctx || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    b200cd_bvh* b = nullptr;
+    int rc = alloc_bvh(ctx, ntris, 0, false, &b);
+    if (rc != B200CD_OK) return rc;
+    b->built = true;  // contents arrive through the device views
+    b->cur = 0;
+    *out = b;
+    return B200CD_OK;
+}
+
+// ------------------------------------------------------------------ query
+
+namespace {
+
+int grow(b200cd_ctx* ctx, uint2** buf, uint64_t* cap, uint64_t want) {
+    if (*cap >= want && *buf) return B200CD_OK;
+    cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(buf), std::max<uint64_t>(want, 1) * sizeof(uint2)));
+    *cap = want;
+    return B200CD_OK;
+}
+
+int sort_pairs_impl(b200cd_ctx* ctx, uint2** d_pairs, uint2** d_tmp, uint64_t count, int id_bits, uint32_t** d_hist,
+                    uint32_t** d_status, uint64_t* status_words, cudaStream_t s) {
+    if (count < 2) return B200CD_OK;
+    if (count >= (1ull << 30)) return set_error(ctx, B200CD_E_TOOBIG, "pair list too long to sort");
+    // memory word of a pair {lo_id, hi_id} read as u64 = hi_id << 32 | lo_id: LSD order = hi_id digits, then lo_id digits
+    RadixPass passes[8];
+    int np = 0;
+    for (int sh = 0; sh < id_bits; sh += 8) passes[np++] = {32 + sh, std::min(8, id_bits - sh)};
+    for (int sh = 0; sh < id_bits; sh += 8) passes[np++] = {sh, std::min(8, id_bits - sh)};
+    uint64_t need = radix_tile_status_words((uint32_t)count, np);
+    if (need > *status_words) {
+        cudaFree(*d_status);
+        *d_status = nullptr;
+        *status_words = 0;
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(d_status), need * sizeof(uint32_t)));
+        *status_words = need;
+    }
+    uint64_t* keys[2] = {reinterpret_cast<uint64_t*>(*d_pairs), reinterpret_cast<uint64_t*>(*d_tmp)};
+    int cur = radix_sort(keys, nullptr, (uint32_t)count, passes, np, false, *d_hist, *d_status, *status_words,
+                         ctx->sm_count, s);
+    if (cur == 1) std::swap(*d_pairs, *d_tmp);
+    return B200CD_OK;
+}
+
+int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, uint32_t chunk, int sorted,
+              uint64_t* count_out) {
+    if (!b->built) return set_error(ctx, B200CD_E_INVALID, "BVH not built");
+    if (nshards == 0 || shard >= nshards) return set_error(ctx, B200CD_E_INVALID, "shard must be < nshards");
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = b->n;
+    ctx->stats.query_retries = 0;
+    ctx->stats.candidates = ctx->stats.pairs = 0;
+    *count_out = 0;
+    if (n < 2) {
+        CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q0], s));
+        for (int e : {EV_Q1, EV_Q2, EV_Q3}) CD_CUDA(ctx, cudaEventRecord(ctx->ev[e], s));
+        CD_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->stats.ms_traverse = ctx->stats.ms_narrow = ctx->stats.ms_pair_sort = ctx->stats.ms_query = 0.f;
+        return B200CD_OK;
+    }
+    // query threads of this shard: whole chunks c = shard, shard + nshards, ...
+    if (chunk == 0) chunk = (n + nshards - 1) / nshards;
+    const uint64_t nchunks = ((uint64_t)n + chunk - 1) / chunk;
+    const uint64_t my_chunks = nchunks > shard ? (nchunks - shard + nshards - 1) / nshards : 0;
+    const uint64_t nquery64 = my_chunks * chunk;
+    if (nquery64 > 0xffffffffull) return set_error(ctx, B200CD_E_INVALID, "chunk too large");
+    const uint32_t nquery = (uint32_t)nquery64;
+
+    const uint64_t hint = b->params.pair_capacity_hint;
+    int rc = grow(ctx, &b->d_cand, &b->cand_cap, std::max<uint64_t>(b->cand_cap, std::max<uint64_t>(4ull * nquery + 4096, 4 * hint)));
+    if (rc == B200CD_OK) rc = grow(ctx, &b->d_out, &b->out_cap, std::max<uint64_t>(b->out_cap, std::max<uint64_t>(nquery / 2 + 4096, hint)));
+    if (rc == B200CD_OK && sorted) rc = grow(ctx, &b->d_out_tmp, &b->out_tmp_cap, b->out_cap);
+    if (rc != B200CD_OK) return rc;
+
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q0], s));
+    bool need_broad = true;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (need_broad) {
+            CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(unsigned long long), s));
+            launch_broad(b->d_pairs, b->d_leaves, n, shard, nshards, chunk, nquery, b->d_cand, b->cand_cap, b->d_counters, s);
+            CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
+        } else {
+            CD_CUDA(ctx, cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), s));
+        }
+        launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s);
+        CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q2], s));
+        CD_CUDA(ctx, cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CD_CUDA(ctx, cudaStreamSynchronize(s));
+        CD_CUDA(ctx, cudaGetLastError());
+        const uint64_t ncand = b->h_counters[0], npair = b->h_counters[1];
+        if (b->h_counters[2] & 1ull)
+            return set_error(ctx, B200CD_E_DEPTH, "traversal stack of " + std::to_string(B200CD_MAX_STACK) + " entries exhausted");
+        if (ncand > b->cand_cap) {  // candidate list overflowed: grow to the exact need and redo the traversal
+            rc = grow(ctx, &b->d_cand, &b->cand_cap, ncand + ncand / 16);
+            if (rc != B200CD_OK) return rc;
+            need_broad = true;
+            ctx->stats.query_retries++;
+            continue;
+        }
+        if (npair > b->out_cap) {  // result list overflowed: candidates are intact, redo the narrow phase only
+            rc = grow(ctx, &b->d_out, &b->out_cap, npair + npair / 16);
+            if (rc != B200CD_OK) return rc;
+            need_broad = false;
+            ctx->stats.query_retries++;
+            continue;
+        }
+        ctx->stats.candidates = ncand;
+        ctx->stats.pairs = npair;
+        *count_out = npair;
+        if (sorted && npair > 1) {
+            rc = grow(ctx, &b->d_out_tmp, &b->out_tmp_cap, b->out_cap);
+            if (rc != B200CD_OK) return rc;
+            rc = sort_pairs_impl(ctx, &b->d_out, &b->d_out_tmp, npair, id_bits_for(n), &b->d_hist, &b->d_tile_status,
+                                 &b->tile_status_words, s);
+            if (rc != B200CD_OK) return rc;
+        }
+        CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q3], s));
+        CD_CUDA(ctx, cudaStreamSynchronize(s));
+        CD_CUDA(ctx, cudaGetLastError());
+        ctx->stats.ms_traverse = ev_ms(ctx, EV_Q0, EV_Q1);
+        ctx->stats.ms_narrow = ev_ms(ctx, EV_Q1, EV_Q2);
+        ctx->stats.ms_pair_sort = ev_ms(ctx, EV_Q2, EV_Q3);
+        ctx->stats.ms_query = ev_ms(ctx, EV_Q0, EV_Q3);
+        return B200CD_OK;
+    }
+    return set_error(ctx, B200CD_E_CUDA, "query did not converge after growing its buffers");
+}
+
+}  // namespace
+
+API int b200cd_self_collide_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t shard, uint32_t nshards, uint32_t chunk,
+                                   int sorted, const void** d_pairs_out, uint64_t* count_out) {
+    if (!ctx || !bvh || !count_out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    DeviceGuard g(ctx->device);
+    int rc = run_query(ctx, bvh, shard, nshards, chunk, sorted, count_out);
+    if (d_pairs_out) *d_pairs_out = (rc == B200CD_OK) ? bvh->d_out : nullptr;
+    return rc;
+}
+
+API int b200cd_self_collide_shard(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t shard, uint32_t nshards, uint32_t chunk,
+                                  uint32_t* pairs_out, uint64_t cap, uint64_t* count_out, int sorted) {
+    if (!ctx || !bvh || !count_out || (cap && !pairs_out)) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    DeviceGuard g(ctx->device);
+    int rc = run_query(ctx, bvh, shard, nshards, chunk, sorted, count_out);
+    if (rc != B200CD_OK) return rc;
+    if (*count_out > cap) return set_error(ctx, B200CD_E_CAPACITY, "pair buffer holds " + std::to_string(cap) + ", need " + std::to_string(*count_out));
+    cudaStream_t s = ctx->stream;
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_D0], s));
+    if (*count_out) CD_CUDA(ctx, cudaMemcpyAsync(pairs_out, bvh->d_out, *count_out * sizeof(uint2), cudaMemcpyDeviceToHost, s));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_D1], s));
+    CD_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->stats.ms_download = ev_ms(ctx, EV_D0, EV_D1);
+    return B200CD_OK;
+}
+
+API int b200cd_self_collide(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t* pairs_out, uint64_t cap, uint64_t* count_out,
+                            int sorted) {
+    return b200cd_self_collide_shard(ctx, bvh, 0, 1, 0, pairs_out, cap, count_out, sorted);
+}
+
+API int b200cd_sort_pairs_device(b200cd_ctx* ctx, void* d_pairs, uint64_t count, uint32_t id_bits) {
+    if (!ctx || (count && !d_pairs)) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (id_bits == 0 || id_bits > 32) id_bits = 32;
+    if (count < 2) return B200CD_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    uint2* tmp = nullptr;
+    uint32_t* hist = nullptr;
+    uint32_t* status = nullptr;
+    uint64_t status_words = 0;
+    CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&tmp), count * sizeof(uint2)));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&hist), radix_hist_words(8) * sizeof(uint32_t));
+    int rc = B200CD_OK;
+    if (e != cudaSuccess) rc = set_error(ctx, B200CD_E_NOMEM, "cudaMalloc failed");
+    uint2* p = static_cast<uint2*>(d_pairs);
+    uint2* q = tmp;
+    if (rc == B200CD_OK) rc = sort_pairs_impl(ctx, &p, &q, count, (int)id_bits, &hist, &status, &status_words, s);
+    if (rc == B200CD_OK && p != d_pairs)  // result landed in the temporary: copy back in place
+        if (cudaMemcpyAsync(d_pairs, p, count * sizeof(uint2), cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = B200CD_E_CUDA;
+    cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    cudaFree(hist);
+    cudaFree(status);
+    return rc;
+}

@@ -1,0 +1,147 @@
+// common.cuh — internal types shared by the kernels and the C-ABI host code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "b200cd.h"
+
+#define B200CD_MAX_STACK 96  // traversal stack entries per query (tree depth <= 60 key bits + tie-break)
+
+namespace b200cd {
+
+// ---------------------------------------------------------------- device data layout
+//
+// Traversal node: one child of an internal node. The two children of internal
+// node p sit side by side in pairs[p] (64 B, one aligned fetch gives both boxes,
+// both links and both range ends).
+//   link >= 0 : child is internal node `link`  (visit pairs[link] next)
+//   link <  0 : child is the leaf at sorted position ~link
+//   last      : highest sorted leaf position inside the child's subtree
+struct __align__(32) Node32 {
+    float lo[3];
+    float hi[3];
+    int32_t link;
+    int32_t last;
+};
+struct __align__(64) NodePair {
+    Node32 c[2];
+};
+
+// Everything the narrow phase needs about one triangle, at its sorted position:
+// vertex coordinates (copies, so no indirection), vertex indices for the
+// shared-vertex filter (reference triangle.cuh:18-30) and the triangle ID.
+struct __align__(64) LeafRec {
+    float v[9];       // v0.xyz v1.xyz v2.xyz in the triangle's own vIdx order
+    uint32_t vi[3];
+    uint32_t id;
+    uint32_t pad[3];
+};
+static_assert(sizeof(Node32) == 32 && sizeof(NodePair) == 64 && sizeof(LeafRec) == 64, "layout");
+
+// ---------------------------------------------------------------- host-side objects
+
+}  // namespace b200cd
+
+struct b200cd_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    b200cd_stats stats{};
+    std::string last_error;
+    cudaEvent_t ev[20]{};
+    // scratch shared by builds/queries on this context
+    uint32_t* d_scalars = nullptr;   // small device scratch (counters, flags, bbox)
+    uint32_t* h_scalars = nullptr;   // pinned mirror
+};
+
+struct b200cd_mesh {
+    b200cd_ctx* ctx = nullptr;
+    uint32_t nverts = 0, ntris = 0;
+    float4* d_verts = nullptr;   // nverts float4 (xyz, w = 0)
+    uint32_t* d_idx = nullptr;   // ntris * 3
+};
+
+struct b200cd_bvh {
+    b200cd_ctx* ctx = nullptr;
+    uint32_t n = 0;         // triangles
+    uint32_t nverts = 0;
+    bool built = false;
+    b200cd_params params{};
+    // sort buffers (ping-pong); sorted result is in d_keys[cur] / d_ids[cur]
+    uint64_t* d_keys[2] = {nullptr, nullptr};
+    uint32_t* d_ids[2] = {nullptr, nullptr};
+    int cur = 0;
+    uint32_t* d_hist = nullptr;        // radix histograms / digit bases
+    uint32_t* d_tile_status = nullptr; // decoupled look-back words
+    uint64_t tile_status_words = 0;
+    // hierarchy
+    uint32_t* d_parent = nullptr;      // [n-1 internal | n leaves], value = parent<<1 | side, ~0u = root
+    uint32_t* d_flags = nullptr;       // n-1 refit arrival counters
+    b200cd::NodePair* d_pairs = nullptr;  // n-1
+    b200cd::LeafRec* d_leaves = nullptr;  // n
+    float* d_root_box = nullptr;       // 6 floats
+    // query
+    uint2* d_cand = nullptr;  uint64_t cand_cap = 0;
+    uint2* d_out = nullptr;   uint64_t out_cap = 0;
+    uint2* d_out_tmp = nullptr; uint64_t out_tmp_cap = 0;
+    unsigned long long* d_counters = nullptr;  // [0] candidates, [1] pairs, [2] error flags
+    unsigned long long* h_counters = nullptr;  // pinned
+};
+
+namespace b200cd {
+
+// every kernel launch of this library is counted (b200cd_stats::kernel_launches)
+extern unsigned long long g_kernel_launches;
+inline void count_launch(unsigned n = 1) { g_kernel_launches += n; }
+
+inline int set_error(b200cd_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+#define CD_CUDA(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return b200cd::set_error((ctx), e__ == cudaErrorMemoryAllocation ? B200CD_E_NOMEM      \
+                                                                              : B200CD_E_CUDA,    \
+                                     std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+// kernels' host launchers (each enqueues on `s`, no synchronisation)
+// morton.cu
+void launch_expand_verts(const float* d_xyz, float4* d_verts, uint32_t nverts, cudaStream_t s);
+void launch_check_idx(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, uint32_t* d_flag, int sms, cudaStream_t s);
+void launch_bbox(const float4* d_verts, uint32_t nverts, uint32_t* d_bbox6 /*ordered-uint min3,max3*/, int sms, cudaStream_t s);
+void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t n, const b200cd_params& p,
+                   const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s);
+// radix_sort.cu
+struct RadixPass { int shift; int bits; };
+// sorts n (key,value) items; values may be null (keys only); if iota_values the
+// first pass generates value = index. Result lands in buffer index returned.
+int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
+               bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words,
+               int sms, cudaStream_t s);
+uint64_t radix_tile_status_words(uint32_t n, int npass);
+uint32_t radix_hist_words(int npass);
+// lbvh.cu
+void launch_hierarchy(const uint64_t* d_keys, uint32_t n, uint32_t* d_parent, cudaStream_t s);
+void launch_refit(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, uint32_t n,
+                  const uint32_t* d_parent, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves,
+                  float* d_root_box, cudaStream_t s);
+void launch_export_nodes(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n,
+                         b200cd_node32* d_nodes_out, cudaStream_t s);
+void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const uint32_t* d_parent,
+                     const uint32_t* d_flags, const uint64_t* d_keys, uint32_t n, uint32_t nverts,
+                     uint32_t* d_checks9, cudaStream_t s);
+// collide.cu
+void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, uint32_t n, uint32_t shard, uint32_t nshards,
+                  uint32_t chunk, uint32_t nquery, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
+                  cudaStream_t s);
+void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
+                   unsigned long long* d_counters, int sms, cudaStream_t s);
+
+}  // namespace b200cd

@@ -1,0 +1,284 @@
+// radix_sort.cu — K2: onesweep-style LSD radix sort of (u64 key, u32 value) pairs.
+//
+// Replaces the reference's HOST thrust::sort_by_key(mortons, triangles)
+// (reference load_obj.h:107). Stable, so equal keys keep face (ID) order.
+//
+// Structure (Adinets & Merrill, "Onesweep", 2022 — restated, not library code):
+//   1. rs_histogram  one read of the keys builds the digit histograms of ALL passes
+//                    (shared-memory atomics, then one global atomic per bin);
+//   2. rs_scan       exclusive scan of each pass's 256 bins -> global digit bases;
+//   3. rs_pass x P   one kernel per digit. Each CTA takes a tile of 4096 items
+//                    (ticket from an atomic counter, so look-back never waits on a
+//                    tile that has not started), ranks its keys with a warp-level
+//                    multi-split (__match_any_sync + per-warp shared histograms),
+//                    publishes its per-digit counts and resolves its global offsets
+//                    by DECOUPLED LOOK-BACK over the previous tiles' status words,
+//                    stages the tile in shared memory in digit order and writes it
+//                    out in coalesced runs. Keys and values are read once and
+//                    written once per pass.
+//
+// HBM traffic per pass: 12 B read + 12 B written per item (8+8 keys-only); the
+// histogram adds one 8 B read. Look-back words: 1 KiB per tile per pass.
+#include "common.cuh"
+
+namespace b200cd {
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_IPT = 16;                    // items per thread
+constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 items per tile
+constexpr int RS_RADIX = 256;
+constexpr uint32_t ST_PARTIAL = 1u << 30;     // status word = flag | count  (count < 2^30)
+constexpr uint32_t ST_INCLUSIVE = 2u << 30;
+constexpr uint32_t ST_MASK = (1u << 30) - 1;
+constexpr int RS_MAX_PASS = 8;
+
+struct PassList {
+    int npass;
+    int shift[RS_MAX_PASS];
+    uint32_t mask[RS_MAX_PASS];
+};
+
+// ---- 1. histograms of every pass in one sweep
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram(const uint64_t* __restrict__ keys, uint32_t n,
+                                                           PassList pl, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[RS_MAX_PASS * RS_RADIX];
+    for (int i = threadIdx.x; i < pl.npass * RS_RADIX; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    // grid-stride over 2-key vectors (16-B loads)
+    const uint32_t nvec = n >> 1;
+    const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
+    for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < nvec; i += gridDim.x * RS_THREADS) {
+        ulonglong2 k = __ldg(k2 + i);
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASS; ++p) {
+            if (p < pl.npass) {
+                atomicAdd(&sh[p * RS_RADIX + ((k.x >> pl.shift[p]) & pl.mask[p])], 1u);
+                atomicAdd(&sh[p * RS_RADIX + ((k.y >> pl.shift[p]) & pl.mask[p])], 1u);
+            }
+        }
+    }
+    if ((n & 1u) && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint64_t k = keys[n - 1];
+        for (int p = 0; p < pl.npass; ++p) atomicAdd(&sh[p * RS_RADIX + ((k >> pl.shift[p]) & pl.mask[p])], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pl.npass * RS_RADIX; i += RS_THREADS) {
+        uint32_t c = sh[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// ---- 2. exclusive scan of 256 bins, one block per pass
+__global__ void __launch_bounds__(RS_RADIX) rs_scan(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t wsum[RS_RADIX / 32];
+    uint32_t* h = hist + blockIdx.x * RS_RADIX;
+    uint32_t v = h[threadIdx.x];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += wsum[w];
+    h[threadIdx.x] = base + incl - v;
+}
+
+// ---- 3. one digit pass
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool HAS_VALUES>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
+        uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values,
+        const uint32_t* __restrict__ digit_base_g,  // [256] exclusive global digit offsets of this pass
+        uint32_t* __restrict__ status,              // [ntiles][256] look-back words of this pass
+        uint32_t* __restrict__ ticket) {
+    __shared__ uint32_t warp_hist[RS_WARPS][RS_RADIX + 1];  // +1: bin 256 collects out-of-range padding
+    __shared__ uint32_t digit_base[RS_RADIX];
+    __shared__ uint32_t warp_tot[RS_WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ __align__(16) uint64_t stage[RS_TILE];  // 32 KiB, reused for the values
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < RS_WARPS * (RS_RADIX + 1); i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t tile_base = tile * RS_TILE;
+    const uint32_t tile_items = min((uint32_t)RS_TILE, n - tile_base);
+    const uint32_t my_base = tile_base + warp * (32 * RS_IPT) + lane;  // warp-striped: item k at my_base + 32k
+
+    // load keys
+    uint64_t key[RS_IPT];
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        uint32_t g = my_base + 32 * k;
+        key[k] = (g < n) ? __ldg(keys_in + g) : ~0ull;
+    }
+
+    // warp-level multi-split: rank of every key among the warp's keys with the same digit
+    uint32_t rank[RS_IPT];
+    uint32_t* wh = warp_hist[warp];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        uint32_t g = my_base + 32 * k;
+        uint32_t d = (g < n) ? (uint32_t)((key[k] >> shift) & mask) : (uint32_t)RS_RADIX;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t prev = 0;
+        if ((int)lane == leader) {
+            prev = wh[d];
+            wh[d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[k] = prev + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: exclusive prefix over warps, tile count, look-back
+    {
+        const uint32_t d = tid;  // RS_THREADS == RS_RADIX
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t c = warp_hist[w][d];
+            warp_hist[w][d] = sum;
+            sum += c;
+        }
+        // publish this tile's count for digit d, then sum the counts of earlier tiles
+        uint32_t* my_status = status + (size_t)tile * RS_RADIX + d;
+        st_volatile(my_status, (tile == 0 ? ST_INCLUSIVE : ST_PARTIAL) | sum);
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            while (true) {
+                uint32_t s = ld_volatile(status + (size_t)t * RS_RADIX + d);
+                if ((s & ~ST_MASK) == 0) continue;  // not published yet (tile t is running: tickets are ordered)
+                excl += s & ST_MASK;
+                if (s & ST_INCLUSIVE) break;
+                --t;
+            }
+            st_volatile(my_status, ST_INCLUSIVE | (excl + sum));
+        }
+        // exclusive scan of `sum` over the 256 digits -> where digit d starts inside the tile
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t2 = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t2;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) wbase += (w < (int)warp) ? warp_tot[w] : 0u;
+        uint32_t local_start = wbase + incl - sum;
+        // final position of the item with in-tile slot r and digit d: digit_base[d] + r  (mod 2^32)
+        digit_base[d] = __ldg(digit_base_g + d) + excl - local_start;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) warp_hist[w][d] += local_start;
+    }
+    __syncthreads();
+
+    // stage keys in digit order
+    uint32_t slot[RS_IPT];
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        uint32_t g = my_base + 32 * k;
+        if (g < n) {
+            uint32_t d = (uint32_t)((key[k] >> shift) & mask);
+            slot[k] = wh[d] + rank[k];
+            stage[slot[k]] = key[k];
+        } else {
+            slot[k] = 0;
+        }
+    }
+    __syncthreads();
+    uint32_t pos[RS_IPT];
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        uint32_t r = i * RS_THREADS + tid;
+        if (r < tile_items) {
+            uint64_t kk = stage[r];
+            pos[i] = digit_base[(uint32_t)((kk >> shift) & mask)] + r;
+            keys_out[pos[i]] = kk;
+        }
+    }
+    if (HAS_VALUES) {
+        __syncthreads();
+        uint32_t* vstage = reinterpret_cast<uint32_t*>(stage);
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            uint32_t g = my_base + 32 * k;
+            if (g < n) vstage[slot[k]] = iota_values ? g : __ldg(vals_in + g);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RS_IPT; ++i) {
+            uint32_t r = i * RS_THREADS + tid;
+            if (r < tile_items) vals_out[pos[i]] = vstage[r];
+        }
+    }
+}
+
+}  // namespace
+
+uint32_t radix_hist_words(int npass) { return (uint32_t)(npass * RS_RADIX + RS_MAX_PASS); }  // + tickets
+
+uint64_t radix_tile_status_words(uint32_t n, int npass) {
+    uint64_t tiles = ((uint64_t)n + RS_TILE - 1) / RS_TILE;
+    return tiles * RS_RADIX * (uint64_t)npass;
+}
+
+int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
+               bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words, int sms,
+               cudaStream_t s) {
+    (void)tile_status_words;
+    if (n == 0 || npass == 0) return 0;
+    PassList pl{};
+    pl.npass = npass;
+    for (int p = 0; p < npass; ++p) {
+        pl.shift[p] = passes[p].shift;
+        pl.mask[p] = (1u << passes[p].bits) - 1u;
+    }
+    const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t* d_ticket = d_hist + npass * RS_RADIX;
+    cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);
+    cudaMemsetAsync(d_tile_status, 0, sizeof(uint32_t) * (size_t)tiles * RS_RADIX * npass, s);
+    uint32_t hblocks = min((n / 2 + RS_THREADS - 1) / RS_THREADS + 1, (uint32_t)sms * 8u);
+    rs_histogram<<<hblocks, RS_THREADS, 0, s>>>(keys[0], n, pl, d_hist);
+    count_launch();
+    rs_scan<<<npass, RS_RADIX, 0, s>>>(d_hist);
+    count_launch();
+    int cur = 0;
+    for (int p = 0; p < npass; ++p) {
+        uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
+        if (vals)
+            rs_pass<true><<<tiles, RS_THREADS, 0, s>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n,
+                                                       pl.shift[p], pl.mask[p], (iota_values && p == 0) ? 1 : 0,
+                                                       d_hist + p * RS_RADIX, status, d_ticket + p);
+        else
+            rs_pass<false><<<tiles, RS_THREADS, 0, s>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, pl.shift[p],
+                                                        pl.mask[p], 0, d_hist + p * RS_RADIX, status, d_ticket + p);
+        count_launch();
+        cur ^= 1;
+    }
+    return cur;
+}
+
+}  // namespace b200cd

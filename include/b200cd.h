@@ -1,0 +1,234 @@
+/*
+ * b200cd.h — C ABI of libb200cd.so: B200-native (sm_100a) triangle-mesh
+ * self-collision detection. Drop-in boundary for the one hot path of
+ * Asichurter/GPU-Computing-Course's CollisionDetection project:
+ *
+ *     OBJ / arrays in -> LBVH build -> self-collision query -> colliding pair list out
+ *
+ * The reference has no FFI/plugin interface; its "entry-point surface" is the call
+ * sequence inside main() (reference CollisionDetection/main.cu:47-174). Each entry
+ * point below names the reference call it replaces. All citations are relative to
+ * /root/reference/CollisionDetection/.
+ *
+ * Conventions
+ *   - plain C, opaque handles, every function returns an int status (0 = OK);
+ *     nothing calls exit() (reference: common/book.h:21-31, load_obj.h:34,60,73)
+ *     and nothing throws across the boundary;
+ *   - one context = one GPU = one host thread at a time (externally synchronised);
+ *     multi-GPU = one process (rank) per GPU, each with its own context, sharding
+ *     the query with b200cd_self_collide_shard;
+ *   - the library owns device memory behind handles; the caller owns host buffers;
+ *   - there is NO CPU fallback: without a CUDA device b200cd_create fails.
+ */
+#ifndef B200CD_H
+#define B200CD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CD_ABI_VERSION 1
+
+typedef struct b200cd_ctx b200cd_ctx;
+typedef struct b200cd_mesh b200cd_mesh;
+typedef struct b200cd_bvh b200cd_bvh;
+
+enum {
+    B200CD_OK = 0,
+    B200CD_E_INVALID = 1,   /* bad argument */
+    B200CD_E_CUDA = 2,      /* CUDA runtime error, see b200cd_last_error */
+    B200CD_E_NOMEM = 3,     /* host or device allocation failed */
+    B200CD_E_IO = 4,        /* file could not be opened / read */
+    B200CD_E_PARSE = 5,     /* OBJ line not in the accepted dialect */
+    B200CD_E_CAPACITY = 6,  /* caller's pair buffer too small; *count_out holds the true count */
+    B200CD_E_DEPTH = 7,     /* traversal stack exhausted (tree deeper than B200CD_MAX_STACK) */
+    B200CD_E_NODEVICE = 8,  /* no usable sm_100 device */
+    B200CD_E_TOOBIG = 9     /* mesh exceeds 2^30 triangles or vertices */
+};
+
+/* Morton normalisation and key width.
+ * Reference: morton.h:43-58 hard-codes origin/extent for the flag mesh and
+ * morton.h:70-89 builds 63-bit codes (20 bits per axis used); morton.h:31-40 holds
+ * the unused 30-bit variant. b200cd_default_params() yields exactly those
+ * constants; auto_box != 0 replaces them with the mesh's own bounding box. */
+typedef struct b200cd_params {
+    double morton_origin[3];
+    double morton_extent[3];
+    int32_t key_bits;            /* 63 or 30 */
+    int32_t auto_box;            /* 0: use origin/extent above; 1: mesh bounding box */
+    uint64_t pair_capacity_hint; /* expected number of colliding pairs (0 = let the library guess) */
+} b200cd_params;
+
+/* One BVH node as exported by b200cd_bvh_download, in the reference's Karras
+ * numbering (bvh.cuh:161-198): nodes[0 .. n-2] are the internal nodes with their
+ * Karras index (root = 0), nodes[n-1+j] is the leaf of sorted position j.
+ * left/right are such unified node numbers (-1 for leaves). 32 bytes: the
+ * reference's 112-byte Node (bvh.cuh:25-43) holds six doubles that are always
+ * exact copies of fp32 vertex coordinates (load_obj.h:38,50-52), so float
+ * storage is lossless. */
+typedef struct b200cd_node32 {
+    float lo[3];
+    float hi[3];
+    int32_t left;
+    int32_t right;
+} b200cd_node32;
+
+/* Per-stage device times of the most recent build / query on a context, from CUDA
+ * events on the context's stream (reference: printElapsedTime, main.cu:19-24). */
+typedef struct b200cd_stats {
+    float ms_upload;      /* H2D + vertex expansion (mesh_from_arrays / load_obj) */
+    float ms_morton;      /* K1: centroid + Morton keys (+ bounding box when auto_box) */
+    float ms_sort;        /* K2: onesweep radix sort of (key, id) */
+    float ms_hierarchy;   /* K3: Karras hierarchy */
+    float ms_refit;       /* K4: leaf records + bottom-up AABB refit */
+    float ms_build;       /* K1..K4 end to end */
+    float ms_traverse;    /* K5: broad phase (BVH traversal -> candidate pairs) */
+    float ms_narrow;      /* K6: fp64 triangle-triangle tests -> pairs */
+    float ms_pair_sort;   /* optional lexicographic sort of the pair list */
+    float ms_query;       /* K5 + K6 (+ sort) end to end */
+    float ms_download;    /* D2H of the pair list */
+    uint32_t ntris, nverts;
+    uint64_t candidates;  /* AABB-overlapping leaf pairs handed to the narrow phase */
+    uint64_t pairs;       /* colliding pairs found */
+    uint32_t sort_passes; /* radix passes actually run */
+    uint32_t query_retries; /* times a stage was re-run after growing a buffer */
+    uint64_t kernel_launches; /* cumulative count of this library's kernel launches on the context */
+} b200cd_stats;
+
+/* Structural self-checks, the counters the reference prints on every run
+ * (check.cuh:64-96, main.cu:113-136): all must be 0 except null_parent_internal,
+ * which is 1 (the root). */
+typedef struct b200cd_checks {
+    uint32_t null_parent_internal; /* check.cuh:74 */
+    uint32_t wrong_bound_count;    /* check.cuh:73  (visit counter != 2) */
+    uint32_t null_child;           /* check.cuh:75-76 */
+    uint32_t uninit_box_internal;  /* check.cuh:77 */
+    uint32_t null_parent_leaf;     /* check.cuh:91 */
+    uint32_t bad_triangle;         /* check.cuh:92, :29-50 (vertex index out of range) */
+    uint32_t uninit_box_leaf;      /* check.cuh:93 */
+    uint32_t unsorted_keys;        /* load_obj.h:109-115 (strictly increasing; ties count) */
+    uint32_t box_not_enclosing;    /* ours: a parent box that does not contain its children */
+} b200cd_checks;
+
+/* ---- context ------------------------------------------------------------ */
+
+/* Replaces the implicit "device 0, default stream" of main.cu. */
+int b200cd_create(int device, b200cd_ctx** out);
+int b200cd_destroy(b200cd_ctx* ctx);
+/* Run all of the context's work on a caller-owned cudaStream_t (e.g. the stream
+ * a benchmark records its CUDA events on). NULL restores the private stream. */
+int b200cd_set_stream(b200cd_ctx* ctx, void* cuda_stream);
+int b200cd_synchronize(b200cd_ctx* ctx);
+int b200cd_get_stats(const b200cd_ctx* ctx, b200cd_stats* out);
+const char* b200cd_strerror(int status);
+const char* b200cd_last_error(const b200cd_ctx* ctx);
+int b200cd_abi_version(void);
+
+void b200cd_default_params(b200cd_params* p);
+
+/* Page-locked host buffers for callers that want full-rate H2D/D2H. */
+int b200cd_host_alloc(void** out, uint64_t bytes);
+int b200cd_host_free(void* p);
+
+/* ---- mesh in ------------------------------------------------------------ */
+
+/* Replaces loadObj (load_obj.h:24-103) + the H2D copies of main.cu:78-88.
+ * Same dialect and quirks: only "v %f %f %f" and "f %d/%d %d/%d %d/%d" lines are
+ * read (load_obj.h:50,68), indices are 1-based (load_obj.h:81-83), triangle ID =
+ * face order (load_obj.h:94), a last line without '\n' is dropped (load_obj.h:41).
+ * Malformed lines and out-of-range / forward vertex references return
+ * B200CD_E_PARSE instead of exit()/undefined behaviour. */
+int b200cd_mesh_load_obj(b200cd_ctx* ctx, const char* path, b200cd_mesh** out);
+
+/* Array twin of the above: xyz = nverts*3 floats, tri_idx = ntris*3 0-based
+ * indices, triangle ID = array order. Host pointers. */
+int b200cd_mesh_from_arrays(b200cd_ctx* ctx, const float* xyz, uint32_t nverts,
+                            const uint32_t* tri_idx, uint32_t ntris, b200cd_mesh** out);
+/* Same, but the two arrays are already in device memory on the context's GPU. */
+int b200cd_mesh_from_device(b200cd_ctx* ctx, const void* d_xyz, uint32_t nverts,
+                            const void* d_tri_idx, uint32_t ntris, b200cd_mesh** out);
+/* Overwrite the contents of an existing mesh in place (same nverts / ntris):
+ * xyz and/or tri_idx may be NULL to keep that array. Host (on_device = 0) or
+ * device pointers. This is the per-frame update of a cloth / flag simulation and
+ * the steady-state upload path (no allocation). */
+int b200cd_mesh_update(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, const uint32_t* tri_idx,
+                       int on_device);
+int b200cd_mesh_info(const b200cd_mesh* mesh, uint32_t* nverts, uint32_t* ntris);
+int b200cd_mesh_download(b200cd_ctx* ctx, const b200cd_mesh* mesh, float* xyz, uint32_t* tri_idx);
+int b200cd_mesh_destroy(b200cd_mesh* mesh);
+
+/* ---- BVH build ---------------------------------------------------------- */
+
+/* Replaces: centroid + morton3D (load_obj.h:89-91, morton.h:70-89), the host
+ * thrust::sort_by_key (load_obj.h:107), fillLeafNodes (bvh.cuh:125, main.cu:92),
+ * generateHierarchyParallel (bvh.cuh:146, main.cu:99) and calBoundingBox
+ * (bvh.cuh:258, main.cu:107). Asynchronous on the context's stream. */
+int b200cd_bvh_build(b200cd_ctx* ctx, const b200cd_mesh* mesh, const b200cd_params* params,
+                     b200cd_bvh** out);
+/* Rebuild in place, reusing every allocation of an existing BVH (steady state). */
+int b200cd_bvh_rebuild(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh,
+                       const b200cd_params* params);
+/* Keep topology and order, recompute leaf records and all boxes from the mesh's
+ * current vertex positions (K4 only). */
+int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh);
+/* Parity hooks: any pointer may be NULL. nodes: 2n-1 entries (see b200cd_node32),
+ * sorted_keys / sorted_ids: n entries (load_obj.h:107 result). */
+int b200cd_bvh_download(b200cd_ctx* ctx, const b200cd_bvh* bvh, b200cd_node32* nodes,
+                        uint64_t* sorted_keys, uint32_t* sorted_ids);
+/* The reference's per-run self-checks (check.cuh:29-96) on the device. */
+int b200cd_bvh_validate(b200cd_ctx* ctx, const b200cd_bvh* bvh, const b200cd_mesh* mesh,
+                        b200cd_checks* out);
+int b200cd_bvh_destroy(b200cd_bvh* bvh);
+
+/* ---- self-collision query ------------------------------------------------ */
+
+/* Replaces findCollisions (collision.cuh:73-88, main.cu:142) + the D2H of
+ * main.cu:145-146. pairs_out receives *count_out pairs as uint32_t[2], lower
+ * triangle ID first (tri_contact.cuh:81); sorted != 0 => lexicographic order.
+ * The pair SET equals the reference's: {(a,b): a<b, no shared vertex index
+ * (triangle.cuh:18-30), AABBs strictly overlap (box.cuh:40-43),
+ * checkTriangleContact(a,b) (tri_contact.cuh:19-78)}. If more than `cap` pairs
+ * exist, nothing is written, *count_out holds the count and
+ * B200CD_E_CAPACITY is returned (the reference overruns its 500-pair buffer,
+ * main.cu:81, collision.cuh:40-42). pairs_out may be NULL with cap = 0 to count. */
+int b200cd_self_collide(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t* pairs_out, uint64_t cap,
+                        uint64_t* count_out, int sorted);
+
+/* Query-sharded form for one rank of a multi-GPU job: only the query triangles of
+ * sorted-leaf chunks c with c % nshards == shard are traversed (chunk = leaves per
+ * chunk; 0 = one contiguous slice per shard). The union over all shards is the
+ * full pair set; shards are disjoint. */
+int b200cd_self_collide_shard(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t shard, uint32_t nshards,
+                              uint32_t chunk, uint32_t* pairs_out, uint64_t cap,
+                              uint64_t* count_out, int sorted);
+
+/* Device-resident result: *d_pairs_out points at library-owned device memory
+ * (valid until the next query on this BVH), *count_out pairs of uint32_t[2]. */
+int b200cd_self_collide_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t shard, uint32_t nshards,
+                               uint32_t chunk, int sorted, const void** d_pairs_out,
+                               uint64_t* count_out);
+
+/* Lexicographic sort of a device-resident pair list (e.g. after gathering the
+ * per-rank lists on rank 0). id_bits = number of significant bits in a triangle
+ * ID (0 = 32). In place. */
+int b200cd_sort_pairs_device(b200cd_ctx* ctx, void* d_pairs, uint64_t count, uint32_t id_bits);
+
+/* Device views for replicating a built BVH to other ranks (NCCL broadcast is
+ * done by the caller on these buffers): three blobs — traversal nodes, leaf
+ * records, sorted ids. b200cd_bvh_alloc_like creates an empty BVH of the same
+ * shape on the receiving rank. */
+typedef struct b200cd_bvh_view {
+    void* d_nodes;   uint64_t nodes_bytes;
+    void* d_leaves;  uint64_t leaves_bytes;
+    void* d_ids;     uint64_t ids_bytes;
+    uint32_t ntris;
+} b200cd_bvh_view;
+int b200cd_bvh_view_get(b200cd_ctx* ctx, b200cd_bvh* bvh, b200cd_bvh_view* out);
+int b200cd_bvh_alloc_like(b200cd_ctx* ctx, uint32_t ntris, b200cd_bvh** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CD_H */

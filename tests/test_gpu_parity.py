@@ -1,0 +1,136 @@
+"""GPU parity: every stage of the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bit-exact bar (BASELINE.json north_star): keys, sorted order, tree topology, node bounds
+(0 ulp — they are min/max of fp32 inputs) and the sorted colliding-pair set.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+UNIT = dict(origin=(0.0, 0.0, 0.0), extent=(1.0, 1.0, 1.0))
+
+
+def oracle_stages(co, xyz, idx, op):
+    keys = co.morton_keys(xyz, idx, op)
+    sk, si = co.sort_keys(keys)
+    h = co.hierarchy(sk)
+    b = co.refit(xyz, idx, si, h)
+    pairs, ctr = co.self_collide(xyz, idx, si, h, b)
+    return dict(keys=keys, sk=sk, si=si, h=h, bounds=b, pairs=co.sort_pairs(pairs), ctr=ctr)
+
+
+def check_all_stages(cd, co, ctx, xyz, idx, origin=None, extent=None, key_bits=63, auto_box=False):
+    if auto_box:
+        op = co.auto_params(xyz, key_bits)
+    elif origin is None:
+        op = co.default_params(key_bits)
+    else:
+        op = co.make_params(origin, extent, key_bits)
+    ref = oracle_stages(co, xyz, idx, op)
+    gp = cd.make_params(origin, extent, key_bits, auto_box)
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, gp)
+    nodes, skeys, sids = bvh.download()
+    n = len(idx)
+    assert np.array_equal(skeys, ref["sk"]), "sorted Morton keys differ"
+    assert np.array_equal(sids, ref["si"]), "sorted triangle ids differ"
+    if n >= 2:
+        assert np.array_equal(nodes["left"][: n - 1], ref["h"]["left"]), "left children differ"
+        assert np.array_equal(nodes["right"][: n - 1], ref["h"]["right"]), "right children differ"
+    gb = np.concatenate([nodes["lo"], nodes["hi"]], axis=1).astype(np.float64)
+    assert np.array_equal(gb, ref["bounds"]), "node bounds differ (expected 0 ulp)"
+    chk = bvh.validate(mesh)
+    expect_unsorted = int(np.sum(ref["sk"][1:] <= ref["sk"][:-1])) if n > 1 else 0
+    assert chk == dict(null_parent_internal=1 if n >= 2 else 0, wrong_bound_count=0, null_child=0,
+                       uninit_box_internal=0, null_parent_leaf=0, bad_triangle=0, uninit_box_leaf=0,
+                       unsorted_keys=expect_unsorted, box_not_enclosing=0), chk
+    pairs = ctx.self_collide(bvh, sorted=True)
+    assert pairs.shape == ref["pairs"].shape, (pairs.shape, ref["pairs"].shape)
+    assert np.array_equal(pairs, ref["pairs"]), "colliding-pair set differs"
+    unsorted_pairs = ctx.self_collide(bvh, sorted=False)
+    assert np.array_equal(co.sort_pairs(unsorted_pairs.copy()), ref["pairs"])
+    st = ctx.stats()
+    assert st["pairs"] == len(pairs)
+    bvh.destroy()
+    mesh.destroy()
+    return ref, st
+
+
+def test_soup_small_unit_cube(cd, co, ctx, mg):
+    xyz, idx = mg.soup(20000, seed=3)
+    ref, st = check_all_stages(cd, co, ctx, xyz, idx, **UNIT)
+    assert len(ref["pairs"]) > 1000
+
+
+def test_soup_reference_box_default_params(cd, co, ctx, mg):
+    xyz, idx = mg.soup(50000, seed=11, origin=(0.1, -0.4, -0.3), extent=(2.8, 0.6, 2.2))
+    check_all_stages(cd, co, ctx, xyz, idx)
+
+
+def test_soup_256k(cd, co, ctx, mg):
+    xyz, idx = mg.soup(1 << 18, seed=1234)
+    ref, st = check_all_stages(cd, co, ctx, xyz, idx, **UNIT)
+    assert st["candidates"] >= st["pairs"]
+
+
+def test_cloth_dense_contacts_shared_vertices(cd, co, ctx, mg):
+    xyz, idx = mg.cloth_fold(200, 200)
+    ref, _ = check_all_stages(cd, co, ctx, xyz, idx)
+    assert len(ref["pairs"]) > 0.1 * len(idx)
+
+
+def test_flag_standin(cd, co, ctx, mg):
+    xyz, idx = mg.flag(300, 300)
+    ref, _ = check_all_stages(cd, co, ctx, xyz, idx)
+    assert 0 < len(ref["pairs"]) < 2000
+
+
+def test_two_sheets(cd, co, ctx, mg):
+    xyz, idx = mg.two_sheets(200)
+    check_all_stages(cd, co, ctx, xyz, idx, **UNIT)
+
+
+def test_auto_box(cd, co, ctx, mg):
+    xyz, idx = mg.soup(30000, seed=5, origin=(-7.0, 3.0, 100.0), extent=(2.0, 9.0, 0.5))
+    check_all_stages(cd, co, ctx, xyz, idx, auto_box=True)
+
+
+def test_30bit_keys_with_duplicates(cd, co, ctx, mg):
+    # 60000 triangles in 2^30 cells still collide now and then; a tight cluster forces many ties
+    xyz, idx = mg.soup(60000, seed=8)
+    xyz2, idx2 = mg.soup(4000, h=1e-4, seed=9, origin=(0.5, 0.5, 0.5), extent=(0.002, 0.002, 0.002))
+    xyz = np.concatenate([xyz, xyz2])
+    idx = np.concatenate([idx, idx2 + 3 * 60000]).astype(np.uint32)
+    ref, _ = check_all_stages(cd, co, ctx, xyz, idx, key_bits=30, **UNIT)
+    assert len(np.unique(ref["keys"])) < len(idx), "test needs duplicate keys"
+
+
+def test_all_keys_identical(cd, co, ctx, mg):
+    # every centroid in one Morton cell: the tree is decided by the index tie-break alone
+    xyz, idx = mg.soup(3000, h=0.2, seed=4, origin=(0.5, 0.5, 0.5), extent=(1e-9, 1e-9, 1e-9))
+    ref, _ = check_all_stages(cd, co, ctx, xyz, idx, key_bits=30, origin=(0, 0, 0), extent=(1, 1, 1))
+    assert len(np.unique(ref["keys"])) == 1
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 32, 33, 4095, 4096, 4097])
+def test_tiny_and_tile_boundary_sizes(cd, co, ctx, mg, n):
+    xyz, idx = mg.soup(n, h=0.3, seed=100 + n)
+    check_all_stages(cd, co, ctx, xyz, idx, **UNIT)
+
+
+def test_empty_mesh(cd, ctx):
+    mesh = ctx.mesh_from_arrays(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+    bvh = ctx.bvh_build(mesh, cd.default_params())
+    assert len(ctx.self_collide(bvh)) == 0
+    bvh.destroy()
+    mesh.destroy()
+
+
+def test_brute_force_small(cd, co, ctx, mg):
+    xyz, idx = mg.soup(1500, h=0.08, seed=77)
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, cd.make_params(**UNIT))
+    pairs = ctx.self_collide(bvh)
+    assert np.array_equal(pairs, co.brute_force(xyz, idx))
+    assert len(pairs) > 100
