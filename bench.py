@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — Mtri/s end-to-end self-collision (BVH build + query) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one pass of the hot path over one synthetic mesh: BVH build (Morton keys, radix
+sort, Karras hierarchy, refit) + self-collision query (traversal, fp64 narrow phase, sorted pair
+list). Workloads (BASELINE.json `configs`):
+    soup16m    C4  random triangle soup, 2^24 triangles in the unit cube   (default at N = 1)
+    sheets64m  C5  two 4096x4096-quad sheets, 2^26 triangles               (default at N > 1)
+    cloth1m    C3  accordion-folded sheet, 1 002 528 triangles, dense contacts
+    flag1m     C1/C2 stand-in for the missing flag mesh, 1 262 460 triangles
+N > 1: one rank per GPU (torchrun), query-sharded over ranks with a replicated BVH, per-rank pair
+lists gathered over NCCL and sorted on rank 0; strong scaling (the mesh is fixed).
+
+Prints ONE JSON line on rank 0. `value` = triangles / device time with the mesh resident in HBM;
+`e2e` = the same through the host-buffer C-ABI calls (H2D of the mesh and D2H of the pair list
+inside the timed region). `--impl reference` times the reference's own CPU functions
+(oracle/_ref, else the oracle port) on a bounded sample of the same workload.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "gpu-computing-course_b200"
+
+METRIC = "Mtri/s end-to-end self-collision (build+query)"
+UNIT = "Mtri/s"
+UNIT_CUBE = ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+
+WORKLOADS = {
+    # name: (kind, args, morton box or None = reference constants)
+    "soup16m": ("soup", dict(n=1 << 24, seed=1234), UNIT_CUBE),
+    "soup1m": ("soup", dict(n=1 << 20, seed=1234), UNIT_CUBE),
+    "sheets64m": ("two_sheets", dict(nq=4096, seed=7), UNIT_CUBE),
+    "sheets16m": ("two_sheets", dict(nq=2048, seed=7), UNIT_CUBE),
+    "cloth1m": ("cloth_fold", dict(nx=708, ny=708), None),
+    "flag1m": ("flag", dict(nx=795, nz=794), None),
+}
+
+
+def workload_sizes(mg, name):
+    kind, kw, _ = WORKLOADS[name]
+    if kind == "soup":
+        return 3 * kw["n"], kw["n"]
+    if kind == "two_sheets":
+        return mg.grid_sizes(kw["nq"], kw["nq"], 2)
+    if kind == "cloth_fold":
+        return mg.grid_sizes(kw["nx"], kw["ny"])
+    return mg.grid_sizes(kw["nx"], kw["nz"])
+
+
+def generate(mg, name, out=None):
+    kind, kw, _ = WORKLOADS[name]
+    return getattr(mg, kind)(**kw, out=out)
+
+
+def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes):
+    """Compulsory HBM bytes per stage for OUR data layout, each array read or
+    written once per pass. n triangles, nverts vertices."""
+    return {
+        # K1: 12 B indices + one 16 B float4 per vertex (each vertex is read at least once) + 8 B key out
+        "morton": 12 * n + 16 * nverts + 8 * n,
+        # K2: histogram reads the keys once; every pass reads and writes (8 B key + 4 B id)
+        #     (first pass generates the ids: no 4 B read)
+        "sort": 8 * n + sort_passes * 24 * n - 4 * n,
+        # K3: keys in, one 4 B parent word per node out
+        "hierarchy": 8 * n + 8 * n,
+        # K4: sorted ids + indices + vertices in, 64 B leaf record + 64 B node pair out, sibling
+        #     half (32 B) read back by the merging thread, parent word + arrival flag per node
+        "refit": 4 * n + 12 * n + 16 * nverts + 64 * n + 64 * n + 32 * n + 8 * n + 8 * n,
+        # K5: every node pair (64 B) and every query record (64 B) once, 8 B per candidate out
+        "traverse": 64 * n + 64 * n + 8 * ncand,
+        # K6: candidate in, two 64 B leaf records per candidate, 8 B per pair out
+        "narrow": 8 * ncand + 128 * ncand + 8 * npairs,
+    }
+
+
+STAGE_KERNEL = {"morton": "morton_kernel", "sort": "rs_pass (x passes) + rs_histogram", "hierarchy": "hierarchy_kernel",
+                "refit": "refit_kernel", "traverse": "broad_kernel", "narrow": "narrow_kernel"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi's clocks / throttle reasons, sampled through NVML while the timed region runs"""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.sm_max = index, period, [], set(), None
+        self._stop_evt = threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+
+def cpu_reference_run(name, sample_tris, threads, repeats=1):
+    """The reference's own host functions (oracle/_ref) — or the oracle port — on a bounded
+    sample of workload `name`: same generator and contact density, `sample_tris` triangles placed
+    inside the reference's hard-coded Morton box (morton.h:43-58) where its keys are valid.
+    Returns (Mtri/s list per repeat, info dict)."""
+    import numpy as np
+    mg = importlib.import_module(f"{PKG}.meshgen")
+    from oracle import refcd, cdoracle  # bench.py's CPU legs are one of the places allowed to run oracle/
+    kind, kw, _ = WORKLOADS[name]
+    if kind == "soup":
+        xyz, idx = mg.soup(sample_tris, seed=kw["seed"], origin=(0.1, -0.4, -0.3), extent=(2.8, 0.6, 2.2))
+        sample = f"{sample_tris}-triangle soup, same generator/density as {name}, inside the reference Morton box"
+    elif kind == "two_sheets":
+        nq = max(8, int(round((sample_tris / 4) ** 0.5)))
+        xyz, idx = mg.two_sheets(nq, seed=kw["seed"])
+        o, e = np.array(mg.REF_ORIGIN), np.array(mg.REF_EXTENT)
+        xyz = (o + 0.05 * e + xyz.astype(np.float64) * (0.9 * e.min())).astype(np.float32)  # uniform scale into the box
+        sample = f"two_sheets nq={nq} ({len(idx)} triangles), uniformly scaled into the reference Morton box"
+    elif kind == "cloth_fold":
+        s = max(8, int(round((sample_tris / 2) ** 0.5)))
+        xyz, idx = mg.cloth_fold(s, s)
+        sample = f"cloth_fold {s}x{s} ({len(idx)} triangles)"
+    else:
+        s = max(8, int(round((sample_tris / 2) ** 0.5)))
+        xyz, idx = mg.flag(s, s)
+        sample = f"flag {s}x{s} ({len(idx)} triangles)"
+    n = len(idx)
+    vals, stages = [], None
+    if refcd.available():
+        kind_s = "reference"
+        for _ in range(repeats):
+            m = refcd.RefMesh.from_arrays(xyz, idx)   # centroid + morton3D + thrust::sort_by_key (load_obj.h:89-107)
+            m.build()                                 # fillLeafNodesCpu, generateHierarchyParallelCpu, calBoundingBoxCpu
+            npairs = len(m.collide(threads))          # findCollisionIterativeCpu per sorted leaf
+            t = m.timing()
+            total_ms = t["load"] + t["fill"] + t["hierarchy"] + t["refit"] + t["query"]
+            vals.append(n / total_ms / 1e3)
+            stages = dict(t, pairs=npairs)
+            m.close()
+        how = ("reference host functions via oracle/ref_driver.cu; build stages serial as in the reference "
+               f"(cpu.cuh:103,125,171), query loop over {threads} thread(s)")
+    else:
+        kind_s = "port"
+        threads = 1
+        op = cdoracle.default_params()
+        for _ in range(repeats):
+            pairs, tm = cdoracle.run(xyz, idx, op)
+            total_ms = tm.ms_morton + tm.ms_sort + tm.ms_hierarchy + tm.ms_refit + tm.ms_query
+            vals.append(n / total_ms / 1e3)
+            stages = dict(morton=tm.ms_morton, sort=tm.ms_sort, hierarchy=tm.ms_hierarchy, refit=tm.ms_refit,
+                          query=tm.ms_query, pairs=int(tm.pairs))
+        how = "oracle/cd_oracle.c (plain-C restatement), one thread"
+    return vals, {"kind": kind_s, "cores": threads, "sample": sample, "how": how, "stages_ms": stages,
+                  "host_cores_available": os.cpu_count()}
+
+
+def run_reference_arm(args, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 alone
+    threads = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    sample_tris = (1 << 20) if total <= 40 else (1 << 18)
+    t0 = time.time()
+    vals, info = cpu_reference_run(workload, sample_tris, threads, repeats=total)
+    timed = vals[args.warmup:] or vals
+    v = len(timed) / sum(1.0 / x for x in timed)  # total triangles / total time over the timed steps
+    mg = importlib.import_module(f"{PKG}.meshgen")
+    nverts, ntris = workload_sizes(mg, workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e-3 * sample_tris / v, 3) if v else None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "triangles": ntris, "vertices": nverts},
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"], "how": info["how"], "stages_ms": info["stages_ms"],
+                         "host_cores_available": info["host_cores_available"]},
+        "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": round(time.time() - t0, 1),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+def run_gpu_arm(args, workload):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device. The collision path has no CPU fallback "
+                         "(use --impl reference for the CPU arm).")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cd = importlib.import_module(f"{PKG}.binding")
+    mg = importlib.import_module(f"{PKG}.meshgen")
+    mgpu = importlib.import_module(f"{PKG}.multigpu")
+
+    kind, kw, box = WORKLOADS[workload]
+    nverts, ntris = workload_sizes(mg, workload)
+    # the mesh a caller would hand us: page-locked host arrays (every rank holds the whole mesh)
+    xyz, xyz_ptr = cd.pinned_array((nverts, 3), np.float32)
+    idx, idx_ptr = cd.pinned_array((ntris, 3), np.uint32)
+    generate(mg, workload, out=(xyz, idx))
+    params = cd.make_params(*box) if box else cd.default_params()
+
+    ctx = cd.Context(local_rank)
+    runner = mgpu.ShardedSelfCollision(cd, ctx, chunk=args.chunk)  # binds the library to torch's current stream
+    mesh = ctx.mesh_from_host_ptr(xyz_ptr, nverts, idx_ptr, ntris)
+    bvh = ctx.bvh_build(mesh, params)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sizes the candidate / pair buffers, so timed steps never reallocate)
+    merged = None
+    for _ in range(max(args.warmup, 3)):
+        merged = runner.step(bvh, mesh, params)
+    npairs_total = int(merged.numel()) if rank == 0 else 0
+    host_pairs = torch.empty(max(npairs_total, 1) + 1024, dtype=torch.int64).pin_memory() if rank == 0 else None
+    # count_launch() is process-wide; sample before/after the timed region
+    launches0 = ctx.stats()["kernel_launches"]
+
+    stage_keys = ("ms_morton", "ms_sort", "ms_hierarchy", "ms_refit", "ms_build", "ms_traverse", "ms_narrow",
+                  "ms_pair_sort", "ms_query")
+    acc = {k: 0.0 for k in stage_keys}
+    last = {}
+
+    # ---- timed region 1: mesh resident in HBM
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        merged = runner.step(bvh, mesh, params)
+        st = ctx.stats()  # per-stage CUDA-event times of this step (events on the same stream)
+        for k in stage_keys:
+            acc[k] += st[k]
+        last = st
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.finish()
+    launches = ctx.stats()["kernel_launches"] - launches0
+
+    # ---- timed region 2: end to end through the host-buffer calls
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d = 12 * nverts + 12 * ntris
+    d2h = 0
+    barrier()
+    ev2.record()
+    for _ in range(args.steps):
+        mesh.update_from_ptr(xyz_ptr, idx_ptr)            # b200cd_mesh_update: H2D of vertices + indices
+        if world == 1:
+            ctx.bvh_rebuild(bvh, mesh, params)            # b200cd_bvh_rebuild
+            cnt = ctx.self_collide_into(bvh, host_pairs.data_ptr(), host_pairs.numel(), sorted=True)  # + D2H
+            d2h = 8 * cnt
+        else:
+            merged = runner.step(bvh, mesh, params)
+            if rank == 0:
+                host_pairs[: merged.numel()].copy_(merged, non_blocking=True)
+                d2h = 8 * int(merged.numel())
+            torch.cuda.current_stream().synchronize()
+    ev3.record()
+    barrier()
+    ms_e2e = ev2.elapsed_time(ev3)
+
+    # ---- max over ranks
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        K = args.steps
+        ms_step = ms_total / K
+        value = ntris / ms_step / 1e3
+        e2e_value = ntris / (ms_e2e / K) / 1e3
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        ncand, npairs = int(last.get("candidates", 0)), int(last.get("pairs", 0))
+        abytes = algorithmic_bytes(ntris, nverts, ncand, npairs, int(last.get("sort_passes", 8)))
+        if world > 1:  # per-rank share of the query stages
+            abytes["traverse"] = 64 * ntris + 64 * ntris // world + 8 * ncand
+        stages = {}
+        for s, key in (("morton", "ms_morton"), ("sort", "ms_sort"), ("hierarchy", "ms_hierarchy"), ("refit", "ms_refit"),
+                       ("traverse", "ms_traverse"), ("narrow", "ms_narrow")):
+            ms = acc[key] / K
+            gbs = abytes[s] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            stages[s] = {"kernel": STAGE_KERNEL[s], "ms": round(ms, 4), "algorithmic_bytes": int(abytes[s]),
+                         "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        dominant = max(("morton", "hierarchy", "refit", "traverse", "narrow"), key=lambda s: stages[s]["ms"])
+        sort_launch_ms = stages["sort"]["ms"] / max(int(last.get("sort_passes", 8)), 1)
+        if sort_launch_ms > stages[dominant]["ms"]:
+            dominant = "sort"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(workload, {}).get(dominant)
+        roofline = {"bound": "hbm", "kernel": STAGE_KERNEL[dominant], "stage": dominant,
+                    "achieved": stages[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": stages[dominant]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "launch_ms": stages[dominant]["ms"], "algorithmic_bytes": stages[dominant]["algorithmic_bytes"],
+                    "stages": stages,
+                    "e2e_algorithmic_bytes": int(sum(abytes.values())),
+                    "e2e_frac": round(sum(abytes.values()) / ((acc["ms_build"] + acc["ms_query"]) / K * 1e-3) / 1e9 / peak, 4)
+                    if acc["ms_build"] + acc["ms_query"] > 0 else None}
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "triangles": ntris, "vertices": nverts,
+                       "morton_box": "unit cube" if box else "reference constants (morton.h:45,51,57)",
+                       "key_bits": 63, "pairs": npairs_total,
+                       "parallelism": "single GPU" if world == 1 else f"query-sharded x{world}, replicated BVH, "
+                                      f"block-cyclic chunks of {args.chunk} sorted leaves, NCCL gather + sort on rank 0",
+                       "l2_policy": "inputs larger than L2 (mesh + BVH >> 126 MB); no explicit flush"},
+            "bvh_build_ms": round(acc["ms_build"] / K, 4), "query_ms": round(acc["ms_query"] / K, 4),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(ms_e2e / K, 4)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            vals, info = cpu_reference_run(workload, args.cpu_sample, 1)
+            line["cpu_baseline"] = {"value": round(vals[0], 4), "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                                    "sample": info["sample"], "how": info["how"], "stages_ms": info["stages_ms"],
+                                    "host_cores_available": info["host_cores_available"]}
+        print(json.dumps(line), flush=True)
+
+    bvh.destroy()
+    mesh.destroy()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--chunk", type=int, default=1 << 14, help="sorted leaves per block-cyclic query chunk (N > 1)")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 21, help="triangles in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    workload = args.workload or ("soup16m" if args.gpus == 1 else "sheets64m")
+
+    if args.impl == "reference":
+        run_reference_arm(args, workload)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched by hand: re-exec under torchrun, one rank per GPU (the driver does this itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)]
+        raise SystemExit(subprocess.call(cmd + sys.argv[1:]))
+    run_gpu_arm(args, workload)
+
+
+if __name__ == "__main__":
+    main()

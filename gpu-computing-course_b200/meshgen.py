@@ -48,30 +48,38 @@ def soup(n, h=None, seed=1234, origin=(0.0, 0.0, 0.0), extent=(1.0, 1.0, 1.0), o
     return xyz, idx
 
 
-def _grid_alloc(nx, ny, sheets=1):
-    nv = (nx + 1) * (ny + 1) * sheets
-    nt = 2 * nx * ny * sheets
+def grid_sizes(nx, ny, sheets=1):
+    """(nverts, ntris) of the grid workloads"""
+    return (nx + 1) * (ny + 1) * sheets, 2 * nx * ny * sheets
+
+
+def _grid_alloc(nx, ny, sheets=1, out=None):
+    nv, nt = grid_sizes(nx, ny, sheets)
+    if out is not None:  # caller-owned (e.g. pinned) buffers
+        xyz, idx = out
+        assert xyz.shape == (nv, 3) and xyz.dtype == np.float32 and idx.shape == (nt, 3) and idx.dtype == np.uint32
+        return xyz, idx
     return np.empty((nv, 3), np.float32), np.empty((nt, 3), np.uint32)
 
 
-def cloth_fold(nx=708, ny=708, layers=8, gap_edges=0.5, amp=1.5, wl_edges=12.0, seed=1):
+def cloth_fold(nx=708, ny=708, layers=8, gap_edges=0.5, amp=1.5, wl_edges=12.0, seed=1, out=None):
     """C3: accordion-folded sheet inside the reference Morton box, dense contacts."""
-    xyz, idx = _grid_alloc(nx, ny)
+    xyz, idx = _grid_alloc(nx, ny, out=out)
     lib().mg_cloth_fold(C.c_uint32(nx), C.c_uint32(ny), C.c_uint32(layers), C.c_double(gap_edges), C.c_double(amp),
                         C.c_double(wl_edges), C.c_uint64(seed), _p(xyz, C.c_float), _p(idx, C.c_uint32))
     return xyz, idx
 
 
-def two_sheets(nq=4096, seed=7):
+def two_sheets(nq=4096, seed=7, out=None):
     """C5: two nq x nq-quad sheets intersecting along curves, unit cube."""
-    xyz, idx = _grid_alloc(nq, nq, 2)
+    xyz, idx = _grid_alloc(nq, nq, 2, out=out)
     lib().mg_two_sheets(C.c_uint32(nq), C.c_uint64(seed), _p(xyz, C.c_float), _p(idx, C.c_uint32))
     return xyz, idx
 
 
-def flag(nx=795, nz=794, nfold=3, seed=2021):
+def flag(nx=795, nz=794, nfold=3, seed=2021, out=None):
     """C1/C2 stand-in for the missing flag-2000-changed.obj (1 262 460 triangles by default)."""
-    xyz, idx = _grid_alloc(nx, nz)
+    xyz, idx = _grid_alloc(nx, nz, out=out)
     lib().mg_flag(C.c_uint32(nx), C.c_uint32(nz), C.c_uint32(nfold), C.c_uint64(seed), _p(xyz, C.c_float),
                   _p(idx, C.c_uint32))
     return xyz, idx

@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "load_obj.h"
@@ -166,6 +167,48 @@ REF_API uint64_t ref_collide(void* h) {
         if (m->pairs.size() / 2 - m->npairs < (size_t)n + 16) m->pairs.resize(m->pairs.size() * 2 + 2 * (size_t)n);
         findCollisionIterativeCpu(&m->inner[0], m->leaves[i].triangle, &m->leaves[i].box, m->verts.data(),
                                   &m->npairs, m->pairs.data());
+    }
+    m->ms_query = now_ms() - t0;
+    return m->npairs;
+}
+
+/* Same reference function per query, but the (independent) queries are split over host
+ * threads — OUR parallelisation, used only for bench.py's "all host threads" CPU arm. Each
+ * thread appends to its own buffer through the reference's count/out arguments; the lists are
+ * concatenated afterwards. The reference itself is serial (cpu.cuh:268). */
+REF_API uint64_t ref_collide_mt(void* h, int nthreads) {
+    auto* m = static_cast<RefMesh*>(h);
+    const int n = (int)m->tris.size();
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::vector<unsigned int>> bufs(nthreads);
+    std::vector<unsigned int> counts(nthreads, 0u);
+    double t0 = now_ms();
+    auto work = [&](int t) {
+        std::vector<unsigned int>& buf = bufs[t];
+        buf.assign(1 << 16, 0u);
+        unsigned int cnt = 0;
+        // interleaved blocks of 1024 sorted leaves: neighbouring queries cost about the same
+        for (int blk = t; blk * 1024 < n; blk += nthreads) {
+            const int lo = blk * 1024, hi = lo + 1024 < n ? lo + 1024 : n;
+            for (int i = lo; i < hi; ++i) {
+                if (buf.size() / 2 - cnt < (size_t)n + 16) buf.resize(buf.size() * 2 + 2 * (size_t)n);
+                findCollisionIterativeCpu(&m->inner[0], m->leaves[i].triangle, &m->leaves[i].box, m->verts.data(),
+                                          &cnt, buf.data());
+            }
+        }
+        counts[t] = cnt;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    m->npairs = 0;
+    for (int t = 0; t < nthreads; ++t) m->npairs += counts[t];
+    m->pairs.assign(2 * (size_t)m->npairs + 2, 0u);
+    size_t off = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        memcpy(m->pairs.data() + off, bufs[t].data(), (size_t)counts[t] * 8);
+        off += 2 * (size_t)counts[t];
     }
     m->ms_query = now_ms() - t0;
     return m->npairs;

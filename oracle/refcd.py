@@ -25,6 +25,7 @@ def lib():
         _LIB.ref_load_obj.restype = C.c_void_p
         _LIB.ref_from_arrays.restype = C.c_void_p
         _LIB.ref_collide.restype = C.c_uint64
+        _LIB.ref_collide_mt.restype = C.c_uint64
         _LIB.ref_morton3D.restype = C.c_uint64
         _LIB.ref_morton3D.argtypes = [C.c_double] * 3
         for f in ("ref_free", "ref_num_verts", "ref_num_tris", "ref_get_mesh", "ref_get_sorted", "ref_build",
@@ -93,8 +94,9 @@ class RefMesh:
                             _p(bounded, C.c_uint32), _p(bounds, C.c_double))
         return dict(left=left, right=right, parent=parent, bounded=bounded, bounds=bounds)
 
-    def collide(self):
-        cnt = lib().ref_collide(self.h)
+    def collide(self, nthreads=1):
+        """nthreads > 1: the reference's per-query function over host threads (our parallel loop)"""
+        cnt = lib().ref_collide(self.h) if nthreads <= 1 else lib().ref_collide_mt(self.h, C.c_int(nthreads))
         out = np.empty((cnt, 2), np.uint32)
         if cnt:
             lib().ref_get_pairs(self.h, _p(out, C.c_uint32))

@@ -108,8 +108,8 @@ def test_30bit_keys_with_duplicates(cd, co, ctx, mg):
 
 def test_all_keys_identical(cd, co, ctx, mg):
     # every centroid in one Morton cell: the tree is decided by the index tie-break alone
-    xyz, idx = mg.soup(3000, h=0.2, seed=4, origin=(0.5, 0.5, 0.5), extent=(1e-9, 1e-9, 1e-9))
-    ref, _ = check_all_stages(cd, co, ctx, xyz, idx, key_bits=30, origin=(0, 0, 0), extent=(1, 1, 1))
+    xyz, idx = mg.soup(3000, h=0.08, seed=4)
+    ref, _ = check_all_stages(cd, co, ctx, xyz, idx, key_bits=30, origin=(0, 0, 0), extent=(4096, 4096, 4096))
     assert len(np.unique(ref["keys"])) == 1
 
 
@@ -134,3 +134,78 @@ def test_brute_force_small(cd, co, ctx, mg):
     pairs = ctx.self_collide(bvh)
     assert np.array_equal(pairs, co.brute_force(xyz, idx))
     assert len(pairs) > 100
+
+
+def test_sharded_query_union_equals_full(cd, co, ctx, mg):
+    """each shard reports exactly the pairs whose smaller sorted position it owns (multigpu.owner_of_pairs)"""
+    import importlib
+    mgpu = importlib.import_module("gpu-computing-course_b200.multigpu")
+    xyz, idx = mg.soup(40000, seed=21)
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, cd.make_params(**UNIT))
+    _, _, sids = bvh.download(nodes=False)
+    full = ctx.self_collide(bvh, sorted=True)
+    for nshards, chunk in ((2, 0), (3, 1000), (8, 256), (4, 1 << 14)):
+        owner = mgpu.owner_of_pairs(full, sids, nshards, chunk)
+        parts = []
+        for s in range(nshards):
+            part = ctx.self_collide(bvh, sorted=True, shard=s, nshards=nshards, chunk=chunk)
+            assert np.array_equal(part, full[owner == s]), (nshards, chunk, s)
+            parts.append(part)
+        assert np.array_equal(co.sort_pairs(np.concatenate(parts)), full)
+    with pytest.raises(cd.B200cdError):
+        ctx.self_collide(bvh, shard=2, nshards=2)
+    bvh.destroy()
+    mesh.destroy()
+
+
+def test_rebuild_and_refit_after_vertex_update(cd, co, ctx, mg):
+    xyz, idx = mg.cloth_fold(150, 150)
+    p = cd.default_params()
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, p)
+    first = ctx.self_collide(bvh)
+    # move the vertices a little: refit keeps topology/order, boxes and pair set must follow the new positions
+    rng = np.random.default_rng(3)
+    xyz2 = (xyz + rng.normal(0, 2e-4, xyz.shape)).astype(np.float32)
+    mesh.update(xyz=xyz2)
+    ctx.bvh_refit(bvh, mesh)
+    chk = bvh.validate(mesh)
+    assert chk["box_not_enclosing"] == 0 and chk["wrong_bound_count"] == 0
+    refit_pairs = ctx.self_collide(bvh)
+    op = co.default_params()
+    ref2, _ = co.run(xyz2, idx, op)
+    assert np.array_equal(refit_pairs, ref2)  # the pair set does not depend on tree shape
+    # a full rebuild in place agrees stage by stage with a fresh oracle run
+    ctx.bvh_rebuild(bvh, mesh, p)
+    nodes, sk, si = bvh.download()
+    rk, ri = co.sort_keys(co.morton_keys(xyz2, idx, op))
+    assert np.array_equal(sk, rk) and np.array_equal(si, ri)
+    assert np.array_equal(ctx.self_collide(bvh), ref2)
+    assert not np.array_equal(first, ref2)
+    bvh.destroy()
+    mesh.destroy()
+
+
+def test_capacity_error_reports_true_count(cd, ctx, mg):
+    import ctypes as C
+    xyz, idx = mg.soup(20000, seed=3)
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, cd.make_params(**UNIT))
+    full = ctx.self_collide(bvh)
+    out = np.full((10, 2), 0xFFFFFFFF, np.uint32)
+    cnt = C.c_uint64()
+    rc = cd.lib().b200cd_self_collide(ctx.h, bvh.h, out.ctypes.data_as(C.c_void_p), C.c_uint64(10), C.byref(cnt), C.c_int(1))
+    assert rc == cd.E_CAPACITY and cnt.value == len(full)
+    assert (out == 0xFFFFFFFF).all()  # nothing written (the reference overruns its 500-pair buffer, main.cu:81)
+    rc = cd.lib().b200cd_self_collide(ctx.h, bvh.h, None, C.c_uint64(0), C.byref(cnt), C.c_int(0))
+    assert rc in (cd.OK, cd.E_CAPACITY) and cnt.value == len(full)  # count-only call
+    bvh.destroy()
+    mesh.destroy()
+
+
+def test_bad_vertex_index_is_rejected(cd, ctx):
+    xyz = np.zeros((3, 3), np.float32)
+    with pytest.raises(cd.B200cdError) as e:
+        ctx.mesh_from_arrays(xyz, np.array([[0, 1, 3]], np.uint32))
+    assert e.value.status == cd.E_INVALID
