@@ -308,19 +308,20 @@ int new_mesh(b200cd_ctx* ctx, uint32_t nverts, uint32_t ntris, b200cd_mesh** out
     return B200CD_OK;
 }
 
-int upload(b200cd_ctx* ctx, b200cd_mesh* m, const float* xyz, const uint32_t* idx, bool on_device) {
+// keep_stage: the float3 landing buffer stays allocated for the next frame (b200cd_mesh_update);
+// one-shot uploads (mesh_from_arrays / load_obj) give it back.
+int upload(b200cd_ctx* ctx, b200cd_mesh* m, const float* xyz, const uint32_t* idx, bool on_device, bool keep_stage) {
     cudaStream_t s = ctx->stream;
+    if (xyz && m->nverts && !on_device && !m->d_stage)
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&m->d_stage), 12ull * m->nverts));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_U0], s));
     if (xyz && m->nverts) {
         const float* src = xyz;
-        float* staging = nullptr;
         if (!on_device) {
-            CD_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&staging), 12ull * m->nverts, s));
-            CD_CUDA(ctx, cudaMemcpyAsync(staging, xyz, 12ull * m->nverts, cudaMemcpyHostToDevice, s));
-            src = staging;
+            CD_CUDA(ctx, cudaMemcpyAsync(m->d_stage, xyz, 12ull * m->nverts, cudaMemcpyHostToDevice, s));
+            src = m->d_stage;
         }
         launch_expand_verts(src, m->d_verts, m->nverts, s);
-        if (staging) CD_CUDA(ctx, cudaFreeAsync(staging, s));
     }
     if (idx && m->ntris)
         CD_CUDA(ctx, cudaMemcpyAsync(m->d_idx, idx, 12ull * m->ntris, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
@@ -332,6 +333,10 @@ int upload(b200cd_ctx* ctx, b200cd_mesh* m, const float* xyz, const uint32_t* id
     CD_CUDA(ctx, cudaStreamSynchronize(s));  // the caller may free / reuse its buffers on return
     CD_CUDA(ctx, cudaGetLastError());
     ctx->stats.ms_upload = ev_ms(ctx, EV_U0, EV_U1);
+    if (!keep_stage && m->d_stage) {
+        cudaFree(m->d_stage);
+        m->d_stage = nullptr;
+    }
     if (idx && ctx->h_scalars[32]) return set_error(ctx, B200CD_E_INVALID, "triangle references a vertex index >= nverts");
     return B200CD_OK;
 }
@@ -345,7 +350,7 @@ API int b200cd_mesh_from_arrays(b200cd_ctx* ctx, const float* xyz, uint32_t nver
     b200cd_mesh* m = nullptr;
     int rc = new_mesh(ctx, nverts, ntris, &m);
     if (rc != B200CD_OK) return rc;
-    rc = upload(ctx, m, xyz, tri_idx, false);
+    rc = upload(ctx, m, xyz, tri_idx, false, false);
     if (rc != B200CD_OK) {
         b200cd_mesh_destroy(m);
         return rc;
@@ -362,7 +367,7 @@ API int b200cd_mesh_from_device(b200cd_ctx* ctx, const void* d_xyz, uint32_t nve
     b200cd_mesh* m = nullptr;
     int rc = new_mesh(ctx, nverts, ntris, &m);
     if (rc != B200CD_OK) return rc;
-    rc = upload(ctx, m, static_cast<const float*>(d_xyz), static_cast<const uint32_t*>(d_tri_idx), true);
+    rc = upload(ctx, m, static_cast<const float*>(d_xyz), static_cast<const uint32_t*>(d_tri_idx), true, false);
     if (rc != B200CD_OK) {
         b200cd_mesh_destroy(m);
         return rc;
@@ -374,7 +379,7 @@ API int b200cd_mesh_from_device(b200cd_ctx* ctx, const void* d_xyz, uint32_t nve
 API int b200cd_mesh_update(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, const uint32_t* tri_idx, int on_device) {
     if (!ctx || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
     DeviceGuard g(ctx->device);
-    return upload(ctx, mesh, xyz, tri_idx, on_device != 0);
+    return upload(ctx, mesh, xyz, tri_idx, on_device != 0, true);
 }
 
 API int b200cd_mesh_info(const b200cd_mesh* mesh, uint32_t* nverts, uint32_t* ntris) {
@@ -406,6 +411,7 @@ API int b200cd_mesh_destroy(b200cd_mesh* mesh) {
     cudaStreamSynchronize(mesh->ctx->stream);
     cudaFree(mesh->d_verts);
     cudaFree(mesh->d_idx);
+    cudaFree(mesh->d_stage);
     delete mesh;
     return B200CD_OK;
 }

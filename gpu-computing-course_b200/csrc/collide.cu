@@ -22,7 +22,8 @@
 //   - traversal only emits CANDIDATES (AABB-overlapping leaf pairs) into a compact
 //     list: per-warp staging in shared memory filled with ballots (no atomics),
 //     flushed with one global atomicAdd per >=32 candidates. The divergent fp64
-//     SAT runs afterwards in its own kernel, one candidate per thread, dense.
+//     SAT runs afterwards in its own kernel, in two warp-dense stages (face-normal axes first,
+//     survivors compacted through a per-warp shared-memory queue, then the other 15 axes).
 //   - results are appended the same way (warp-aggregated atomic).
 // -fmad=false: every double operation rounds separately, like the host reference.
 #include "common.cuh"
@@ -166,18 +167,31 @@ __device__ __forceinline__ bool project6(const D3& ax, const D3& p1, const D3& p
     return true;
 }
 
-// tri_contact.cuh:19-78. The 17 axis tests are a pure conjunction, so testing the
-// cheap face normals first and bailing out early cannot change the result.
-__device__ bool tri_contact(const D3& P1, const D3& P2, const D3& P3, const D3& Q1, const D3& Q2, const D3& Q3) {
+// tri_contact.cuh:19-78, split in two. The 17 axis tests are a pure conjunction, so their order
+// and any early exit cannot change the result; only each expression's own operation order
+// matters, and that is kept literal. Stage A = the two face-normal axes (tri_contact.cuh:58-59),
+// stage B = the nine edge-edge axes and the six in-plane edge normals (tri_contact.cuh:61-75).
+struct SatInput {
+    D3 p2, p3, q1, q2, q3;  // everything translated by P1; p1 is exactly (0,0,0) (tri_contact.cuh:21-26)
+};
+__device__ __forceinline__ SatInput sat_input(const D3& P1, const D3& P2, const D3& P3, const D3& Q1, const D3& Q2,
+                                              const D3& Q3) {
+    return {P2 - P1, P3 - P1, Q1 - P1, Q2 - P1, Q3 - P1};
+}
+__device__ __forceinline__ bool sat_stage_a(const SatInput& t) {
     const D3 p1 = {0.0, 0.0, 0.0};
-    const D3 p2 = P2 - P1, p3 = P3 - P1;
-    const D3 q1 = Q1 - P1, q2 = Q2 - P1, q3 = Q3 - P1;
+    const D3 e1 = t.p2 - p1, e2 = t.p3 - t.p2;
+    const D3 f1 = t.q2 - t.q1, f2 = t.q3 - t.q2;
+    const D3 n1 = cross(e1, e2);
+    if (!project3(n1, t.q1, t.q2, t.q3)) return false;
+    const D3 m1 = cross(f1, f2);
+    return project3(m1, neg(t.q1), t.p2 - t.q1, t.p3 - t.q1);
+}
+__device__ __forceinline__ bool sat_stage_b(const SatInput& t) {
+    const D3 p1 = {0.0, 0.0, 0.0};
+    const D3 &p2 = t.p2, &p3 = t.p3, &q1 = t.q1, &q2 = t.q2, &q3 = t.q3;
     const D3 e1 = p2 - p1, e2 = p3 - p2, e3 = p1 - p3;
     const D3 f1 = q2 - q1, f2 = q3 - q2, f3 = q1 - q3;
-    const D3 n1 = cross(e1, e2);
-    if (!project3(n1, q1, q2, q3)) return false;
-    const D3 m1 = cross(f1, f2);
-    if (!project3(m1, neg(q1), p2 - q1, p3 - q1)) return false;
     if (!project6(cross(e1, f1), p1, p2, p3, q1, q2, q3)) return false;
     if (!project6(cross(e1, f2), p1, p2, p3, q1, q2, q3)) return false;
     if (!project6(cross(e1, f3), p1, p2, p3, q1, q2, q3)) return false;
@@ -187,6 +201,7 @@ __device__ bool tri_contact(const D3& P1, const D3& P2, const D3& P3, const D3& 
     if (!project6(cross(e3, f1), p1, p2, p3, q1, q2, q3)) return false;
     if (!project6(cross(e3, f2), p1, p2, p3, q1, q2, q3)) return false;
     if (!project6(cross(e3, f3), p1, p2, p3, q1, q2, q3)) return false;
+    const D3 n1 = cross(e1, e2), m1 = cross(f1, f2);
     if (!project6(cross(e1, n1), p1, p2, p3, q1, q2, q3)) return false;
     if (!project6(cross(e2, n1), p1, p2, p3, q1, q2, q3)) return false;
     if (!project6(cross(e3, n1), p1, p2, p3, q1, q2, q3)) return false;
@@ -211,19 +226,65 @@ __device__ __forceinline__ Tri load_tri(const LeafRec* __restrict__ leaves, uint
     t.id = __float_as_uint(r3.x);
     return t;
 }
+// vertices only (stage B re-reads the two records; they are L1/L2-hot)
+__device__ __forceinline__ void load_verts(const LeafRec* __restrict__ leaves, uint32_t pos, D3& v0, D3& v1, D3& v2,
+                                           uint32_t& id) {
+    const float4* r = reinterpret_cast<const float4*>(leaves + pos);
+    const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+    v0 = {(double)r0.x, (double)r0.y, (double)r0.z};
+    v1 = {(double)r0.w, (double)r1.x, (double)r1.y};
+    v2 = {(double)r1.z, (double)r1.w, (double)r2.x};
+    id = __float_as_uint(r3.x);
+}
 
-__global__ void __launch_bounds__(256)
+constexpr int NR_THREADS = 256;
+constexpr int NR_WARPS = NR_THREADS / 32;
+constexpr int NR_QUEUE = 64;  // per-warp survivors of stage A waiting for stage B (<= 31 carried + 32 new)
+
+// Stage B on up to 32 queued (P position, Q position) entries, one per lane; contacts are appended
+// with one atomic per warp.
+__device__ __forceinline__ void narrow_stage_b(const LeafRec* __restrict__ leaves, const uint2* wq, uint32_t count,
+                                               uint32_t lane, uint2* __restrict__ out, uint64_t out_cap,
+                                               unsigned long long* __restrict__ counters) {
+    bool hit = false;
+    uint2 res = make_uint2(0, 0);
+    if (lane < count) {
+        const uint2 e = wq[lane];  // x = sorted position of the lower-ID triangle (P), y = of the higher-ID one (Q)
+        D3 P1, P2, P3, Q1, Q2, Q3;
+        load_verts(leaves, e.x, P1, P2, P3, res.x);
+        load_verts(leaves, e.y, Q1, Q2, Q3, res.y);
+        hit = sat_stage_b(sat_input(P1, P2, P3, Q1, Q2, Q3));
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        unsigned long long o = 0;
+        if (lane == 0) o = atomicAdd(counters + 1, (unsigned long long)__popc(m));
+        o = __shfl_sync(0xffffffffu, o, 0) + __popc(m & ((1u << lane) - 1u));
+        if (hit && o < out_cap) out[o] = res;
+    }
+}
+
+// Two-stage narrow phase. Most candidates (AABB-overlapping leaf pairs) are rejected by the two
+// face-normal axes; running all 17 axes per thread leaves a warp with a handful of live lanes.
+// So: stage A (filters + 2 axes) runs dense over the candidate list, its survivors are
+// compacted into a per-warp shared-memory queue by ballot, and stage B (15 axes) runs whenever
+// 32 survivors are waiting - both stages execute with (nearly) full warps.
+__global__ void __launch_bounds__(NR_THREADS, 2)
 narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand, uint64_t cand_cap,
               uint2* __restrict__ out, uint64_t out_cap, unsigned long long* __restrict__ counters) {
+    __shared__ uint2 queue[NR_WARPS][NR_QUEUE];
     const unsigned long long total = min((unsigned long long)cand_cap, counters[0]);
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint2* wq = queue[warp];
+    uint32_t queued = 0;  // warp-uniform
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     // warp-uniform trip count so the ballots below are full-warp
     const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
     for (unsigned long long base = first; base < total; base += stride) {
         const unsigned long long i = base + lane;
-        bool hit = false;
-        uint2 res = make_uint2(0, 0);
+        bool alive = false;
+        uint2 entry = make_uint2(0, 0);
         if (i < total) {
             const uint2 c = __ldcs(cand + i);
             const Tri a = load_tri(leaves, c.x), b = load_tri(leaves, c.y);
@@ -232,18 +293,21 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
                                 a.i1 == b.i2 || a.i2 == b.i0 || a.i2 == b.i1 || a.i2 == b.i2;
             if (!shared && a.id != b.id) {
                 // tri_contact.cuh:81-86: P is the lower-ID triangle
-                if (a.id < b.id) { hit = tri_contact(a.v0, a.v1, a.v2, b.v0, b.v1, b.v2); res = make_uint2(a.id, b.id); }
-                else             { hit = tri_contact(b.v0, b.v1, b.v2, a.v0, a.v1, a.v2); res = make_uint2(b.id, a.id); }
+                if (a.id < b.id) { alive = sat_stage_a(sat_input(a.v0, a.v1, a.v2, b.v0, b.v1, b.v2)); entry = make_uint2(c.x, c.y); }
+                else             { alive = sat_stage_a(sat_input(b.v0, b.v1, b.v2, a.v0, a.v1, a.v2)); entry = make_uint2(c.y, c.x); }
             }
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-            unsigned long long o = 0;
-            if (lane == 0) o = atomicAdd(counters + 1, (unsigned long long)__popc(m));
-            o = __shfl_sync(0xffffffffu, o, 0) + __popc(m & ((1u << lane) - 1u));
-            if (hit && o < out_cap) out[o] = res;
+        const uint32_t m = __ballot_sync(0xffffffffu, alive);
+        if (alive) wq[queued + __popc(m & lt)] = entry;
+        queued += __popc(m);
+        __syncwarp();
+        if (queued >= 32) {
+            narrow_stage_b(leaves, wq + (queued - 32), 32, lane, out, out_cap, counters);  // newest 32: the rest stays at the front
+            queued -= 32;
+            __syncwarp();
         }
     }
+    if (queued) narrow_stage_b(leaves, wq, queued, lane, out, out_cap, counters);
 }
 
 }  // namespace
@@ -260,7 +324,7 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, uint32_t n, 
 
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s) {
-    narrow_kernel<<<sms * 8, 256, 0, s>>>(d_leaves, d_cand, cand_cap, d_out, out_cap, d_counters);
+    narrow_kernel<<<sms * 2 * 4, NR_THREADS, 0, s>>>(d_leaves, d_cand, cand_cap, d_out, out_cap, d_counters);
     count_launch();
 }
 

@@ -62,6 +62,7 @@ struct b200cd_mesh {
     uint32_t nverts = 0, ntris = 0;
     float4* d_verts = nullptr;   // nverts float4 (xyz, w = 0)
     uint32_t* d_idx = nullptr;   // ntris * 3
+    float* d_stage = nullptr;    // nverts * 3: H2D landing area of b200cd_mesh_update (kept between frames)
 };
 
 struct b200cd_bvh {
