@@ -41,7 +41,8 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("ms_upload", "ms_morton", "ms_sort", "ms_hierarchy", "ms_refit", "ms_build",
                                          "ms_traverse", "ms_narrow", "ms_pair_sort", "ms_query", "ms_download")] + \
                [("ntris", C.c_uint32), ("nverts", C.c_uint32), ("candidates", C.c_uint64), ("pairs", C.c_uint64),
-                ("sort_passes", C.c_uint32), ("query_retries", C.c_uint32), ("kernel_launches", C.c_uint64)]
+                ("sort_passes", C.c_uint32), ("query_retries", C.c_uint32), ("kernel_launches", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("warp_steps", C.c_uint64), ("start_entries", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -70,6 +70,8 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_leaves);
     cudaFree(b->d_root_box);
     cudaFree(b->d_cand);
+    cudaFree(b->d_entries);
+    cudaFree(b->d_entry_count);
     cudaFree(b->d_out);
     cudaFree(b->d_out_tmp);
     cudaFree(b->d_counters);
@@ -105,8 +107,8 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
     A(dev_alloc(ctx, &b->d_pairs, n));
     A(dev_alloc(ctx, &b->d_leaves, n));
     A(dev_alloc(ctx, &b->d_root_box, 8));
-    A(dev_alloc(ctx, &b->d_counters, 4));
-    if (rc == B200CD_OK && cudaMallocHost(reinterpret_cast<void**>(&b->h_counters), 4 * sizeof(unsigned long long)) != cudaSuccess)
+    A(dev_alloc(ctx, &b->d_counters, 8));
+    if (rc == B200CD_OK && cudaMallocHost(reinterpret_cast<void**>(&b->h_counters), 8 * sizeof(unsigned long long)) != cudaSuccess)
         rc = set_error(ctx, B200CD_E_NOMEM, "cudaMallocHost failed");
     if (rc != B200CD_OK) {
         free_bvh_buffers(b);
@@ -639,8 +641,11 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
         ctx->stats.ms_traverse = ctx->stats.ms_narrow = ctx->stats.ms_pair_sort = ctx->stats.ms_query = 0.f;
         return B200CD_OK;
     }
-    // query threads of this shard: whole chunks c = shard, shard + nshards, ...
+    // query threads of this shard: whole chunks c = shard, shard + nshards, ... A chunk is a whole number of
+    // traversal blocks (B200CD_QUERY_BLOCK consecutive sorted leaves), so it is rounded up to a multiple of that.
     if (chunk == 0) chunk = (n + nshards - 1) / nshards;
+    if (chunk > 0xffffff00u) return set_error(ctx, B200CD_E_INVALID, "chunk too large");
+    chunk = (chunk + B200CD_QUERY_BLOCK - 1) / B200CD_QUERY_BLOCK * B200CD_QUERY_BLOCK;
     const uint64_t nchunks = ((uint64_t)n + chunk - 1) / chunk;
     const uint64_t my_chunks = nchunks > shard ? (nchunks - shard + nshards - 1) / nshards : 0;
     const uint64_t nquery64 = my_chunks * chunk;
@@ -652,20 +657,32 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
     if (rc == B200CD_OK) rc = grow(ctx, &b->d_out, &b->out_cap, std::max<uint64_t>(b->out_cap, std::max<uint64_t>(nquery / 2 + 4096, hint)));
     if (rc == B200CD_OK && sorted) rc = grow(ctx, &b->d_out_tmp, &b->out_tmp_cap, b->out_cap);
     if (rc != B200CD_OK) return rc;
+    const uint64_t qblocks = ((uint64_t)nquery + B200CD_QUERY_BLOCK - 1) / B200CD_QUERY_BLOCK;
+    if (qblocks > b->entry_blocks) {
+        cudaFree(b->d_entries);
+        cudaFree(b->d_entry_count);
+        b->d_entries = nullptr;
+        b->d_entry_count = nullptr;
+        b->entry_blocks = 0;
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entries), qblocks * B200CD_MAX_ENTRIES * sizeof(Node32)));
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entry_count), qblocks * sizeof(uint32_t)));
+        b->entry_blocks = qblocks;
+    }
 
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q0], s));
     bool need_broad = true;
     for (int attempt = 0; attempt < 4; ++attempt) {
         if (need_broad) {
-            CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(unsigned long long), s));
-            launch_broad(b->d_pairs, b->d_leaves, n, shard, nshards, chunk, nquery, b->d_cand, b->cand_cap, b->d_counters, s);
+            CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
+            launch_broad(b->d_pairs, b->d_leaves, n, shard, nshards, chunk, nquery, b->d_entries, b->d_entry_count, b->d_cand,
+                         b->cand_cap, b->d_counters, s);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
         } else {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), s));
         }
         launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s);
         CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q2], s));
-        CD_CUDA(ctx, cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CD_CUDA(ctx, cudaMemcpyAsync(b->h_counters, b->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CD_CUDA(ctx, cudaStreamSynchronize(s));
         CD_CUDA(ctx, cudaGetLastError());
         const uint64_t ncand = b->h_counters[0], npair = b->h_counters[1];
@@ -687,6 +704,9 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
         }
         ctx->stats.candidates = ncand;
         ctx->stats.pairs = npair;
+        ctx->stats.nodes_visited = b->h_counters[3];
+        ctx->stats.warp_steps = b->h_counters[4];
+        ctx->stats.start_entries = b->h_counters[5];
         *count_out = npair;
         if (sorted && npair > 1) {
             rc = grow(ctx, &b->d_out_tmp, &b->out_tmp_cap, b->out_cap);

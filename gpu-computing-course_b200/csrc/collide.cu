@@ -19,6 +19,9 @@
 //     so this halves the traversal without changing the set; the narrow phase is
 //     still called as (lower ID, higher ID) because the SAT is not symmetric in
 //     floating point.
+//   - queries do not start at the root: one thread per block of 256 consecutive sorted leaves
+//     walks the block's ancestors once (entry_kernel) and every query of the block starts at
+//     the handful of subtrees that tile "leaves after me" and overlap the block's union box.
 //   - traversal only emits CANDIDATES (AABB-overlapping leaf pairs) into a compact
 //     list: per-warp staging in shared memory filled with ballots (no atomics),
 //     flushed with one global atomicAdd per >=32 candidates. The divergent fp64
@@ -32,10 +35,11 @@ namespace b200cd {
 
 namespace {
 
-constexpr int BR_THREADS = 128;
+constexpr int BR_THREADS = B200CD_QUERY_BLOCK;  // one block = 256 CONSECUTIVE sorted leaves
 constexpr int BR_WARPS = BR_THREADS / 32;
 constexpr int BR_QUEUE = 128;   // per-warp candidate staging (uint2 each)
 constexpr int BR_FLUSH = 64;    // flush when at least this many are staged (<= 64 arrive per step)
+constexpr int BR_ENTRIES = B200CD_MAX_ENTRIES;
 
 constexpr unsigned long long ERR_STACK = 1ull;
 
@@ -49,50 +53,217 @@ __device__ __forceinline__ bool overlap(const float qlo[3], const float qhi[3], 
 __device__ __forceinline__ float min3_ref(float a, float b, float c) { float t = a; if (b < t) t = b; if (c < t) t = c; return t; }
 __device__ __forceinline__ float max3_ref(float a, float b, float c) { float t = a; if (b > t) t = b; if (c > t) t = c; return t; }
 
-// ---------------------------------------------------------------- K5
+// which sorted-leaf position does query slot t of this shard own (block-cyclic chunks)
+__device__ __forceinline__ uint64_t query_position(uint32_t t, uint32_t shard, uint32_t nshards, uint32_t chunk) {
+    const uint32_t c = t / chunk, w = t - c * chunk;
+    return ((uint64_t)c * nshards + shard) * chunk + w;
+}
+
+struct Child {
+    float4 a, b;  // a = lo.xyz, hi.x ; b = hi.yz, link, last
+    __device__ __forceinline__ int link() const { return __float_as_int(b.z); }
+    __device__ __forceinline__ int last() const { return __float_as_int(b.w); }
+};
+__device__ __forceinline__ void load_children(const NodePair* __restrict__ pairs, int node, Child& l, Child& r) {
+    const float4* p = reinterpret_cast<const float4*>(pairs + node);
+    l.a = __ldg(p); l.b = __ldg(p + 1); r.a = __ldg(p + 2); r.b = __ldg(p + 3);
+}
+
+// ---------------------------------------------------------------- K5a: entry lists
+// Every query of a block [q0, q1] of consecutive sorted leaves needs the leaves j > q whose box
+// overlaps its own. Walking down from the root, almost all of a query's node visits are its own
+// ancestors (collision.cuh:19-71 starts every query at the root). The ancestors are the same for
+// the whole block, so ONE thread per block walks them once and records the maximal subtrees that
+// tile the two target sets:
+//     inside  (q0, q1]   : the canonical decomposition of the block's own range
+//     beyond  (q1, n-1]  : the right siblings along the root -> q1 path
+// (at most two root-to-leaf paths, so O(depth) entries). The traversal kernel then starts each
+// query at those entries instead of at the root. Entry = the child's Node32 as stored in its
+// parent. The emitted candidate SET is unchanged: the entries cover exactly the leaves > q0, the
+// per-query rule (subtree end > q, strict box overlap) is applied to each entry and below it.
+__global__ void __launch_bounds__(128)
+entry_kernel(const NodePair* __restrict__ pairs, uint32_t n, uint32_t shard, uint32_t nshards, uint32_t chunk,
+             uint32_t nblocks, Node32* __restrict__ entries, uint32_t* __restrict__ entry_count) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const uint64_t p0 = query_position(b * BR_THREADS, shard, nshards, chunk);
+    uint32_t cnt = 0;
+    bool overflow = false;
+    Child* out = reinterpret_cast<Child*>(entries + (size_t)b * BR_ENTRIES);
+    auto add = [&](const Child& c) {
+        if (cnt < (uint32_t)BR_ENTRIES) out[cnt++] = c; else overflow = true;
+    };
+    if (p0 + 1 < n) {  // the very last leaf has no partner after it
+        const int q0 = (int)p0;
+        const int q1 = (int)min((uint64_t)n - 1, p0 + BR_THREADS - 1);
+        int node = 0, F = 0;
+        Child l, r;
+        bool split_found = false;
+        // common part of the two paths
+        while (true) {
+            load_children(pairs, node, l, r);
+            const int g = l.last();
+            if (q1 <= g) {            // both ends in the left child: the right child lies entirely beyond q1
+                add(r);
+                if (l.link() < 0) break;
+                node = l.link();
+            } else if (q0 > g) {      // both ends in the right child: the left child lies entirely before q0
+                if (r.link() < 0) break;
+                node = r.link();
+                F = g + 1;
+            } else {                  // q0 <= g < q1: paths part here
+                split_found = true;
+                break;
+            }
+        }
+        if (split_found) {
+            // walk towards q0 inside the left child [F, g]: right siblings lie inside (q0, q1]
+            Child cur = l, a, c;
+            int curF = F;
+            while (true) {
+                if (curF >= q0 || cur.link() < 0) {  // whole subtree inside the block's range (leaf q0 itself: harmless)
+                    add(cur);
+                    break;
+                }
+                load_children(pairs, cur.link(), a, c);
+                if (q0 <= a.last()) { add(c); cur = a; }
+                else { curF = a.last() + 1; cur = c; }
+            }
+            // walk towards q1 inside the right child: left siblings lie inside the range, right siblings beyond it
+            cur = r;
+            while (true) {
+                if (cur.last() <= q1 || cur.link() < 0) {
+                    add(cur);
+                    break;
+                }
+                load_children(pairs, cur.link(), a, c);
+                if (q1 <= a.last()) { add(c); cur = a; }
+                else { add(a); cur = c; }
+            }
+        }
+        if (overflow) {  // pathologically deep tree: fall back to "start at the root" (two entries = the root's children)
+            load_children(pairs, 0, l, r);
+            out[0] = l; out[1] = r;
+            cnt = 2;
+        }
+    }
+    entry_count[b] = cnt;
+}
+
+// ---------------------------------------------------------------- K5b: traversal
 __global__ void __launch_bounds__(BR_THREADS)
 broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, uint32_t n, uint32_t shard,
-             uint32_t nshards, uint32_t chunk, uint32_t nquery, uint2* __restrict__ cand, uint64_t cand_cap,
+             uint32_t nshards, uint32_t chunk, uint32_t nquery, const Node32* __restrict__ entries,
+             const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand, uint64_t cand_cap,
              unsigned long long* __restrict__ counters) {
     __shared__ uint2 queue[BR_WARPS][BR_QUEUE];
+    __shared__ Child s_entry[BR_ENTRIES];
+    __shared__ float s_red[BR_WARPS][6];
+    __shared__ uint32_t s_nentry;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     uint2* wq = queue[warp];
     uint32_t staged = 0;  // warp-uniform
+    if (threadIdx.x == 0) s_nentry = 0;
 
-    // which query (sorted leaf position) this thread owns: block-cyclic over shards
+    // this thread's query (sorted leaf position)
     const uint32_t t = blockIdx.x * BR_THREADS + threadIdx.x;
     uint32_t q = 0xffffffffu;
     if (t < nquery) {
-        uint32_t c = t / chunk, w = t - c * chunk;
-        uint64_t qq = ((uint64_t)c * nshards + shard) * chunk + w;
-        if (qq < n) q = (uint32_t)qq;
+        const uint64_t qq = query_position(t, shard, nshards, chunk);
+        if (qq + 1 < n) q = (uint32_t)qq;  // the last leaf has no partner with a larger position
     }
-    float qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
-    int node = -1;
-    if (q != 0xffffffffu && q + 1 < n) {  // the last leaf has no partner with a larger position
+    const float inf = __int_as_float(0x7f800000);
+    float qlo[3] = {inf, inf, inf}, qhi[3] = {-inf, -inf, -inf};
+    if (q != 0xffffffffu) {
         const float4* r = reinterpret_cast<const float4*>(leaves + q);
         const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
         // v0 = r0.xyz, v1 = (r0.w, r1.x, r1.y), v2 = (r1.z, r1.w, r2.x); box.cuh:13-22
         qlo[0] = min3_ref(r0.x, r0.w, r1.z); qhi[0] = max3_ref(r0.x, r0.w, r1.z);
         qlo[1] = min3_ref(r0.y, r1.x, r1.w); qhi[1] = max3_ref(r0.y, r1.x, r1.w);
         qlo[2] = min3_ref(r0.z, r1.y, r2.x); qhi[2] = max3_ref(r0.z, r1.y, r2.x);
-        node = 0;
     }
+    // union box of the block's queries
+    float ulo[3], uhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ulo[k] = qlo[k]; uhi[k] = qhi[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ulo[k] = fminf(ulo[k], __shfl_xor_sync(0xffffffffu, ulo[k], o));
+            uhi[k] = fmaxf(uhi[k], __shfl_xor_sync(0xffffffffu, uhi[k], o));
+        }
+        if (lane == 0) { s_red[warp][k] = ulo[k]; s_red[warp][3 + k] = uhi[k]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ulo[k] = s_red[0][k]; uhi[k] = s_red[0][3 + k];
+#pragma unroll
+        for (int w = 1; w < BR_WARPS; ++w) { ulo[k] = fminf(ulo[k], s_red[w][k]); uhi[k] = fmaxf(uhi[k], s_red[w][3 + k]); }
+    }
+    // keep the entries whose box overlaps the union box (order is irrelevant)
+    const uint32_t nent = __ldg(entry_count + blockIdx.x);
+    if (threadIdx.x < nent) {
+        const float4* e = reinterpret_cast<const float4*>(entries + (size_t)blockIdx.x * BR_ENTRIES + threadIdx.x);
+        Child c;
+        c.a = __ldg(e); c.b = __ldg(e + 1);
+        if (overlap(ulo, uhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y)) s_entry[atomicAdd(&s_nentry, 1u)] = c;
+    }
+    __syncthreads();
+    const uint32_t nkeep = s_nentry;
+
     int stack[B200CD_MAX_STACK];
     int sp = 0;
     bool overflow = false;
 
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counters + 0, (unsigned long long)staged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < staged; i += 32)
+            if (base + i < cand_cap) __stcs(cand + base + i, wq[i]);
+        staged = 0;
+        __syncwarp();
+    };
+    // stage (q, leaf) candidates of the whole warp: positions by ballot, no atomics
+    auto stage2 = [&](bool candL, int leafL, bool candR, int leafR) {
+        const uint32_t bL = __ballot_sync(0xffffffffu, candL), bR = __ballot_sync(0xffffffffu, candR);
+        if (bL | bR) {
+            const uint32_t nL = __popc(bL);
+            if (candL) wq[staged + __popc(bL & lt)] = make_uint2(q, (uint32_t)leafL);
+            if (candR) wq[staged + nL + __popc(bR & lt)] = make_uint2(q, (uint32_t)leafR);
+            staged += nL + __popc(bR);
+            __syncwarp();
+            if (staged >= BR_FLUSH) flush();
+        }
+    };
+
+    // start points: every kept entry that ends after q and overlaps q's box (warp-uniform loop)
+    for (uint32_t e = 0; e < nkeep; ++e) {
+        const Child c = s_entry[e];
+        const bool hit = q != 0xffffffffu && c.last() > (int)q &&
+                         overlap(qlo, qhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y);
+        const int link = c.link();
+        if (hit && link >= 0) {
+            if (sp < B200CD_MAX_STACK) stack[sp++] = link; else overflow = true;
+        }
+        stage2(hit && link < 0, ~link, false, 0);
+    }
+    int node = sp > 0 ? stack[--sp] : -1;
+    uint32_t visits = 0, iters = 0;  // traversal statistics (b200cd_stats::nodes_visited / warp_steps)
+
     while (__any_sync(0xffffffffu, node >= 0)) {
         bool candL = false, candR = false;
         int leafL = 0, leafR = 0;
+        ++iters;
         if (node >= 0) {
-            const float4* p = reinterpret_cast<const float4*>(pairs + node);
-            const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
-            const int linkL = __float_as_int(a1.z), lastL = __float_as_int(a1.w);
-            const int linkR = __float_as_int(b1.z), lastR = __float_as_int(b1.w);
-            const bool hitL = lastL > (int)q && overlap(qlo, qhi, a0.x, a0.y, a0.z, a0.w, a1.x, a1.y);
-            const bool hitR = lastR > (int)q && overlap(qlo, qhi, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+            ++visits;
+            Child l, r;
+            load_children(pairs, node, l, r);
+            const int linkL = l.link(), linkR = r.link();
+            const bool hitL = l.last() > (int)q && overlap(qlo, qhi, l.a.x, l.a.y, l.a.z, l.a.w, l.b.x, l.b.y);
+            const bool hitR = r.last() > (int)q && overlap(qlo, qhi, r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y);
             candL = hitL && linkL < 0; leafL = ~linkL;
             candR = hitR && linkR < 0; leafR = ~linkR;
             const bool goL = hitL && linkL >= 0, goR = hitR && linkR >= 0;
@@ -107,33 +278,16 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
                 node = sp > 0 ? stack[--sp] : -1;
             }
         }
-        // stage candidates (q, leaf) — positions by ballot, no atomics
-        const uint32_t bL = __ballot_sync(0xffffffffu, candL), bR = __ballot_sync(0xffffffffu, candR);
-        if (bL | bR) {
-            const uint32_t nL = __popc(bL);
-            if (candL) wq[staged + __popc(bL & lt)] = make_uint2(q, (uint32_t)leafL);
-            if (candR) wq[staged + nL + __popc(bR & lt)] = make_uint2(q, (uint32_t)leafR);
-            staged += nL + __popc(bR);
-            __syncwarp();
-            if (staged >= BR_FLUSH) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(counters + 0, (unsigned long long)staged);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                for (uint32_t i = lane; i < staged; i += 32)
-                    if (base + i < cand_cap) __stcs(cand + base + i, wq[i]);
-                staged = 0;
-                __syncwarp();
-            }
-        }
+        stage2(candL, leafL, candR, leafR);
     }
-    if (staged) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counters + 0, (unsigned long long)staged);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (uint32_t i = lane; i < staged; i += 32)
-            if (base + i < cand_cap) __stcs(cand + base + i, wq[i]);
-    }
+    if (staged) flush();
     if (overflow) atomicOr(counters + 2, ERR_STACK);
+    visits = __reduce_add_sync(0xffffffffu, visits);
+    if (lane == 0) {
+        atomicAdd(counters + 3, (unsigned long long)visits);
+        atomicAdd(counters + 4, (unsigned long long)iters);
+        atomicAdd(counters + 5, (unsigned long long)nkeep);
+    }
 }
 
 // ---------------------------------------------------------------- K6
@@ -313,12 +467,14 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
 }  // namespace
 
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, uint32_t n, uint32_t shard, uint32_t nshards,
-                  uint32_t chunk, uint32_t nquery, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
-                  cudaStream_t s) {
+                  uint32_t chunk, uint32_t nquery, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
+                  uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s) {
     if (n < 2 || nquery == 0) return;
-    uint32_t blocks = (nquery + BR_THREADS - 1) / BR_THREADS;
-    broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, d_cand, cand_cap,
-                                               d_counters);
+    const uint32_t blocks = (nquery + BR_THREADS - 1) / BR_THREADS;
+    entry_kernel<<<(blocks + 127) / 128, 128, 0, s>>>(d_pairs, n, shard, nshards, chunk, blocks, d_entries, d_entry_count);
+    count_launch();
+    broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, d_entries,
+                                               d_entry_count, d_cand, cand_cap, d_counters);
     count_launch();
 }
 

@@ -8,6 +8,8 @@
 #include "b200cd.h"
 
 #define B200CD_MAX_STACK 96  // traversal stack entries per query (tree depth <= 60 key bits + tie-break)
+#define B200CD_QUERY_BLOCK 256  // consecutive sorted leaves per traversal block (query chunks are multiples of this)
+#define B200CD_MAX_ENTRIES 64   // start subtrees recorded per traversal block
 
 namespace b200cd {
 
@@ -85,6 +87,9 @@ struct b200cd_bvh {
     b200cd::LeafRec* d_leaves = nullptr;  // n
     float* d_root_box = nullptr;       // 6 floats
     // query
+    b200cd::Node32* d_entries = nullptr;  // [blocks][B200CD_MAX_ENTRIES] traversal start subtrees
+    uint32_t* d_entry_count = nullptr;    // [blocks]
+    uint64_t entry_blocks = 0;
     uint2* d_cand = nullptr;  uint64_t cand_cap = 0;
     uint2* d_out = nullptr;   uint64_t out_cap = 0;
     uint2* d_out_tmp = nullptr; uint64_t out_tmp_cap = 0;
@@ -140,8 +145,8 @@ void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const uin
                      uint32_t* d_checks9, cudaStream_t s);
 // collide.cu
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, uint32_t n, uint32_t shard, uint32_t nshards,
-                  uint32_t chunk, uint32_t nquery, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
-                  cudaStream_t s);
+                  uint32_t chunk, uint32_t nquery, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
+                  uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s);
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s);
 

@@ -7,7 +7,7 @@
 //   1. rs_histogram  one read of the keys builds the digit histograms of ALL passes
 //                    (shared-memory atomics, then one global atomic per bin);
 //   2. rs_scan       exclusive scan of each pass's 256 bins -> global digit bases;
-//   3. rs_pass x P   one kernel per digit. Each CTA takes a tile of 4096 items
+//   3. rs_pass x P   one kernel per digit. Each CTA (512 threads x 8 items) takes a tile of 4096 items
 //                    (ticket from an atomic counter, so look-back never waits on a
 //                    tile that has not started), ranks its keys with a warp-level
 //                    multi-split (__match_any_sync + per-warp shared histograms),
@@ -25,15 +25,16 @@ namespace b200cd {
 
 namespace {
 
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_IPT = 16;                    // items per thread
+constexpr int RS_IPT = 8;                     // items per thread
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 items per tile
 constexpr int RS_RADIX = 256;
 constexpr uint32_t ST_PARTIAL = 1u << 30;     // status word = flag | count  (count < 2^30)
 constexpr uint32_t ST_INCLUSIVE = 2u << 30;
 constexpr uint32_t ST_MASK = (1u << 30) - 1;
 constexpr int RS_MAX_PASS = 8;
+constexpr int RS_LOOKBACK = 4;                // predecessor status words fetched per look-back round
 
 struct PassList {
     int npass;
@@ -42,15 +43,16 @@ struct PassList {
 };
 
 // ---- 1. histograms of every pass in one sweep
-__global__ void __launch_bounds__(RS_THREADS) rs_histogram(const uint64_t* __restrict__ keys, uint32_t n,
+constexpr int RH_THREADS = 256;
+__global__ void __launch_bounds__(RH_THREADS) rs_histogram(const uint64_t* __restrict__ keys, uint32_t n,
                                                            PassList pl, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[RS_MAX_PASS * RS_RADIX];
-    for (int i = threadIdx.x; i < pl.npass * RS_RADIX; i += RS_THREADS) sh[i] = 0;
+    for (int i = threadIdx.x; i < pl.npass * RS_RADIX; i += RH_THREADS) sh[i] = 0;
     __syncthreads();
     // grid-stride over 2-key vectors (16-B loads)
     const uint32_t nvec = n >> 1;
     const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
-    for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < nvec; i += gridDim.x * RS_THREADS) {
+    for (uint32_t i = blockIdx.x * RH_THREADS + threadIdx.x; i < nvec; i += gridDim.x * RH_THREADS) {
         ulonglong2 k = __ldg(k2 + i);
 #pragma unroll
         for (int p = 0; p < RS_MAX_PASS; ++p) {
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const uint64_t* __res
         for (int p = 0; p < pl.npass; ++p) atomicAdd(&sh[p * RS_RADIX + ((k >> pl.shift[p]) & pl.mask[p])], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < pl.npass * RS_RADIX; i += RS_THREADS) {
+    for (int i = threadIdx.x; i < pl.npass * RS_RADIX; i += RH_THREADS) {
         uint32_t c = sh[i];
         if (c) atomicAdd(&hist[i], c);
     }
@@ -99,18 +101,24 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// 512 threads x 8 items, two CTAs per SM (<= 64 registers): 32 resident warps hide the
+// load -> rank -> look-back -> scatter latency chain of each tile behind the other tile's.
 template <bool HAS_VALUES>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 2)
 rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
         uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values,
         const uint32_t* __restrict__ digit_base_g,  // [256] exclusive global digit offsets of this pass
         uint32_t* __restrict__ status,              // [ntiles][256] look-back words of this pass
         uint32_t* __restrict__ ticket) {
-    __shared__ uint32_t warp_hist[RS_WARPS][RS_RADIX + 1];  // +1: bin 256 collects out-of-range padding
-    __shared__ uint32_t digit_base[RS_RADIX];
-    __shared__ uint32_t warp_tot[RS_WARPS];
-    __shared__ uint32_t s_tile;
-    __shared__ __align__(16) uint64_t stage[RS_TILE];  // 32 KiB, reused for the values
+    // dynamic shared memory (> 48 KiB): [stage_k 32 KiB][stage_v 16 KiB if values][warp_hist][digit_base][warp_tot][tile]
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t* stage_k = reinterpret_cast<uint64_t*>(rs_smem);
+    uint32_t* stage_v = reinterpret_cast<uint32_t*>(rs_smem + RS_TILE * 8);
+    uint32_t (*warp_hist)[RS_RADIX + 1] = reinterpret_cast<uint32_t (*)[RS_RADIX + 1]>(
+        rs_smem + RS_TILE * 8 + (HAS_VALUES ? RS_TILE * 4 : 0));  // +1: bin 256 collects out-of-range padding
+    uint32_t* digit_base = &warp_hist[RS_WARPS][0];
+    uint32_t* warp_tot = digit_base + RS_RADIX;
+    uint32_t& s_tile = warp_tot[RS_RADIX / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -121,12 +129,20 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
     const uint32_t tile_items = min((uint32_t)RS_TILE, n - tile_base);
     const uint32_t my_base = tile_base + warp * (32 * RS_IPT) + lane;  // warp-striped: item k at my_base + 32k
 
-    // load keys
+    // load keys (and values: their latency overlaps the ranking)
     uint64_t key[RS_IPT];
+    uint32_t val[RS_IPT];
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
-        uint32_t g = my_base + 32 * k;
+        const uint32_t g = my_base + 32 * k;
         key[k] = (g < n) ? __ldg(keys_in + g) : ~0ull;
+    }
+    if (HAS_VALUES) {
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            const uint32_t g = my_base + 32 * k;
+            val[k] = iota_values ? g : ((g < n) ? __ldg(vals_in + g) : 0u);
+        }
     }
 
     // warp-level multi-split: rank of every key among the warp's keys with the same digit
@@ -135,10 +151,10 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
-        uint32_t g = my_base + 32 * k;
-        uint32_t d = (g < n) ? (uint32_t)((key[k] >> shift) & mask) : (uint32_t)RS_RADIX;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(peers) - 1;
+        const uint32_t g = my_base + 32 * k;
+        const uint32_t d = (g < n) ? (uint32_t)((key[k] >> shift) & mask) : (uint32_t)RS_RADIX;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
         uint32_t prev = 0;
         if ((int)lane == leader) {
             prev = wh[d];
@@ -151,43 +167,54 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
     __syncthreads();
 
     // per digit: exclusive prefix over warps, tile count, look-back
-    {
-        const uint32_t d = tid;  // RS_THREADS == RS_RADIX
-        uint32_t sum = 0;
+    uint32_t sum = 0, excl = 0, incl = 0;
+    if (tid < RS_RADIX) {
+        const uint32_t d = tid;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
-            uint32_t c = warp_hist[w][d];
+            const uint32_t c = warp_hist[w][d];
             warp_hist[w][d] = sum;
             sum += c;
         }
         // publish this tile's count for digit d, then sum the counts of earlier tiles
         uint32_t* my_status = status + (size_t)tile * RS_RADIX + d;
         st_volatile(my_status, (tile == 0 ? ST_INCLUSIVE : ST_PARTIAL) | sum);
-        uint32_t excl = 0;
         if (tile > 0) {
             int t = (int)tile - 1;
-            while (true) {
-                uint32_t s = ld_volatile(status + (size_t)t * RS_RADIX + d);
-                if ((s & ~ST_MASK) == 0) continue;  // not published yet (tile t is running: tickets are ordered)
-                excl += s & ST_MASK;
-                if (s & ST_INCLUSIVE) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                // fetch several predecessors at once: their latencies overlap; consume in order
+                uint32_t sv[RS_LOOKBACK];
+#pragma unroll
+                for (int j = 0; j < RS_LOOKBACK; ++j)
+                    sv[j] = (t - j >= 0) ? ld_volatile(status + (size_t)(t - j) * RS_RADIX + d) : ST_INCLUSIVE;
+#pragma unroll
+                for (int j = 0; j < RS_LOOKBACK; ++j) {
+                    if (done) break;
+                    if ((sv[j] & ~ST_MASK) == 0) break;  // not published yet (tile is running: tickets are ordered) - refetch from here
+                    excl += sv[j] & ST_MASK;
+                    --t;
+                    if (sv[j] & ST_INCLUSIVE) done = true;
+                }
             }
             st_volatile(my_status, ST_INCLUSIVE | (excl + sum));
         }
         // exclusive scan of `sum` over the 256 digits -> where digit d starts inside the tile
-        uint32_t incl = sum;
+        incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t2 = __shfl_up_sync(0xffffffffu, incl, o);
+            const uint32_t t2 = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= (uint32_t)o) incl += t2;
         }
         if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (tid < RS_RADIX) {
+        const uint32_t d = tid;
         uint32_t wbase = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) wbase += (w < (int)warp) ? warp_tot[w] : 0u;
-        uint32_t local_start = wbase + incl - sum;
+        for (int w = 0; w < RS_RADIX / 32; ++w) wbase += (w < (int)warp) ? warp_tot[w] : 0u;
+        const uint32_t local_start = wbase + incl - sum;
         // final position of the item with in-tile slot r and digit d: digit_base[d] + r  (mod 2^32)
         digit_base[d] = __ldg(digit_base_g + d) + excl - local_start;
 #pragma unroll
@@ -195,45 +222,33 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
     }
     __syncthreads();
 
-    // stage keys in digit order
-    uint32_t slot[RS_IPT];
+    // stage keys (and values) in digit order
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
-        uint32_t g = my_base + 32 * k;
+        const uint32_t g = my_base + 32 * k;
         if (g < n) {
-            uint32_t d = (uint32_t)((key[k] >> shift) & mask);
-            slot[k] = wh[d] + rank[k];
-            stage[slot[k]] = key[k];
-        } else {
-            slot[k] = 0;
+            const uint32_t d = (uint32_t)((key[k] >> shift) & mask);
+            const uint32_t slot = wh[d] + rank[k];
+            stage_k[slot] = key[k];
+            if (HAS_VALUES) stage_v[slot] = val[k];
         }
     }
     __syncthreads();
-    uint32_t pos[RS_IPT];
+    // write out: consecutive slots of one digit land on consecutive addresses
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
-        uint32_t r = i * RS_THREADS + tid;
+        const uint32_t r = i * RS_THREADS + tid;
         if (r < tile_items) {
-            uint64_t kk = stage[r];
-            pos[i] = digit_base[(uint32_t)((kk >> shift) & mask)] + r;
-            keys_out[pos[i]] = kk;
+            const uint64_t kk = stage_k[r];
+            const uint32_t pos = digit_base[(uint32_t)((kk >> shift) & mask)] + r;
+            keys_out[pos] = kk;
+            if (HAS_VALUES) vals_out[pos] = stage_v[r];
         }
     }
-    if (HAS_VALUES) {
-        __syncthreads();
-        uint32_t* vstage = reinterpret_cast<uint32_t*>(stage);
-#pragma unroll
-        for (int k = 0; k < RS_IPT; ++k) {
-            uint32_t g = my_base + 32 * k;
-            if (g < n) vstage[slot[k]] = iota_values ? g : __ldg(vals_in + g);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < RS_IPT; ++i) {
-            uint32_t r = i * RS_THREADS + tid;
-            if (r < tile_items) vals_out[pos[i]] = vstage[r];
-        }
-    }
+}
+
+constexpr size_t rs_smem_bytes(bool has_values) {
+    return (size_t)RS_TILE * 8 + (has_values ? (size_t)RS_TILE * 4 : 0) + sizeof(uint32_t) * (RS_WARPS * (RS_RADIX + 1) + RS_RADIX + RS_RADIX / 32 + 1);
 }
 
 }  // namespace
@@ -257,11 +272,19 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
         pl.mask[p] = (1u << passes[p].bits) - 1u;
     }
     const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    static bool attr_set[64] = {};  // > 48 KiB of dynamic shared memory must be opted into, once per function and device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaFuncSetAttribute(rs_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+        cudaFuncSetAttribute(rs_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     uint32_t* d_ticket = d_hist + npass * RS_RADIX;
     cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);
     cudaMemsetAsync(d_tile_status, 0, sizeof(uint32_t) * (size_t)tiles * RS_RADIX * npass, s);
-    uint32_t hblocks = min((n / 2 + RS_THREADS - 1) / RS_THREADS + 1, (uint32_t)sms * 8u);
-    rs_histogram<<<hblocks, RS_THREADS, 0, s>>>(keys[0], n, pl, d_hist);
+    uint32_t hblocks = min((n / 2 + RH_THREADS - 1) / RH_THREADS + 1, (uint32_t)sms * 8u);
+    rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[0], n, pl, d_hist);
     count_launch();
     rs_scan<<<npass, RS_RADIX, 0, s>>>(d_hist);
     count_launch();
@@ -269,11 +292,11 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     for (int p = 0; p < npass; ++p) {
         uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
         if (vals)
-            rs_pass<true><<<tiles, RS_THREADS, 0, s>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n,
+            rs_pass<true><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n,
                                                        pl.shift[p], pl.mask[p], (iota_values && p == 0) ? 1 : 0,
                                                        d_hist + p * RS_RADIX, status, d_ticket + p);
         else
-            rs_pass<false><<<tiles, RS_THREADS, 0, s>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, pl.shift[p],
+            rs_pass<false><<<tiles, RS_THREADS, rs_smem_bytes(false), s>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, pl.shift[p],
                                                         pl.mask[p], 0, d_hist + p * RS_RADIX, status, d_ticket + p);
         count_launch();
         cur ^= 1;

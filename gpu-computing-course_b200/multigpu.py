@@ -21,9 +21,13 @@ DEFAULT_CHUNK = 1 << 14  # sorted leaves per block-cyclic chunk: spatially coher
 
 # ---- shard arithmetic: the same partition b200cd_self_collide_shard applies (csrc/api.cu run_query)
 
+QUERY_BLOCK = 256  # B200CD_QUERY_BLOCK: traversal blocks are 256 consecutive sorted leaves
+
+
 def resolve_chunk(n, nshards, chunk):
-    """chunk = 0 means one contiguous slice per shard"""
-    return chunk if chunk else (n + nshards - 1) // max(nshards, 1)
+    """chunk = 0 means one contiguous slice per shard; chunks are whole traversal blocks (rounded up)"""
+    c = chunk if chunk else (n + nshards - 1) // max(nshards, 1)
+    return max(1, (c + QUERY_BLOCK - 1) // QUERY_BLOCK) * QUERY_BLOCK
 
 
 def shard_of_position(pos, n, nshards, chunk=DEFAULT_CHUNK):

@@ -95,6 +95,9 @@ typedef struct b200cd_stats {
     uint32_t sort_passes; /* radix passes actually run */
     uint32_t query_retries; /* times a stage was re-run after growing a buffer */
     uint64_t kernel_launches; /* cumulative count of this library's kernel launches on the context */
+    uint64_t nodes_visited;   /* K5: internal nodes fetched, summed over queries (nodes-visited/s = this / ms_traverse) */
+    uint64_t warp_steps;      /* K5: traversal loop iterations summed over warps (x32 = lane slots) */
+    uint64_t start_entries;   /* K5: start subtrees kept per warp, summed over warps */
 } b200cd_stats;
 
 /* Structural self-checks, the counters the reference prints on every run

@@ -72,4 +72,4 @@ def test_shard_partition_covers_every_query_once():
     for n, nshards, chunk in [(1, 1, 0), (10, 3, 0), (1000, 8, 64), (4097, 4, 4096), (100, 8, 16), (5, 8, 0)]:
         seen = np.concatenate([mgpu.shard_positions(s, n, nshards, chunk) for s in range(nshards)])
         assert np.array_equal(np.sort(seen), np.arange(n)), (n, nshards, chunk)
-    assert mgpu.resolve_chunk(10, 3, 0) == 4 and mgpu.resolve_chunk(10, 3, 7) == 7
+    assert mgpu.resolve_chunk(10, 3, 0) == 256 and mgpu.resolve_chunk(1000, 3, 300) == 512
