@@ -64,7 +64,6 @@ void free_bvh_buffers(b200cd_bvh* b) {
     }
     cudaFree(b->d_hist);
     cudaFree(b->d_tile_status);
-    cudaFree(b->d_parent);
     cudaFree(b->d_flags);
     cudaFree(b->d_pairs);
     cudaFree(b->d_leaves);
@@ -96,7 +95,6 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
         A(dev_alloc(ctx, &b->d_keys[0], n));
         A(dev_alloc(ctx, &b->d_keys[1], n));
         A(dev_alloc(ctx, &b->d_ids[1], n));
-        A(dev_alloc(ctx, &b->d_parent, 2ull * n));
         A(dev_alloc(ctx, &b->d_flags, n));
     }
     A(dev_alloc(ctx, &b->d_ids[0], n));
@@ -156,10 +154,9 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
                             b->tile_status_words, ctx->sm_count, s);
     }
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
-    launch_hierarchy(b->d_keys[b->cur], n, b->d_parent, s);  // K3
-    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));
-    launch_refit(m->d_verts, m->d_idx, b->d_ids[b->cur], n, b->d_parent, b->d_flags, b->d_pairs, b->d_leaves,
-                 b->d_root_box, s);  // K4
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));  // (K3 is fused into K4: ms_hierarchy stays ~0)
+    launch_build_tree(m->d_verts, m->d_idx, b->d_ids[b->cur], b->d_keys[b->cur], n, b->d_flags, b->d_pairs, b->d_leaves,
+                      b->d_root_box, s);  // K3+K4
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, cudaGetLastError());
     ctx->stats.sort_passes = (uint32_t)npass;
@@ -497,15 +494,16 @@ API int b200cd_bvh_rebuild(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* 
 
 API int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh) {
     if (!ctx || !bvh || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
-    if (!bvh->built || bvh->n != mesh->ntris || !bvh->d_parent) return set_error(ctx, B200CD_E_INVALID, "BVH not built for this mesh");
+    if (!bvh->built || bvh->n != mesh->ntris || !bvh->d_keys[0]) return set_error(ctx, B200CD_E_INVALID, "BVH not built for this mesh");
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->stream;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));
-    launch_refit(mesh->d_verts, mesh->d_idx, bvh->d_ids[bvh->cur], bvh->n, bvh->d_parent, bvh->d_flags, bvh->d_pairs,
-                 bvh->d_leaves, bvh->d_root_box, s);
+    // the sorted keys are kept, so the same climb reproduces the same topology around the new boxes
+    launch_build_tree(mesh->d_verts, mesh->d_idx, bvh->d_ids[bvh->cur], bvh->d_keys[bvh->cur], bvh->n, bvh->d_flags,
+                      bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, s);
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, cudaGetLastError());
     ctx->stats.ms_build = -1.f;
@@ -526,10 +524,15 @@ API int b200cd_bvh_download(b200cd_ctx* ctx, const b200cd_bvh* bvh, b200cd_node3
         const uint64_t cnt = 2ull * n - 1;
         CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_nodes), cnt * sizeof(b200cd_node32)));
         cudaMemsetAsync(d_nodes, 0xff, cnt * sizeof(b200cd_node32), s);
-        launch_export_nodes(bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, n, d_nodes, s);
-        cudaError_t e = cudaMemcpyAsync(nodes, d_nodes, cnt * sizeof(b200cd_node32), cudaMemcpyDeviceToHost, s);
+        uint32_t* d_scratch = nullptr;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_scratch), 2 * cnt * sizeof(uint32_t));
+        if (e == cudaSuccess) {
+            launch_export_nodes(bvh->d_pairs, bvh->d_root_box, n, d_scratch, d_nodes, s);
+            e = cudaMemcpyAsync(nodes, d_nodes, cnt * sizeof(b200cd_node32), cudaMemcpyDeviceToHost, s);
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         cudaFree(d_nodes);
+        cudaFree(d_scratch);
         CD_CUDA(ctx, e);
     }
     if (sorted_keys) {
@@ -543,15 +546,19 @@ API int b200cd_bvh_download(b200cd_ctx* ctx, const b200cd_bvh* bvh, b200cd_node3
 
 API int b200cd_bvh_validate(b200cd_ctx* ctx, const b200cd_bvh* bvh, const b200cd_mesh* mesh, b200cd_checks* out) {
     if (!ctx || !bvh || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
-    if (!bvh->built || !bvh->d_parent) return set_error(ctx, B200CD_E_INVALID, "BVH not built on this context");
+    if (!bvh->built) return set_error(ctx, B200CD_E_INVALID, "BVH not built");
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->stream;
     uint32_t* d_chk = ctx->d_scalars + 16;
-    launch_validate(bvh->d_pairs, bvh->d_leaves, bvh->d_parent, bvh->d_flags, bvh->d_keys[bvh->cur], bvh->n,
-                    mesh ? mesh->nverts : bvh->nverts, d_chk, s);
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 16, d_chk, 9 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CD_CUDA(ctx, cudaStreamSynchronize(s));
-    CD_CUDA(ctx, cudaGetLastError());
+    uint32_t* d_scratch = nullptr;
+    CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_scratch), 2 * (2ull * std::max<uint32_t>(bvh->n, 1u)) * sizeof(uint32_t)));
+    launch_validate(bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, bvh->d_keys[0] ? bvh->d_keys[bvh->cur] : nullptr, bvh->n,
+                    mesh ? mesh->nverts : bvh->nverts, d_scratch, d_chk, s);
+    cudaError_t e = cudaMemcpyAsync(ctx->h_scalars + 16, d_chk, 9 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_scratch);
+    CD_CUDA(ctx, e);
     memcpy(out, ctx->h_scalars + 16, 9 * sizeof(uint32_t));
     return B200CD_OK;
 }
@@ -674,7 +681,7 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
     for (int attempt = 0; attempt < 4; ++attempt) {
         if (need_broad) {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
-            launch_broad(b->d_pairs, b->d_leaves, n, shard, nshards, chunk, nquery, b->d_entries, b->d_entry_count, b->d_cand,
+            launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, shard, nshards, chunk, nquery, b->d_entries, b->d_entry_count, b->d_cand,
                          b->cand_cap, b->d_counters, s);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
         } else {

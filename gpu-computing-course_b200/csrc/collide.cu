@@ -15,7 +15,7 @@
 // found is ours:
 //   - every unordered leaf pair {i, j} is discovered ONCE, by the query with the
 //     smaller sorted position: a child whose subtree ends at or before the query's
-//     own position (Node32::last <= q) is pruned. The AABB predicate is symmetric,
+//     own position is pruned. The AABB predicate is symmetric,
 //     so this halves the traversal without changing the set; the narrow phase is
 //     still called as (lower ID, higher ID) because the SAT is not symmetric in
 //     floating point.
@@ -60,9 +60,9 @@ __device__ __forceinline__ uint64_t query_position(uint32_t t, uint32_t shard, u
 }
 
 struct Child {
-    float4 a, b;  // a = lo.xyz, hi.x ; b = hi.yz, link, last
+    float4 a, b;  // a = lo.xyz, hi.x ; b = hi.yz, link, ext (Node32)
     __device__ __forceinline__ int link() const { return __float_as_int(b.z); }
-    __device__ __forceinline__ int last() const { return __float_as_int(b.w); }
+    __device__ __forceinline__ int ext() const { return __float_as_int(b.w); }
 };
 __device__ __forceinline__ void load_children(const NodePair* __restrict__ pairs, int node, Child& l, Child& r) {
     const float4* p = reinterpret_cast<const float4*>(pairs + node);
@@ -82,31 +82,35 @@ __device__ __forceinline__ void load_children(const NodePair* __restrict__ pairs
 // parent. The emitted candidate SET is unchanged: the entries cover exactly the leaves > q0, the
 // per-query rule (subtree end > q, strict box overlap) is applied to each entry and below it.
 __global__ void __launch_bounds__(128)
-entry_kernel(const NodePair* __restrict__ pairs, uint32_t n, uint32_t shard, uint32_t nshards, uint32_t chunk,
-             uint32_t nblocks, Node32* __restrict__ entries, uint32_t* __restrict__ entry_count) {
+entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_box, uint32_t n, uint32_t shard,
+             uint32_t nshards, uint32_t chunk, uint32_t nblocks, Node32* __restrict__ entries,
+             uint32_t* __restrict__ entry_count) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const uint64_t p0 = query_position(b * BR_THREADS, shard, nshards, chunk);
+    const int root = reinterpret_cast<const int*>(root_box)[6];
     uint32_t cnt = 0;
     bool overflow = false;
     Child* out = reinterpret_cast<Child*>(entries + (size_t)b * BR_ENTRIES);
-    auto add = [&](const Child& c) {
+    auto add = [&](Child c, int last) {  // entries carry the LAST leaf of their subtree in ext
+        c.b.w = __int_as_float(last);
         if (cnt < (uint32_t)BR_ENTRIES) out[cnt++] = c; else overflow = true;
     };
     if (p0 + 1 < n) {  // the very last leaf has no partner after it
         const int q0 = (int)p0;
         const int q1 = (int)min((uint64_t)n - 1, p0 + BR_THREADS - 1);
-        int node = 0, F = 0;
+        int node = root, F = 0, L = (int)n - 1;  // current node = split index; its leaf range [F, L]
         Child l, r;
         bool split_found = false;
-        // common part of the two paths
+        // common part of the two paths. Left child = [F, node], right child = [node+1, L].
         while (true) {
             load_children(pairs, node, l, r);
-            const int g = l.last();
+            const int g = node;
             if (q1 <= g) {            // both ends in the left child: the right child lies entirely beyond q1
-                add(r);
+                add(r, L);
                 if (l.link() < 0) break;
                 node = l.link();
+                L = g;
             } else if (q0 > g) {      // both ends in the right child: the left child lies entirely before q0
                 if (r.link() < 0) break;
                 node = r.link();
@@ -117,34 +121,40 @@ entry_kernel(const NodePair* __restrict__ pairs, uint32_t n, uint32_t shard, uin
             }
         }
         if (split_found) {
+            const int g = node;
             // walk towards q0 inside the left child [F, g]: right siblings lie inside (q0, q1]
             Child cur = l, a, c;
-            int curF = F;
+            int curF = F, curL = g;
             while (true) {
                 if (curF >= q0 || cur.link() < 0) {  // whole subtree inside the block's range (leaf q0 itself: harmless)
-                    add(cur);
+                    add(cur, curL);
                     break;
                 }
-                load_children(pairs, cur.link(), a, c);
-                if (q0 <= a.last()) { add(c); cur = a; }
-                else { curF = a.last() + 1; cur = c; }
+                const int m = cur.link();
+                load_children(pairs, m, a, c);
+                if (q0 <= m) { add(c, curL); cur = a; curL = m; }
+                else { curF = m + 1; cur = c; }
             }
-            // walk towards q1 inside the right child: left siblings lie inside the range, right siblings beyond it
+            // walk towards q1 inside the right child [g+1, L]: left siblings lie inside the range, right siblings beyond it
             cur = r;
+            curL = L;
             while (true) {
-                if (cur.last() <= q1 || cur.link() < 0) {
-                    add(cur);
+                if (curL <= q1 || cur.link() < 0) {
+                    add(cur, curL);
                     break;
                 }
-                load_children(pairs, cur.link(), a, c);
-                if (q1 <= a.last()) { add(c); cur = a; }
-                else { add(a); cur = c; }
+                const int m = cur.link();
+                load_children(pairs, m, a, c);
+                if (q1 <= m) { add(c, curL); cur = a; curL = m; }
+                else { add(a, m); cur = c; }
             }
         }
         if (overflow) {  // pathologically deep tree: fall back to "start at the root" (two entries = the root's children)
-            load_children(pairs, 0, l, r);
-            out[0] = l; out[1] = r;
-            cnt = 2;
+            load_children(pairs, root, l, r);
+            cnt = 0;
+            overflow = false;
+            add(l, root);
+            add(r, (int)n - 1);
         }
     }
     entry_count[b] = cnt;
@@ -242,7 +252,7 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
     // start points: every kept entry that ends after q and overlaps q's box (warp-uniform loop)
     for (uint32_t e = 0; e < nkeep; ++e) {
         const Child c = s_entry[e];
-        const bool hit = q != 0xffffffffu && c.last() > (int)q &&
+        const bool hit = q != 0xffffffffu && c.ext() > (int)q &&
                          overlap(qlo, qhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y);
         const int link = c.link();
         if (hit && link >= 0) {
@@ -262,8 +272,9 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
             Child l, r;
             load_children(pairs, node, l, r);
             const int linkL = l.link(), linkR = r.link();
-            const bool hitL = l.last() > (int)q && overlap(qlo, qhi, l.a.x, l.a.y, l.a.z, l.a.w, l.b.x, l.b.y);
-            const bool hitR = r.last() > (int)q && overlap(qlo, qhi, r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y);
+            // left child = leaves [.., node], right child = leaves [node+1, r.ext]: skip what ends at or before q
+            const bool hitL = node > (int)q && overlap(qlo, qhi, l.a.x, l.a.y, l.a.z, l.a.w, l.b.x, l.b.y);
+            const bool hitR = r.ext() > (int)q && overlap(qlo, qhi, r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y);
             candL = hitL && linkL < 0; leafL = ~linkL;
             candR = hitR && linkR < 0; leafR = ~linkR;
             const bool goL = hitL && linkL >= 0, goR = hitR && linkR >= 0;
@@ -466,12 +477,12 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
 
 }  // namespace
 
-void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, uint32_t n, uint32_t shard, uint32_t nshards,
-                  uint32_t chunk, uint32_t nquery, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
+void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
+                  uint32_t nshards, uint32_t chunk, uint32_t nquery, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
                   uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s) {
     if (n < 2 || nquery == 0) return;
     const uint32_t blocks = (nquery + BR_THREADS - 1) / BR_THREADS;
-    entry_kernel<<<(blocks + 127) / 128, 128, 0, s>>>(d_pairs, n, shard, nshards, chunk, blocks, d_entries, d_entry_count);
+    entry_kernel<<<(blocks + 127) / 128, 128, 0, s>>>(d_pairs, d_root_box, n, shard, nshards, chunk, blocks, d_entries, d_entry_count);
     count_launch();
     broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, d_entries,
                                                d_entry_count, d_cand, cand_cap, d_counters);

@@ -15,17 +15,19 @@ namespace b200cd {
 
 // ---------------------------------------------------------------- device data layout
 //
-// Traversal node: one child of an internal node. The two children of internal
-// node p sit side by side in pairs[p] (64 B, one aligned fetch gives both boxes,
-// both links and both range ends).
+// Traversal node: one child of an internal node. Internal node s is "the split between the
+// sorted leaves s and s+1"; its two children sit side by side in pairs[s] (64 B, one aligned
+// fetch gives both boxes, both links and the node's leaf range).
 //   link >= 0 : child is internal node `link`  (visit pairs[link] next)
 //   link <  0 : child is the leaf at sorted position ~link
-//   last      : highest sorted leaf position inside the child's subtree
+//   ext       : the far end of the child's leaf range - FIRST leaf for the left child c[0]
+//               (its last leaf is s), LAST leaf for the right child c[1] (its first is s+1).
+//               In a traversal entry list (collide.cu) ext is always the LAST leaf.
 struct __align__(32) Node32 {
     float lo[3];
     float hi[3];
     int32_t link;
-    int32_t last;
+    int32_t ext;
 };
 struct __align__(64) NodePair {
     Node32 c[2];
@@ -81,11 +83,10 @@ struct b200cd_bvh {
     uint32_t* d_tile_status = nullptr; // decoupled look-back words
     uint64_t tile_status_words = 0;
     // hierarchy
-    uint32_t* d_parent = nullptr;      // [n-1 internal | n leaves], value = parent<<1 | side, ~0u = root
-    uint32_t* d_flags = nullptr;       // n-1 refit arrival counters
+    uint32_t* d_flags = nullptr;       // n-1 arrival counters of the splits merged through global memory
     b200cd::NodePair* d_pairs = nullptr;  // n-1
     b200cd::LeafRec* d_leaves = nullptr;  // n
-    float* d_root_box = nullptr;       // 6 floats
+    float* d_root_box = nullptr;       // 6 floats + [6] = index of the root node (int)
     // query
     b200cd::Node32* d_entries = nullptr;  // [blocks][B200CD_MAX_ENTRIES] traversal start subtrees
     uint32_t* d_entry_count = nullptr;    // [blocks]
@@ -134,18 +135,17 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
 uint64_t radix_tile_status_words(uint32_t n, int npass);
 uint32_t radix_hist_words(int npass);
 // lbvh.cu
-void launch_hierarchy(const uint64_t* d_keys, uint32_t n, uint32_t* d_parent, cudaStream_t s);
-void launch_refit(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, uint32_t n,
-                  const uint32_t* d_parent, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves,
-                  float* d_root_box, cudaStream_t s);
-void launch_export_nodes(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n,
+void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
+                       uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
+                       cudaStream_t s);
+// d_scratch: 2 * (2n-1) words
+void launch_export_nodes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t* d_scratch,
                          b200cd_node32* d_nodes_out, cudaStream_t s);
-void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const uint32_t* d_parent,
-                     const uint32_t* d_flags, const uint64_t* d_keys, uint32_t n, uint32_t nverts,
-                     uint32_t* d_checks9, cudaStream_t s);
+void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, const uint64_t* d_keys,
+                     uint32_t n, uint32_t nverts, uint32_t* d_scratch, uint32_t* d_checks9, cudaStream_t s);
 // collide.cu
-void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, uint32_t n, uint32_t shard, uint32_t nshards,
-                  uint32_t chunk, uint32_t nquery, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
+void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
+                  uint32_t nshards, uint32_t chunk, uint32_t nquery, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
                   uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s);
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s);

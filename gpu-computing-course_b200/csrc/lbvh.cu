@@ -1,75 +1,44 @@
-// lbvh.cu — K3 (Karras hierarchy) and K4 (leaf records + bottom-up AABB refit),
-// plus the parity/validation helpers (node export, structural self-checks).
+// lbvh.cu — K3+K4 fused: LBVH topology, leaf records and node boxes in ONE bottom-up pass,
+// plus the parity/validation helpers (node export in the reference's numbering, self-checks).
 //
 // Reference semantics (under /root/reference/CollisionDetection/):
-//   K3  bvh.cuh:48 (delta), :100-123 (determineRange), :57-98 (findSplit),
-//       :146-199 (generateHierarchyParallel): internal node i covers the key range
-//       that contains i and its more-similar neighbour; children are
-//       leaf/internal by "split == first" / "split+1 == last"; root = internal 0.
-//   K4  bvh.cuh:258-285 (calBoundingBox), box.cuh:13-32 (Box::set / Box::merge),
-//       mathop.cuh:17-44 (comparison-based min/max).
+//   hierarchy  bvh.cuh:48 (delta), :100-123 (determineRange), :57-98 (findSplit),
+//              :146-199 (generateHierarchyParallel): a binary radix tree over the sorted Morton
+//              codes; internal node i covers the key range that contains i and its more-similar
+//              neighbour; root = internal 0.
+//   refit      bvh.cuh:258-285 (calBoundingBox), box.cuh:13-32 (Box::set / Box::merge),
+//              mathop.cuh:17-44 (comparison-based min/max): leaves first, the SECOND thread to
+//              reach a node merges its children (atomic visit counter).
 //
-// What is different here, by design:
-//   - delta() breaks ties between equal keys with the leaf index (Karras 2012 §4);
-//     the reference builds a malformed tree for duplicate codes (load_obj.h:110-115
-//     only reports them). With unique keys the tree is node-for-node identical.
-//   - no pointer-linked 112-byte Node (bvh.cuh:25-43) and no fillLeafNodes pass
-//     (bvh.cuh:125-144): K3 writes only a parent word per node; K4 writes the
-//     traversal layout directly — the two children of internal node p live side by
-//     side in pairs[p] (64 B), each a 32-byte Node32 {box, link, last}.
-//   - the refit publishes a child's box with __threadfence() before the arrival
-//     atomic and reads the sibling through L2 (__ldcg); the reference has neither
-//     (bvh.cuh:270-278) and relies on luck.
+// What is ours:
+//   - The reference finds every internal node's range and split with two binary searches over
+//     the keys (top-down information), then climbs again for the boxes. The same tree is the
+//     Cartesian tree of the adjacent-key similarities delta(i) = clz(key[i] ^ key[i+1]): a node
+//     covering [F, L] hangs under the split between L and L+1 if delta(L) > delta(F-1), else under
+//     the split between F-1 and F (Apetrei 2014). So one bottom-up climb builds topology AND
+//     boxes: no parent array, no search kernel. Equal keys are ordered by sorted position
+//     (delta = 64 + clz(i ^ (i+1)), Karras 2012 section 4); the reference builds a malformed tree for
+//     duplicate codes (load_obj.h:110-115 only reports them). With unique keys the tree is
+//     node-for-node the reference's; b200cd_bvh_download renumbers nodes to the reference's
+//     (Karras) indices for the parity tests.
+//   - Storage: internal node s = "the split between sorted leaves s and s+1" lives in pairs[s]
+//     (64 B): both children side by side, each a 32-byte Node32 {box, link, ext} with
+//     ext = first leaf of the subtree for the left child (its last leaf is s itself) and
+//     ext = last leaf for the right child (its first leaf is s+1).
+//   - Each block owns 256 consecutive sorted leaves and climbs in SHARED memory while both
+//     children of a split lie inside the block (~97 % of all merges): the arrival flag, the
+//     sibling's half and the similarities never touch HBM, and the finished 64-byte node is
+//     written once. Only the few nodes that straddle block boundaries use the global protocol:
+//     publish my half, __threadfence(), atomic arrival flag, read the sibling's half through L2
+//     (the reference has neither fence nor cache bypass, bvh.cuh:270-278).
 #include "common.cuh"
 
 namespace b200cd {
 
 namespace {
 
-constexpr uint32_t ROOT_PARENT = 0xffffffffu;
+constexpr int BL = 256;  // sorted leaves per block
 
-// ---------------------------------------------------------------- K3
-__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, uint64_t ki, int j) {
-    if (j < 0 || j >= n) return -1;
-    uint64_t x = ki ^ __ldg(keys + j);
-    return x ? __clzll((long long)x) : 64 + __clz(i ^ j);
-}
-
-__global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restrict__ keys, int n,
-                                                       uint32_t* __restrict__ parent) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    const uint64_t ki = __ldg(keys + i);
-    // direction of the range and the prefix length it must beat
-    int dn = delta(keys, n, i, ki, i + 1), dp = delta(keys, n, i, ki, i - 1);
-    int d = (dn - dp) >= 0 ? 1 : -1;
-    int dmin = d > 0 ? dp : dn;
-    // exponential search for an upper bound of the range length, then binary search
-    int lmax = 2;
-    while (delta(keys, n, i, ki, i + lmax * d) > dmin) lmax <<= 1;
-    int l = 0;
-    for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (delta(keys, n, i, ki, i + (l + t) * d) > dmin) l += t;
-    int j = i + l * d;
-    int first = min(i, j), last = max(i, j);
-    // split: highest position in [first, last) sharing more than the range's common prefix with `first`
-    uint64_t kf = __ldg(keys + first);
-    int common = delta(keys, n, first, kf, last);
-    int split = first, step = last - first;
-    do {
-        step = (step + 1) >> 1;
-        int cand = split + step;
-        if (cand < last && delta(keys, n, first, kf, cand) > common) split = cand;
-    } while (step > 1);
-    // parent words: internal nodes first (n-1 of them), then leaves
-    uint32_t a = (split == first) ? (uint32_t)(n - 1 + split) : (uint32_t)split;
-    uint32_t b = (split + 1 == last) ? (uint32_t)(n - 1 + split + 1) : (uint32_t)(split + 1);
-    parent[a] = ((uint32_t)i << 1);
-    parent[b] = ((uint32_t)i << 1) | 1u;
-    if (i == 0) parent[0] = ROOT_PARENT;
-}
-
-// ---------------------------------------------------------------- K4
 __device__ __forceinline__ float min3_ref(float a, float b, float c) {  // mathop.cuh:38-44
     float t = a;
     if (b < t) t = b;
@@ -85,109 +54,248 @@ __device__ __forceinline__ float max3_ref(float a, float b, float c) {  // matho
 __device__ __forceinline__ float min2_ref(float a, float b) { return (a < b) ? a : b; }  // mathop.cuh:21-23
 __device__ __forceinline__ float max2_ref(float a, float b) { return (a > b) ? a : b; }  // mathop.cuh:17-19
 
-__device__ __forceinline__ void store_node(Node32* dst, const float lo[3], const float hi[3], int link, int last) {
-    float4* p = reinterpret_cast<float4*>(dst);
-    __stcg(p, make_float4(lo[0], lo[1], lo[2], hi[0]));
-    __stcg(p + 1, make_float4(hi[1], hi[2], __int_as_float(link), __int_as_float(last)));
+// similarity of the sorted neighbours i and i+1 (bvh.cuh:48 restricted to adjacent keys, + tie-break)
+__device__ __forceinline__ int similarity(uint64_t a, uint64_t b, int i) {
+    const uint64_t x = a ^ b;
+    return x ? __clzll((long long)x) : 64 + __clz(i ^ (i + 1));
+}
+__device__ __forceinline__ int similarity_at(const uint64_t* __restrict__ keys, int n, int i) {
+    if (i < 0 || i >= n - 1) return -1;
+    return similarity(__ldg(keys + i), __ldg(keys + i + 1), i);
 }
 
-__global__ void __launch_bounds__(256)
-refit_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ sorted_ids,
-             uint32_t n, const uint32_t* __restrict__ parent, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
-             LeafRec* __restrict__ leaves, float* __restrict__ root_box) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    // leaf record: the triangle at sorted position j, vertices copied next to their indices and ID
-    const uint32_t id = __ldg(sorted_ids + j);
-    const uint32_t* f = idx + 3ull * id;
-    const uint32_t i0 = __ldg(f), i1 = __ldg(f + 1), i2 = __ldg(f + 2);
-    const float4 a = __ldg(verts + i0), b = __ldg(verts + i1), c = __ldg(verts + i2);
-    float4* rec = reinterpret_cast<float4*>(leaves + j);
-    __stcs(rec, make_float4(a.x, a.y, a.z, b.x));
-    __stcs(rec + 1, make_float4(b.y, b.z, c.x, c.y));
-    __stcs(rec + 2, make_float4(c.z, __uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2)));
-    __stcs(rec + 3, make_float4(__uint_as_float(id), 0.f, 0.f, 0.f));
-    // leaf box, box.cuh:13-22
-    float lo[3] = {min3_ref(a.x, b.x, c.x), min3_ref(a.y, b.y, c.y), min3_ref(a.z, b.z, c.z)};
-    float hi[3] = {max3_ref(a.x, b.x, c.x), max3_ref(a.y, b.y, c.y), max3_ref(a.z, b.z, c.z)};
-    if (n == 1) {
+struct Carry {  // the subtree a climbing thread currently holds
+    float lo[3], hi[3];
+    int link;  // >= 0: internal node (its split index), < 0: ~leaf position
+    int F, L;  // leaf range
+};
+
+__device__ __forceinline__ void pack(const Carry& c, int ext, float4& a, float4& b) {
+    a = make_float4(c.lo[0], c.lo[1], c.lo[2], c.hi[0]);
+    b = make_float4(c.hi[1], c.hi[2], __int_as_float(c.link), __int_as_float(ext));
+}
+
+// Box::merge(childA, childB), box.cuh:24-32 - operand order A (left) then B (right)
+__device__ __forceinline__ void merge_with(Carry& me, int side, const float4& sa, const float4& sb, int s) {
+    const float slo[3] = {sa.x, sa.y, sa.z}, shi[3] = {sa.w, sb.x, sb.y};
+    const int sext = __float_as_int(sb.w);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { root_box[k] = lo[k]; root_box[3 + k] = hi[k]; }
-        return;
+    for (int k = 0; k < 3; ++k) {
+        const float alo = side ? slo[k] : me.lo[k], blo = side ? me.lo[k] : slo[k];
+        const float ahi = side ? shi[k] : me.hi[k], bhi = side ? me.hi[k] : shi[k];
+        me.lo[k] = min2_ref(alo, blo);
+        me.hi[k] = max2_ref(ahi, bhi);
     }
-    int link = ~(int)j, last = (int)j;
-    uint32_t pw = __ldg(parent + (n - 1) + j);
-    // climb: the first thread to reach a node stops, the second merges (bvh.cuh:269-283)
+    if (side) me.F = sext; else me.L = sext;  // the sibling's far end
+    me.link = s;
+}
+
+__device__ __forceinline__ void write_root(const Carry& c, float* __restrict__ root_box) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { root_box[k] = c.lo[k]; root_box[3 + k] = c.hi[k]; }
+    reinterpret_cast<int*>(root_box)[6] = c.link;  // index of the root node (or ~0 when n == 1)
+}
+
+// Global-memory climb for the few subtrees that straddle block boundaries (bvh.cuh:269-283 protocol
+// + fences). `have_slot`: the first arrival's split/side are already known (conversion of a deposit
+// left in shared memory).
+__device__ void climb_global(Carry c, bool have_slot, int s, int side, const uint64_t* __restrict__ keys, int n,
+                             uint32_t* __restrict__ flags, NodePair* __restrict__ pairs, float* __restrict__ root_box) {
     while (true) {
-        const uint32_t p = pw >> 1, side = pw & 1u;
-        store_node(&pairs[p].c[side], lo, hi, link, last);
-        __threadfence();  // publish my half before announcing arrival
-        if (atomicAdd(flags + p, 1u) == 0u) return;
-        __threadfence();
-        // the sibling's half was published before its atomic; read it through L2
-        const float4* sp = reinterpret_cast<const float4*>(&pairs[p].c[side ^ 1u]);
-        const float4 s0 = __ldcg(sp), s1 = __ldcg(sp + 1);
-        const float slo[3] = {s0.x, s0.y, s0.z}, shi[3] = {s0.w, s1.x, s1.y};
-        const int slast = __float_as_int(s1.w);
-        // Box::merge(childA, childB), box.cuh:24-32 — operand order A then B
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float alo = side ? slo[k] : lo[k], blo = side ? lo[k] : slo[k];
-            float ahi = side ? shi[k] : hi[k], bhi = side ? hi[k] : shi[k];
-            lo[k] = min2_ref(alo, blo);
-            hi[k] = max2_ref(ahi, bhi);
+        if (!have_slot) {
+            const int dl = similarity_at(keys, n, c.F - 1), dr = similarity_at(keys, n, c.L);
+            if (dl < 0 && dr < 0) {
+                write_root(c, root_box);
+                return;
+            }
+            const bool right = dr > dl;
+            s = right ? c.L : c.F - 1;
+            side = right ? 0 : 1;
         }
-        last = max(last, slast);
-        link = (int)p;
-        pw = __ldg(parent + p);
-        if (pw == ROOT_PARENT) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { root_box[k] = lo[k]; root_box[3 + k] = hi[k]; }
-            return;
+        have_slot = false;
+        float4 a, b;
+        pack(c, side ? c.L : c.F, a, b);
+        float4* mine = reinterpret_cast<float4*>(&pairs[s].c[side]);
+        __stcg(mine, a);
+        __stcg(mine + 1, b);
+        __threadfence();  // publish my half before announcing arrival
+        if (atomicAdd(flags + s, 1u) == 0u) return;
+        __threadfence();
+        const float4* sib = reinterpret_cast<const float4*>(&pairs[s].c[side ^ 1]);
+        const float4 sa = __ldcg(sib), sb = __ldcg(sib + 1);  // published before the sibling's atomic; read through L2
+        merge_with(c, side, sa, sb, s);
+    }
+}
+
+__global__ void __launch_bounds__(BL)
+build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ sorted_ids,
+             const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
+             LeafRec* __restrict__ leaves, float* __restrict__ root_box) {
+    __shared__ int s_sim[BL + 1];          // s_sim[i] = similarity of sorted positions (B0-1+i, B0+i); -1 outside
+    __shared__ uint32_t s_flag[BL];        // per split B0+i: bit 0 = left child arrived, bit 1 = right child arrived
+    __shared__ float4 s_dep[BL][2][2];     // per split, per side: the child's Node32 (ext as in pairs[])
+    const int tid = threadIdx.x;
+    const int B0 = blockIdx.x * BL;
+    const int j = B0 + tid;
+    const int Bend = min(B0 + BL, n) - 1;  // last leaf of this block
+
+    // ---- leaf record + leaf box; similarities of the block's neighbours
+    Carry c;
+    uint64_t kj = 0;
+    if (j < n) {
+        const uint32_t id = __ldg(sorted_ids + j);
+        const uint32_t* f = idx + 3ull * id;
+        const uint32_t i0 = __ldg(f), i1 = __ldg(f + 1), i2 = __ldg(f + 2);
+        const float4 a = __ldg(verts + i0), b = __ldg(verts + i1), d = __ldg(verts + i2);
+        float4* rec = reinterpret_cast<float4*>(leaves + j);
+        __stcs(rec, make_float4(a.x, a.y, a.z, b.x));
+        __stcs(rec + 1, make_float4(b.y, b.z, d.x, d.y));
+        __stcs(rec + 2, make_float4(d.z, __uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2)));
+        __stcs(rec + 3, make_float4(__uint_as_float(id), 0.f, 0.f, 0.f));
+        // box.cuh:13-22
+        c.lo[0] = min3_ref(a.x, b.x, d.x); c.lo[1] = min3_ref(a.y, b.y, d.y); c.lo[2] = min3_ref(a.z, b.z, d.z);
+        c.hi[0] = max3_ref(a.x, b.x, d.x); c.hi[1] = max3_ref(a.y, b.y, d.y); c.hi[2] = max3_ref(a.z, b.z, d.z);
+        c.link = ~j;
+        c.F = c.L = j;
+        kj = __ldg(keys + j);
+        // similarity(j, j+1) goes to s_sim[tid + 1]
+        s_sim[tid + 1] = (j + 1 < n) ? similarity(kj, __ldg(keys + j + 1), j) : -1;
+        if (tid == 0) s_sim[0] = (j > 0) ? similarity(__ldg(keys + j - 1), kj, j - 1) : -1;
+    } else {
+        s_sim[tid + 1] = -1;
+    }
+    s_flag[tid] = 0;
+    __syncthreads();
+
+    // ---- climb inside the block: splits s with both neighbours in the block, B0 <= s < Bend
+    bool pending = false;  // holding a subtree whose parent split lies outside the block's shared-memory range
+    if (j < n) {
+        if (n == 1) {
+            write_root(c, root_box);
+        } else {
+            while (true) {
+                const int dl = s_sim[c.F - B0], dr = s_sim[c.L - B0 + 1];  // similarity(F-1), similarity(L)
+                if (dl < 0 && dr < 0) {  // covers [0, n-1]
+                    write_root(c, root_box);
+                    break;
+                }
+                const bool right = dr > dl;          // parent extends to the right: I am its left child
+                const int s = right ? c.L : c.F - 1;
+                const int side = right ? 0 : 1;
+                if (s < B0 || s >= Bend) {
+                    pending = true;
+                    break;
+                }
+                const int ls = s - B0;
+                float4 a, b;
+                pack(c, side ? c.L : c.F, a, b);
+                s_dep[ls][side][0] = a;
+                s_dep[ls][side][1] = b;
+                __threadfence_block();
+                const uint32_t old = atomicOr(&s_flag[ls], 1u << side);
+                if (old == 0u) break;  // first arrival: the deposit stays for the sibling
+                __threadfence_block();
+                const float4 sa = s_dep[ls][side ^ 1][0], sb = s_dep[ls][side ^ 1][1];
+                // both halves are here: write the finished node once (left child, right child)
+                float4* dst = reinterpret_cast<float4*>(pairs + s);
+                __stcs(dst + 2 * side, a);
+                __stcs(dst + 2 * side + 1, b);
+                __stcs(dst + 2 * (side ^ 1), sa);
+                __stcs(dst + 2 * (side ^ 1) + 1, sb);
+                merge_with(c, side, sa, sb, s);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- leftovers continue through global memory
+    if (pending) climb_global(c, false, 0, 0, keys, n, flags, pairs, root_box);
+    // a deposit whose sibling never showed up inside the block (the sibling reaches beyond it):
+    // thread t converts split B0+t into a global arrival
+    if (tid < BL - 1 && B0 + tid < Bend) {
+        const uint32_t f = s_flag[tid];
+        if (f == 1u || f == 2u) {
+            const int side = (f == 1u) ? 0 : 1;
+            const float4 a = s_dep[tid][side][0], b = s_dep[tid][side][1];
+            Carry d;
+            d.lo[0] = a.x; d.lo[1] = a.y; d.lo[2] = a.z; d.hi[0] = a.w; d.hi[1] = b.x; d.hi[2] = b.y;
+            d.link = __float_as_int(b.z);
+            const int ext = __float_as_int(b.w);
+            const int s = B0 + tid;
+            if (side == 0) { d.F = ext; d.L = s; } else { d.F = s + 1; d.L = ext; }
+            climb_global(d, true, s, side, keys, n, flags, pairs, root_box);
         }
     }
 }
 
-// ---------------------------------------------------------------- parity export
+// ---------------------------------------------------------------- renumbering to the reference's indices
+// Karras numbering (bvh.cuh:161-198): an internal node that is a LEFT child has the index of the
+// last leaf of its range, a RIGHT child the index of its first leaf, the root is 0.
+// unified ids: internal split s -> s, leaf j -> (n-1)+j.
+__global__ void __launch_bounds__(256)
+parent_kernel(const NodePair* __restrict__ pairs, uint32_t n, uint32_t* __restrict__ parent_side,
+              uint32_t* __restrict__ refcount) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n - 1) return;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int link = pairs[s].c[side].link;
+        const uint32_t u = link >= 0 ? (uint32_t)link : (n - 1) + (uint32_t)~link;
+        if (u < 2 * n - 1) {
+            parent_side[u] = (s << 1) | (uint32_t)side;
+            if (refcount) atomicAdd(refcount + u, 1u);
+        }
+    }
+}
+
 // nodes_out[0..n-2] internal (Karras index), nodes_out[n-1+j] leaf j; see b200cd_node32.
 __global__ void __launch_bounds__(256)
-export_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_box, uint32_t n,
-              b200cd_node32* __restrict__ out) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+export_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_box,
+              const uint32_t* __restrict__ parent_side, uint32_t n, b200cd_node32* __restrict__ out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 1) {
-        if (p == 0) {
+        if (s == 0) {
             for (int k = 0; k < 3; ++k) { out[0].lo[k] = root_box[k]; out[0].hi[k] = root_box[3 + k]; }
             out[0].left = out[0].right = -1;
         }
         return;
     }
-    if (p >= n - 1) return;
+    if (s >= n - 1) return;
+    const uint32_t root = (uint32_t) reinterpret_cast<const int*>(root_box)[6];
+    // range of node t: [pairs[t].c[0].ext (= first leaf), pairs[t].c[1].ext (= last leaf)]
+    auto karras = [&](uint32_t t) -> uint32_t {
+        if (t == root) return 0u;
+        const uint32_t side = parent_side[t] & 1u;
+        return side == 0 ? (uint32_t)pairs[t].c[1].ext : (uint32_t)pairs[t].c[0].ext;
+    };
+    const uint32_t me = karras(s);
     int child_no[2];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const Node32 c = pairs[p].c[s];
-        int node = c.link >= 0 ? c.link : (int)(n - 1) + ~c.link;
-        child_no[s] = node;
+    for (int side = 0; side < 2; ++side) {
+        const Node32 c = pairs[s].c[side];
+        const int node = c.link >= 0 ? (int)karras((uint32_t)c.link) : (int)(n - 1) + ~c.link;
+        child_no[side] = node;
         for (int k = 0; k < 3; ++k) { out[node].lo[k] = c.lo[k]; out[node].hi[k] = c.hi[k]; }
         if (c.link < 0) out[node].left = out[node].right = -1;
     }
-    out[p].left = child_no[0];
-    out[p].right = child_no[1];
-    if (p == 0)
+    out[me].left = child_no[0];
+    out[me].right = child_no[1];
+    if (s == root)
         for (int k = 0; k < 3; ++k) { out[0].lo[k] = root_box[k]; out[0].hi[k] = root_box[3 + k]; }
 }
 
 // ---------------------------------------------------------------- structural self-checks (check.cuh:29-96)
 __global__ void __launch_bounds__(256)
-validate_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves,
-                const uint32_t* __restrict__ parent, const uint32_t* __restrict__ flags,
+validate_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, const float* __restrict__ root_box,
+                const uint32_t* __restrict__ parent_side, const uint32_t* __restrict__ refcount,
                 const uint64_t* __restrict__ keys, uint32_t n, uint32_t nverts, uint32_t* __restrict__ chk) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t root = n > 1 ? (uint32_t) reinterpret_cast<const int*>(root_box)[6] : 0u;
     if (t < n) {  // leaf checks
         if (n > 1) {
-            uint32_t pw = parent[n - 1 + t];
-            if (pw == ROOT_PARENT || (pw >> 1) >= n - 1) atomicAdd(chk + 4, 1u);
+            if (refcount[n - 1 + t] != 1u) atomicAdd(chk + 4, 1u);  // null (or duplicate) parent, check.cuh:91
             else {
+                const uint32_t pw = parent_side[n - 1 + t];
                 const Node32 me = pairs[pw >> 1].c[pw & 1u];
                 if (me.link != ~(int)t) atomicAdd(chk + 4, 1u);
                 if (!(me.lo[0] <= me.hi[0] && me.lo[1] <= me.hi[1] && me.lo[2] <= me.hi[2])) atomicAdd(chk + 6, 1u);
@@ -198,58 +306,86 @@ validate_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ 
         if (t + 1 < n && keys && !(keys[t] < keys[t + 1])) atomicAdd(chk + 7, 1u);
     }
     if (n > 1 && t < n - 1) {  // internal checks
-        uint32_t pw = parent[t];
-        if (pw == ROOT_PARENT) atomicAdd(chk + 0, 1u);
-        if (flags[t] != 2u) atomicAdd(chk + 1, 1u);
+        const uint32_t rc = refcount[t];
+        if (rc == 0u) atomicAdd(chk + 0, 1u);  // no parent: exactly one node (the root) may say so, check.cuh:74
         const Node32 L = pairs[t].c[0], R = pairs[t].c[1];
         auto bad_link = [&](int link) { return link >= 0 ? (uint32_t)link >= n - 1 : (uint32_t)~link >= n; };
-        if (bad_link(L.link)) atomicAdd(chk + 2, 1u);
-        if (bad_link(R.link)) atomicAdd(chk + 2, 1u);
-        bool okL = L.lo[0] <= L.hi[0] && L.lo[1] <= L.hi[1] && L.lo[2] <= L.hi[2];
-        bool okR = R.lo[0] <= R.hi[0] && R.lo[1] <= R.hi[1] && R.lo[2] <= R.hi[2];
+        const bool badL = bad_link(L.link), badR = bad_link(R.link);
+        if (badL) atomicAdd(chk + 2, 1u);
+        if (badR) atomicAdd(chk + 2, 1u);
+        // "bounded by exactly two children" (check.cuh:73): the children's leaf ranges must tile [first, last]
+        bool tiled = !badL && !badR && L.ext <= (int)t && (int)t < R.ext && rc <= 1u && (rc == 1u || t == root);
+        if (tiled) {
+            if (L.link >= 0) tiled = pairs[L.link].c[0].ext == L.ext && pairs[L.link].c[1].ext == (int)t;
+            else tiled = ~L.link == (int)t && L.ext == (int)t;
+        }
+        if (tiled) {
+            if (R.link >= 0) tiled = pairs[R.link].c[0].ext == (int)t + 1 && pairs[R.link].c[1].ext == R.ext;
+            else tiled = ~R.link == (int)t + 1 && R.ext == (int)t + 1;
+        }
+        if (!tiled) atomicAdd(chk + 1, 1u);
+        const bool okL = L.lo[0] <= L.hi[0] && L.lo[1] <= L.hi[1] && L.lo[2] <= L.hi[2];
+        const bool okR = R.lo[0] <= R.hi[0] && R.lo[1] <= R.hi[1] && R.lo[2] <= R.hi[2];
         if (!okL || !okR) atomicAdd(chk + 3, 1u);
-        if (pw != ROOT_PARENT && (pw >> 1) < n - 1) {  // my box, stored in my parent, must enclose my children
+        // my box (stored in my parent, or the root box) must enclose my children
+        float mlo[3], mhi[3];
+        bool have = false;
+        if (t == root) {
+            for (int k = 0; k < 3; ++k) { mlo[k] = root_box[k]; mhi[k] = root_box[3 + k]; }
+            have = true;
+        } else if (rc == 1u) {
+            const uint32_t pw = parent_side[t];
             const Node32 me = pairs[pw >> 1].c[pw & 1u];
+            for (int k = 0; k < 3; ++k) { mlo[k] = me.lo[k]; mhi[k] = me.hi[k]; }
+            have = me.link == (int)t;
+            if (!have) atomicAdd(chk + 8, 1u);
+        }
+        if (have) {
             bool enc = true;
             for (int k = 0; k < 3; ++k)
-                enc = enc && me.lo[k] <= L.lo[k] && me.lo[k] <= R.lo[k] && me.hi[k] >= L.hi[k] && me.hi[k] >= R.hi[k];
-            if (!enc || me.link != (int)t) atomicAdd(chk + 8, 1u);
+                enc = enc && mlo[k] <= L.lo[k] && mlo[k] <= R.lo[k] && mhi[k] >= L.hi[k] && mhi[k] >= R.hi[k];
+            if (!enc) atomicAdd(chk + 8, 1u);
         }
     }
 }
 
 }  // namespace
 
-void launch_hierarchy(const uint64_t* d_keys, uint32_t n, uint32_t* d_parent, cudaStream_t s) {
-    if (n < 2) return;
-    hierarchy_kernel<<<(n - 1 + 255) / 256, 256, 0, s>>>(d_keys, (int)n, d_parent);
-    count_launch();
-}
-
-void launch_refit(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, uint32_t n,
-                  const uint32_t* d_parent, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves,
-                  float* d_root_box, cudaStream_t s) {
+void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
+                       uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
+                       cudaStream_t s) {
     if (!n) return;
     if (n > 1) cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (size_t)(n - 1), s);
-    refit_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_verts, d_idx, d_sorted_ids, n, d_parent, d_flags, d_pairs,
-                                                 d_leaves, d_root_box);
+    build_kernel<<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs, d_leaves,
+                                                  d_root_box);
     count_launch();
 }
 
-void launch_export_nodes(const NodePair* d_pairs, const LeafRec*, const float* d_root_box, uint32_t n,
+// d_scratch: 2 * (2n-1) words (parent_side, refcount)
+void launch_export_nodes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t* d_scratch,
                          b200cd_node32* d_nodes_out, cudaStream_t s) {
     if (!n) return;
-    uint32_t work = n > 1 ? n - 1 : 1;
-    export_kernel<<<(work + 255) / 256, 256, 0, s>>>(d_pairs, d_root_box, n, d_nodes_out);
+    const uint32_t work = n > 1 ? n - 1 : 1;
+    if (n > 1) {
+        parent_kernel<<<(work + 255) / 256, 256, 0, s>>>(d_pairs, n, d_scratch, nullptr);
+        count_launch();
+    }
+    export_kernel<<<(work + 255) / 256, 256, 0, s>>>(d_pairs, d_root_box, d_scratch, n, d_nodes_out);
     count_launch();
 }
 
-void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const uint32_t* d_parent,
-                     const uint32_t* d_flags, const uint64_t* d_keys, uint32_t n, uint32_t nverts,
-                     uint32_t* d_checks9, cudaStream_t s) {
+void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, const uint64_t* d_keys,
+                     uint32_t n, uint32_t nverts, uint32_t* d_scratch, uint32_t* d_checks9, cudaStream_t s) {
     cudaMemsetAsync(d_checks9, 0, 9 * sizeof(uint32_t), s);
     if (!n) return;
-    validate_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_pairs, d_leaves, d_parent, d_flags, d_keys, n, nverts,
+    uint32_t* parent_side = d_scratch;
+    uint32_t* refcount = d_scratch + (2ull * n - 1);
+    cudaMemsetAsync(d_scratch, 0, sizeof(uint32_t) * 2 * (2ull * n - 1), s);
+    if (n > 1) {
+        parent_kernel<<<(n - 1 + 255) / 256, 256, 0, s>>>(d_pairs, n, parent_side, refcount);
+        count_launch();
+    }
+    validate_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_pairs, d_leaves, d_root_box, parent_side, refcount, d_keys, n, nverts,
                                                    d_checks9);
     count_launch();
 }
