@@ -65,6 +65,7 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_hist);
     cudaFree(b->d_tile_status);
     cudaFree(b->d_flags);
+    cudaFree(b->d_build_scratch);
     cudaFree(b->d_pairs);
     cudaFree(b->d_leaves);
     cudaFree(b->d_root_box);
@@ -96,6 +97,10 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
         A(dev_alloc(ctx, &b->d_keys[1], n));
         A(dev_alloc(ctx, &b->d_ids[1], n));
         A(dev_alloc(ctx, &b->d_flags, n));
+        if (rc == B200CD_OK && cudaMalloc(&b->d_build_scratch, build_tree_scratch_bytes(n)) != cudaSuccess) {
+            cudaGetLastError();
+            rc = set_error(ctx, B200CD_E_NOMEM, "cudaMalloc failed");
+        }
     }
     A(dev_alloc(ctx, &b->d_ids[0], n));
     // radix scratch is sized for the larger of the key sort and an n-pair result sort; grown on demand
@@ -156,7 +161,7 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));  // (K3 is fused into K4: ms_hierarchy stays ~0)
     launch_build_tree(m->d_verts, m->d_idx, b->d_ids[b->cur], b->d_keys[b->cur], n, b->d_flags, b->d_pairs, b->d_leaves,
-                      b->d_root_box, s);  // K3+K4
+                      b->d_root_box, b->d_build_scratch, s);  // K3+K4
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, cudaGetLastError());
     ctx->stats.sort_passes = (uint32_t)npass;
@@ -503,7 +508,7 @@ API int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* me
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));
     // the sorted keys are kept, so the same climb reproduces the same topology around the new boxes
     launch_build_tree(mesh->d_verts, mesh->d_idx, bvh->d_ids[bvh->cur], bvh->d_keys[bvh->cur], bvh->n, bvh->d_flags,
-                      bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, s);
+                      bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, bvh->d_build_scratch, s);
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, cudaGetLastError());
     ctx->stats.ms_build = -1.f;

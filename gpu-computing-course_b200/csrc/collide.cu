@@ -65,8 +65,8 @@ struct Child {
     __device__ __forceinline__ int ext() const { return __float_as_int(b.w); }
 };
 __device__ __forceinline__ void load_children(const NodePair* __restrict__ pairs, int node, Child& l, Child& r) {
-    const float4* p = reinterpret_cast<const float4*>(pairs + node);
-    l.a = __ldg(p); l.b = __ldg(p + 1); r.a = __ldg(p + 2); r.b = __ldg(p + 3);
+    ld256_nc(&pairs[node].c[0], l.a, l.b);
+    ld256_nc(&pairs[node].c[1], r.a, r.b);
 }
 
 // ---------------------------------------------------------------- K5a: entry lists
@@ -94,7 +94,7 @@ entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_
     Child* out = reinterpret_cast<Child*>(entries + (size_t)b * BR_ENTRIES);
     auto add = [&](Child c, int last) {  // entries carry the LAST leaf of their subtree in ext
         c.b.w = __int_as_float(last);
-        if (cnt < (uint32_t)BR_ENTRIES) out[cnt++] = c; else overflow = true;
+        if (cnt < (uint32_t)BR_ENTRIES) { st256(out + cnt, c.a, c.b); ++cnt; } else overflow = true;
     };
     if (p0 + 1 < n) {  // the very last leaf has no partner after it
         const int q0 = (int)p0;
@@ -186,8 +186,9 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
     const float inf = __int_as_float(0x7f800000);
     float qlo[3] = {inf, inf, inf}, qhi[3] = {-inf, -inf, -inf};
     if (q != 0xffffffffu) {
-        const float4* r = reinterpret_cast<const float4*>(leaves + q);
-        const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+        float4 r0, r1, r2, r3;
+        ld256_nc(leaves + q, r0, r1);
+        ld256_nc(reinterpret_cast<const float4*>(leaves + q) + 2, r2, r3);
         // v0 = r0.xyz, v1 = (r0.w, r1.x, r1.y), v2 = (r1.z, r1.w, r2.x); box.cuh:13-22
         qlo[0] = min3_ref(r0.x, r0.w, r1.z); qhi[0] = max3_ref(r0.x, r0.w, r1.z);
         qlo[1] = min3_ref(r0.y, r1.x, r1.w); qhi[1] = max3_ref(r0.y, r1.x, r1.w);
@@ -215,9 +216,8 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
     // keep the entries whose box overlaps the union box (order is irrelevant)
     const uint32_t nent = __ldg(entry_count + blockIdx.x);
     if (threadIdx.x < nent) {
-        const float4* e = reinterpret_cast<const float4*>(entries + (size_t)blockIdx.x * BR_ENTRIES + threadIdx.x);
         Child c;
-        c.a = __ldg(e); c.b = __ldg(e + 1);
+        ld256_nc(entries + (size_t)blockIdx.x * BR_ENTRIES + threadIdx.x, c.a, c.b);
         if (overlap(ulo, uhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y)) s_entry[atomicAdd(&s_nentry, 1u)] = c;
     }
     __syncthreads();
@@ -381,8 +381,9 @@ struct Tri {
     uint32_t i0, i1, i2, id;
 };
 __device__ __forceinline__ Tri load_tri(const LeafRec* __restrict__ leaves, uint32_t pos) {
-    const float4* r = reinterpret_cast<const float4*>(leaves + pos);
-    const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+    float4 r0, r1, r2, r3;
+    ld256_nc(leaves + pos, r0, r1);
+    ld256_nc(reinterpret_cast<const float4*>(leaves + pos) + 2, r2, r3);
     Tri t;
     t.v0 = {(double)r0.x, (double)r0.y, (double)r0.z};
     t.v1 = {(double)r0.w, (double)r1.x, (double)r1.y};
@@ -394,8 +395,9 @@ __device__ __forceinline__ Tri load_tri(const LeafRec* __restrict__ leaves, uint
 // vertices only (stage B re-reads the two records; they are L1/L2-hot)
 __device__ __forceinline__ void load_verts(const LeafRec* __restrict__ leaves, uint32_t pos, D3& v0, D3& v1, D3& v2,
                                            uint32_t& id) {
-    const float4* r = reinterpret_cast<const float4*>(leaves + pos);
-    const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+    float4 r0, r1, r2, r3;
+    ld256_nc(leaves + pos, r0, r1);
+    ld256_nc(reinterpret_cast<const float4*>(leaves + pos) + 2, r2, r3);
     v0 = {(double)r0.x, (double)r0.y, (double)r0.z};
     v1 = {(double)r0.w, (double)r1.x, (double)r1.y};
     v2 = {(double)r1.z, (double)r1.w, (double)r2.x};

@@ -115,25 +115,49 @@ __device__ void climb_global(Carry c, bool have_slot, int s, int side, const uin
         have_slot = false;
         float4 a, b;
         pack(c, side ? c.L : c.F, a, b);
-        float4* mine = reinterpret_cast<float4*>(&pairs[s].c[side]);
-        __stcg(mine, a);
-        __stcg(mine + 1, b);
+        st256_cg(&pairs[s].c[side], a, b);
         __threadfence();  // publish my half before announcing arrival
         if (atomicAdd(flags + s, 1u) == 0u) return;
         __threadfence();
-        const float4* sib = reinterpret_cast<const float4*>(&pairs[s].c[side ^ 1]);
-        const float4 sa = __ldcg(sib), sb = __ldcg(sib + 1);  // published before the sibling's atomic; read through L2
+        float4 sa, sb;
+        ld256_cg(&pairs[s].c[side ^ 1], sa, sb);  // published before the sibling's atomic; read through L2
         merge_with(c, side, sa, sb, s);
     }
+}
+
+// A subtree whose parent split lies outside its block's shared-memory range: parked in a global
+// list by build_kernel and carried up by upper_kernel, so that the 256-leaf blocks retire as soon
+// as their shared-memory climb is done instead of idling behind a few threads doing
+// fence + atomic round trips.
+struct __align__(16) Pending {
+    float4 a, b;      // Node32 image: lo.xyz hi.x | hi.yz link ext
+    int F, L;         // leaf range
+    int slot, side;   // side < 0: the parent split is still to be decided from the keys
+};
+
+__global__ void __launch_bounds__(128)
+upper_kernel(const Pending* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t capacity,
+             const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
+             float* __restrict__ root_box) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(__ldg(list_count), capacity)) return;
+    const Pending p = list[i];
+    Carry c;
+    c.lo[0] = p.a.x; c.lo[1] = p.a.y; c.lo[2] = p.a.z; c.hi[0] = p.a.w; c.hi[1] = p.b.x; c.hi[2] = p.b.y;
+    c.link = __float_as_int(p.b.z);
+    c.F = p.F; c.L = p.L;
+    climb_global(c, p.side >= 0, p.slot, p.side, keys, n, flags, pairs, root_box);
 }
 
 __global__ void __launch_bounds__(BL)
 build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ sorted_ids,
              const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
-             LeafRec* __restrict__ leaves, float* __restrict__ root_box) {
+             LeafRec* __restrict__ leaves, float* __restrict__ root_box, Pending* __restrict__ list,
+             uint32_t* __restrict__ list_count, uint32_t capacity) {
     __shared__ int s_sim[BL + 1];          // s_sim[i] = similarity of sorted positions (B0-1+i, B0+i); -1 outside
     __shared__ uint32_t s_flag[BL];        // per split B0+i: bit 0 = left child arrived, bit 1 = right child arrived
     __shared__ float4 s_dep[BL][2][2];     // per split, per side: the child's Node32 (ext as in pairs[])
+    __shared__ uint32_t s_npend, s_base;
     const int tid = threadIdx.x;
     const int B0 = blockIdx.x * BL;
     const int j = B0 + tid;
@@ -148,10 +172,9 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
         const uint32_t i0 = __ldg(f), i1 = __ldg(f + 1), i2 = __ldg(f + 2);
         const float4 a = __ldg(verts + i0), b = __ldg(verts + i1), d = __ldg(verts + i2);
         float4* rec = reinterpret_cast<float4*>(leaves + j);
-        __stcs(rec, make_float4(a.x, a.y, a.z, b.x));
-        __stcs(rec + 1, make_float4(b.y, b.z, d.x, d.y));
-        __stcs(rec + 2, make_float4(d.z, __uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2)));
-        __stcs(rec + 3, make_float4(__uint_as_float(id), 0.f, 0.f, 0.f));
+        st256(rec, make_float4(a.x, a.y, a.z, b.x), make_float4(b.y, b.z, d.x, d.y));
+        st256(rec + 2, make_float4(d.z, __uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2)),
+              make_float4(__uint_as_float(id), 0.f, 0.f, 0.f));
         // box.cuh:13-22
         c.lo[0] = min3_ref(a.x, b.x, d.x); c.lo[1] = min3_ref(a.y, b.y, d.y); c.lo[2] = min3_ref(a.z, b.z, d.z);
         c.hi[0] = max3_ref(a.x, b.x, d.x); c.hi[1] = max3_ref(a.y, b.y, d.y); c.hi[2] = max3_ref(a.z, b.z, d.z);
@@ -165,6 +188,7 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
         s_sim[tid + 1] = -1;
     }
     s_flag[tid] = 0;
+    if (tid == 0) s_npend = 0;
     __syncthreads();
 
     // ---- climb inside the block: splits s with both neighbours in the block, B0 <= s < Bend
@@ -197,32 +221,53 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
                 __threadfence_block();
                 const float4 sa = s_dep[ls][side ^ 1][0], sb = s_dep[ls][side ^ 1][1];
                 // both halves are here: write the finished node once (left child, right child)
-                float4* dst = reinterpret_cast<float4*>(pairs + s);
-                __stcs(dst + 2 * side, a);
-                __stcs(dst + 2 * side + 1, b);
-                __stcs(dst + 2 * (side ^ 1), sa);
-                __stcs(dst + 2 * (side ^ 1) + 1, sb);
+                st256(&pairs[s].c[side], a, b);
+                st256(&pairs[s].c[side ^ 1], sa, sb);
                 merge_with(c, side, sa, sb, s);
             }
         }
     }
     __syncthreads();
 
-    // ---- leftovers continue through global memory
-    if (pending) climb_global(c, false, 0, 0, keys, n, flags, pairs, root_box);
-    // a deposit whose sibling never showed up inside the block (the sibling reaches beyond it):
-    // thread t converts split B0+t into a global arrival
-    if (tid < BL - 1 && B0 + tid < Bend) {
-        const uint32_t f = s_flag[tid];
-        if (f == 1u || f == 2u) {
-            const int side = (f == 1u) ? 0 : 1;
-            const float4 a = s_dep[tid][side][0], b = s_dep[tid][side][1];
+    // ---- leftovers are parked for upper_kernel: (1) my own subtree if its parent split lies outside the
+    // block, (2) split B0+tid if only one child arrived (the sibling reaches beyond the block)
+    uint32_t f = 0;
+    if (tid < BL - 1 && B0 + tid < Bend) f = s_flag[tid];
+    const bool conv = (f == 1u || f == 2u);
+    const uint32_t mine = (pending ? 1u : 0u) + (conv ? 1u : 0u);
+    uint32_t at = 0;
+    if (mine) at = atomicAdd(&s_npend, mine);
+    __syncthreads();
+    if (tid == 0 && s_npend) s_base = atomicAdd(list_count, s_npend);
+    __syncthreads();
+    if (!mine) return;
+    at += s_base;
+    if (pending) {
+        if (at < capacity) {
+            Pending p;
+            pack(c, 0, p.a, p.b);
+            p.F = c.F; p.L = c.L; p.slot = 0; p.side = -1;
+            list[at] = p;
+        } else {
+            climb_global(c, false, 0, 0, keys, n, flags, pairs, root_box);  // list full: climb here
+        }
+        ++at;
+    }
+    if (conv) {
+        const int side = (f == 1u) ? 0 : 1;
+        const float4 a = s_dep[tid][side][0], b = s_dep[tid][side][1];
+        const int ext = __float_as_int(b.w);
+        const int s = B0 + tid;
+        Pending p;
+        p.a = a; p.b = b; p.slot = s; p.side = side;
+        if (side == 0) { p.F = ext; p.L = s; } else { p.F = s + 1; p.L = ext; }
+        if (at < capacity) {
+            list[at] = p;
+        } else {
             Carry d;
             d.lo[0] = a.x; d.lo[1] = a.y; d.lo[2] = a.z; d.hi[0] = a.w; d.hi[1] = b.x; d.hi[2] = b.y;
             d.link = __float_as_int(b.z);
-            const int ext = __float_as_int(b.w);
-            const int s = B0 + tid;
-            if (side == 0) { d.F = ext; d.L = s; } else { d.F = s + 1; d.L = ext; }
+            d.F = p.F; d.L = p.L;
             climb_global(d, true, s, side, keys, n, flags, pairs, root_box);
         }
     }
@@ -351,14 +396,28 @@ validate_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ 
 
 }  // namespace
 
+uint64_t build_tree_scratch_bytes(uint32_t n) {  // pending list + its counter
+    return 16 + sizeof(Pending) * (uint64_t)build_tree_pending_capacity(n);
+}
+uint32_t build_tree_pending_capacity(uint32_t n) { return n / 8 + 4096; }
+
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
-                       cudaStream_t s) {
+                       void* d_scratch, cudaStream_t s) {
     if (!n) return;
+    uint32_t* list_count = static_cast<uint32_t*>(d_scratch);
+    Pending* list = reinterpret_cast<Pending*>(static_cast<char*>(d_scratch) + 16);
+    const uint32_t capacity = build_tree_pending_capacity(n);
     if (n > 1) cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (size_t)(n - 1), s);
+    cudaMemsetAsync(list_count, 0, sizeof(uint32_t), s);
     build_kernel<<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs, d_leaves,
-                                                  d_root_box);
+                                                  d_root_box, list, list_count, capacity);
     count_launch();
+    {
+        upper_kernel<<<(capacity + 127) / 128, 128, 0, s>>>(list, list_count, capacity, d_keys, (int)n, d_flags, d_pairs,
+                                                            d_root_box);
+        count_launch();
+    }
 }
 
 // d_scratch: 2 * (2n-1) words (parent_side, refcount)
