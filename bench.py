@@ -72,11 +72,8 @@ def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes):
         # K2: histogram reads the keys once; every pass reads and writes (8 B key + 4 B id)
         #     (first pass generates the ids: no 4 B read)
         "sort": 8 * n + sort_passes * 24 * n - 4 * n,
-        # K3: keys in, one 4 B parent word per node out
-        "hierarchy": 8 * n + 8 * n,
-        # K4: sorted ids + indices + vertices in, 64 B leaf record + 64 B node pair out, sibling
-        #     half (32 B) read back by the merging thread, parent word + arrival flag per node
-        "refit": 4 * n + 12 * n + 16 * nverts + 64 * n + 64 * n + 32 * n + 8 * n + 8 * n,
+        # K3+K4 (fused): sorted ids + keys + indices + vertices in, 64 B leaf record + 64 B node pair out
+        "tree": 4 * n + 8 * n + 12 * n + 16 * nverts + 64 * n + 64 * n,
         # K5: every node pair (64 B) and every query record (64 B) once, 8 B per candidate out
         "traverse": 64 * n + 64 * n + 8 * ncand,
         # K6: candidate in, two 64 B leaf records per candidate, 8 B per pair out
@@ -84,8 +81,8 @@ def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes):
     }
 
 
-STAGE_KERNEL = {"morton": "morton_kernel", "sort": "rs_pass (x passes) + rs_histogram", "hierarchy": "hierarchy_kernel",
-                "refit": "refit_kernel", "traverse": "broad_kernel", "narrow": "narrow_kernel"}
+STAGE_KERNEL = {"morton": "morton_kernel", "sort": "rs_pass (x passes) + rs_histogram", "tree": "build_kernel (+ upper_kernel)",
+                "traverse": "broad_kernel (+ entry_kernel)", "narrow": "narrow_kernel"}
 
 
 class ClockSampler(threading.Thread):
@@ -342,13 +339,13 @@ def run_gpu_arm(args, workload):
         if world > 1:  # per-rank share of the query stages
             abytes["traverse"] = 64 * ntris + 64 * ntris // world + 8 * ncand
         stages = {}
-        for s, key in (("morton", "ms_morton"), ("sort", "ms_sort"), ("hierarchy", "ms_hierarchy"), ("refit", "ms_refit"),
+        for s, key in (("morton", "ms_morton"), ("sort", "ms_sort"), ("tree", "ms_refit"),
                        ("traverse", "ms_traverse"), ("narrow", "ms_narrow")):
             ms = acc[key] / K
             gbs = abytes[s] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             stages[s] = {"kernel": STAGE_KERNEL[s], "ms": round(ms, 4), "algorithmic_bytes": int(abytes[s]),
                          "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
-        dominant = max(("morton", "hierarchy", "refit", "traverse", "narrow"), key=lambda s: stages[s]["ms"])
+        dominant = max(("morton", "tree", "traverse", "narrow"), key=lambda s: stages[s]["ms"])
         sort_launch_ms = stages["sort"]["ms"] / max(int(last.get("sort_passes", 8)), 1)
         if sort_launch_ms > stages[dominant]["ms"]:
             dominant = "sort"
@@ -364,6 +361,11 @@ def run_gpu_arm(args, workload):
                     "e2e_algorithmic_bytes": int(sum(abytes.values())),
                     "e2e_frac": round(sum(abytes.values()) / ((acc["ms_build"] + acc["ms_query"]) / K * 1e-3) / 1e9 / peak, 4)
                     if acc["ms_build"] + acc["ms_query"] > 0 else None}
+        trav_ms = acc["ms_traverse"] / K
+        traversal = {"nodes_visited_per_query": round(last.get("nodes_visited", 0) / max(ntris // world, 1), 2),
+                     "gnodes_per_s": round(last.get("nodes_visited", 0) / (trav_ms * 1e-3) / 1e9, 2) if trav_ms > 0 else None,
+                     "lane_utilisation": round(last.get("nodes_visited", 0) / max(32 * last.get("warp_steps", 0), 1), 3),
+                     "candidates": ncand, "pairs": npairs}
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
@@ -377,7 +379,7 @@ def run_gpu_arm(args, workload):
             "bvh_build_ms": round(acc["ms_build"] / K, 4), "query_ms": round(acc["ms_query"] / K, 4),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / K, 4)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "traversal": traversal,
         }
         if world == 1 and not args.no_cpu_baseline:
             vals, info = cpu_reference_run(workload, args.cpu_sample, 1)
