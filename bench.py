@@ -10,8 +10,10 @@ list). Workloads (BASELINE.json `configs`):
     sheets64m  C5  two 4096x4096-quad sheets, 2^26 triangles               (default at N > 1)
     cloth1m    C3  accordion-folded sheet, 1 002 528 triangles, dense contacts
     flag1m     C1/C2 stand-in for the missing flag mesh, 1 262 460 triangles
-N > 1: one rank per GPU (torchrun), query-sharded over ranks with a replicated BVH, per-rank pair
-lists gathered over NCCL and sorted on rank 0; strong scaling (the mesh is fixed).
+N > 1: one rank per GPU (torchrun). Default: the build and the query are PARTITIONED - each rank owns
+one Morton range of the triangles (distributed sort over NCCL, local tree + query, ghost exchange);
+--mode replicated: every rank builds the whole BVH and the queries are sharded. Either way the
+per-rank pair lists are gathered over NCCL and sorted on rank 0; strong scaling (the mesh is fixed).
 
 Prints ONE JSON line on rank 0. `value` = triangles / device time with the mesh resident in HBM;
 `e2e` = the same through the host-buffer C-ABI calls (H2D of the mesh and D2H of the pair list
@@ -26,6 +28,11 @@ import subprocess
 import sys
 import threading
 import time
+
+# rank 0 must print exactly ONE line on stdout; NCCL_DEBUG=VERSION (set in this image) makes NCCL
+# printf its banner there, so drop that level (warnings and above are kept if asked for)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    del os.environ["NCCL_DEBUG"]
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -255,9 +262,22 @@ def run_gpu_arm(args, workload):
     params = cd.make_params(*box) if box else cd.default_params()
 
     ctx = cd.Context(local_rank)
-    runner = mgpu.ShardedSelfCollision(cd, ctx, chunk=args.chunk)  # binds the library to torch's current stream
     mesh = ctx.mesh_from_host_ptr(xyz_ptr, nverts, idx_ptr, ntris)
-    bvh = ctx.bvh_build(mesh, params)
+    partitioned = world > 1 and args.mode == "partitioned"
+    if partitioned:
+        # each rank owns one Morton range: distributed sort, local tree + query, ghost exchange (multigpu.py)
+        prunner = mgpu.PartitionedSelfCollision(cd, ctx, mesh, params)
+        bvh = prunner.part.bvh
+
+        class _Step:
+            counts = property(lambda self: prunner.counts)
+
+            def step(self, bvh_, mesh_, params_):
+                return prunner.step()
+        runner = _Step()
+    else:
+        runner = mgpu.ShardedSelfCollision(cd, ctx, chunk=args.chunk)  # binds the library to torch's current stream
+        bvh = ctx.bvh_build(mesh, params)
 
     def barrier():
         if world > 1:
@@ -324,6 +344,9 @@ def run_gpu_arm(args, workload):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
 
+    if partitioned:
+        prunner.step(profile=True)  # one extra, untimed step (all ranks) with a synchronise after every phase
+
     if rank == 0:
         K = args.steps
         ms_step = ms_total / K
@@ -336,7 +359,10 @@ def run_gpu_arm(args, workload):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         ncand, npairs = int(last.get("candidates", 0)), int(last.get("pairs", 0))
         abytes = algorithmic_bytes(ntris, nverts, ncand, npairs, int(last.get("sort_passes", 8)))
-        if world > 1:  # per-rank share of the query stages
+        if partitioned:  # rank 0's own Morton range
+            nloc = int(prunner.stats.get("local_triangles", ntris // world))
+            abytes = algorithmic_bytes(nloc, min(nverts, 3 * nloc), ncand, npairs, int(last.get("sort_passes", 8)))
+        elif world > 1:  # per-rank share of the query stages
             abytes["traverse"] = 64 * ntris + 64 * ntris // world + 8 * ncand
         stages = {}
         for s, key in (("morton", "ms_morton"), ("sort", "ms_sort"), ("tree", "ms_refit"),
@@ -373,14 +399,19 @@ def run_gpu_arm(args, workload):
             "config": {"workload": workload, "triangles": ntris, "vertices": nverts,
                        "morton_box": "unit cube" if box else "reference constants (morton.h:45,51,57)",
                        "key_bits": 63, "pairs": npairs_total,
-                       "parallelism": "single GPU" if world == 1 else f"query-sharded x{world}, replicated BVH, "
-                                      f"block-cyclic chunks of {args.chunk} sorted leaves, NCCL gather + sort on rank 0",
+                       "parallelism": "single GPU" if world == 1 else (
+                           f"partitioned x{world}: one Morton range per rank (NCCL all-to-all of (key,id)), local tree + query, "
+                           f"ghost exchange, NCCL gather + sort on rank 0" if partitioned else
+                           f"query-sharded x{world}, replicated BVH, block-cyclic chunks of {args.chunk} sorted leaves, "
+                           f"NCCL gather + sort on rank 0"),
                        "l2_policy": "inputs larger than L2 (mesh + BVH >> 126 MB); no explicit flush"},
             "bvh_build_ms": round(acc["ms_build"] / K, 4), "query_ms": round(acc["ms_query"] / K, 4),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / K, 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "traversal": traversal,
         }
+        if partitioned:
+            line["partition"] = dict(prunner.stats, rank=0, build_ms=ctx.stats()["ms_build"], query_ms=ctx.stats()["ms_query"])
         if world == 1 and not args.no_cpu_baseline:
             vals, info = cpu_reference_run(workload, args.cpu_sample, 1)
             line["cpu_baseline"] = {"value": round(vals[0], 4), "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
@@ -402,6 +433,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="partitioned", choices=["partitioned", "replicated"],
+                    help="N > 1: one Morton range per rank (default) or replicated BVH with sharded queries")
     ap.add_argument("--chunk", type=int, default=1 << 14, help="sorted leaves per block-cyclic query chunk (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 21, help="triangles in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

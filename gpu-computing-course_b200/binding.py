@@ -29,6 +29,9 @@ SYMBOLS = [
     "b200cd_bvh_build", "b200cd_bvh_rebuild", "b200cd_bvh_refit", "b200cd_bvh_download", "b200cd_bvh_validate",
     "b200cd_bvh_destroy", "b200cd_self_collide", "b200cd_self_collide_shard", "b200cd_self_collide_device",
     "b200cd_sort_pairs_device", "b200cd_bvh_view_get", "b200cd_bvh_alloc_like",
+    "b200cd_morton_keys_device", "b200cd_key_histogram_device", "b200cd_bvh_alloc_partial", "b200cd_bvh_key_buffers",
+    "b200cd_partition_keys_device", "b200cd_bvh_build_partial", "b200cd_bvh_chunk_boxes_device",
+    "b200cd_select_ghosts_device", "b200cd_bvh_ghost_buffer", "b200cd_collide_ghosts_device",
 ]
 
 
@@ -208,7 +211,9 @@ class Context:
             raise B200cdError(rc, where, lib().b200cd_last_error(self.h).decode())
 
     def set_stream(self, cuda_stream_handle):
-        self._chk(lib().b200cd_set_stream(self.h, C.c_void_p(cuda_stream_handle)), "set_stream")
+        """cudaStream_t handle as an int (0 = the legacy default stream); None = the context's private stream"""
+        h = C.c_void_p(-1) if cuda_stream_handle is None else C.c_void_p(cuda_stream_handle)
+        self._chk(lib().b200cd_set_stream(self.h, h), "set_stream")
 
     def synchronize(self):
         self._chk(lib().b200cd_synchronize(self.h), "synchronize")
@@ -299,6 +304,60 @@ class Context:
         self._chk(lib().b200cd_self_collide_device(self.h, bvh.h, C.c_uint32(shard), C.c_uint32(nshards),
                                                    C.c_uint32(chunk), C.c_int(1 if sorted else 0), C.byref(ptr),
                                                    C.byref(cnt)), "self_collide_device")
+        return ptr.value, int(cnt.value)
+
+    # ---- partitioned multi-GPU build (include/b200cd.h, "partitioned multi-GPU build"); raw device pointers
+    def morton_keys_device(self, mesh, params, first, count, d_keys_out):
+        self._chk(lib().b200cd_morton_keys_device(self.h, mesh.h, C.byref(params), C.c_uint32(first), C.c_uint32(count),
+                                                  C.c_void_p(d_keys_out)), "morton_keys_device")
+
+    def key_histogram_device(self, d_keys, count, shift, d_hist):
+        self._chk(lib().b200cd_key_histogram_device(self.h, C.c_void_p(d_keys), C.c_uint32(count), C.c_int32(shift),
+                                                    C.c_void_p(d_hist)), "key_histogram_device")
+
+    def bvh_alloc_partial(self, capacity, ghost_capacity, max_peers):
+        b = C.c_void_p()
+        self._chk(lib().b200cd_bvh_alloc_partial(self.h, C.c_uint32(capacity), C.c_uint64(ghost_capacity),
+                                                 C.c_uint32(max_peers), C.byref(b)), "bvh_alloc_partial")
+        return Bvh(self, b, 0)
+
+    def bvh_key_buffers(self, bvh):
+        k, i, cap = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        self._chk(lib().b200cd_bvh_key_buffers(self.h, bvh.h, C.byref(k), C.byref(i), C.byref(cap)), "bvh_key_buffers")
+        return k.value, i.value, cap.value
+
+    def partition_keys_device(self, bvh, d_keys, first_id, count, d_splitters, nsplit, d_keys_out, d_ids_out):
+        counts = (C.c_uint64 * (nsplit + 1))()
+        self._chk(lib().b200cd_partition_keys_device(self.h, bvh.h, C.c_void_p(d_keys), C.c_uint32(first_id), C.c_uint32(count),
+                                                     C.c_void_p(d_splitters), C.c_uint32(nsplit), C.c_void_p(d_keys_out),
+                                                     C.c_void_p(d_ids_out), counts), "partition_keys_device")
+        return [int(c) for c in counts]
+
+    def bvh_build_partial(self, bvh, mesh, params, count):
+        self._chk(lib().b200cd_bvh_build_partial(self.h, bvh.h, mesh.h, C.byref(params), C.c_uint32(count)), "bvh_build_partial")
+        bvh.ntris = count
+
+    def bvh_chunk_boxes_device(self, bvh, K, d_boxes_out):
+        self._chk(lib().b200cd_bvh_chunk_boxes_device(self.h, bvh.h, C.c_uint32(K), C.c_void_p(d_boxes_out)), "bvh_chunk_boxes_device")
+
+    def select_ghosts_device(self, bvh, d_peer_boxes, npeers, K, peer_mask):
+        """-> (device pointer of the per-peer lists, stride in records, [count per peer])"""
+        ptr, stride = C.c_void_p(), C.c_uint64()
+        counts = (C.c_uint64 * npeers)()
+        self._chk(lib().b200cd_select_ghosts_device(self.h, bvh.h, C.c_void_p(d_peer_boxes), C.c_uint32(npeers), C.c_uint32(K),
+                                                    C.c_uint32(peer_mask), C.byref(ptr), C.byref(stride), counts),
+                  "select_ghosts_device")
+        return ptr.value, int(stride.value), [int(c) for c in counts]
+
+    def bvh_ghost_buffer(self, bvh):
+        ptr, cap = C.c_void_p(), C.c_uint64()
+        self._chk(lib().b200cd_bvh_ghost_buffer(self.h, bvh.h, C.byref(ptr), C.byref(cap)), "bvh_ghost_buffer")
+        return ptr.value, int(cap.value)
+
+    def collide_ghosts_device(self, bvh, nghost, keep_pairs=True):
+        cnt, ptr = C.c_uint64(), C.c_void_p()
+        self._chk(lib().b200cd_collide_ghosts_device(self.h, bvh.h, C.c_uint64(nghost), C.c_int(1 if keep_pairs else 0),
+                                                     C.byref(ptr), C.byref(cnt)), "collide_ghosts_device")
         return ptr.value, int(cnt.value)
 
     def sort_pairs_device(self, d_ptr, count, id_bits=0):

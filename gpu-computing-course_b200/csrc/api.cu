@@ -68,6 +68,7 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_build_scratch);
     cudaFree(b->d_pairs);
     cudaFree(b->d_leaves);
+    cudaFree(b->d_ghost_out);
     cudaFree(b->d_root_box);
     cudaFree(b->d_cand);
     cudaFree(b->d_entries);
@@ -84,11 +85,14 @@ int id_bits_for(uint32_t n) {
     return n <= 1 ? 1 : b;
 }
 
-int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200cd_bvh** out) {
+int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200cd_bvh** out, uint64_t ghost_cap = 0,
+              uint32_t max_peers = 0) {
     b200cd_bvh* b = new (std::nothrow) b200cd_bvh;
     if (!b) return set_error(ctx, B200CD_E_NOMEM, "host allocation failed");
     b->ctx = ctx;
     b->n = n;
+    b->cap = n;
+    b->ghost_cap = ghost_cap;
     b->nverts = nverts;
     int rc = B200CD_OK;
     auto A = [&](int r) { if (rc == B200CD_OK) rc = r; };
@@ -108,7 +112,11 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
     A(dev_alloc(ctx, &b->d_hist, radix_hist_words(8)));
     A(dev_alloc(ctx, &b->d_tile_status, b->tile_status_words));
     A(dev_alloc(ctx, &b->d_pairs, n));
-    A(dev_alloc(ctx, &b->d_leaves, n));
+    A(dev_alloc(ctx, &b->d_leaves, (uint64_t)n + ghost_cap));  // ghost records of a partitioned build live after the local leaves
+    if (max_peers) {
+        b->ghost_out_cap = ghost_cap;
+        A(dev_alloc(ctx, &b->d_ghost_out, (uint64_t)max_peers * ghost_cap));
+    }
     A(dev_alloc(ctx, &b->d_root_box, 8));
     A(dev_alloc(ctx, &b->d_counters, 8));
     if (rc == B200CD_OK && cudaMallocHost(reinterpret_cast<void**>(&b->h_counters), 8 * sizeof(unsigned long long)) != cudaSuccess)
@@ -131,21 +139,23 @@ int check_params(b200cd_ctx* ctx, const b200cd_params* p) {
     return B200CD_OK;
 }
 
-int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd_params* p) {
+// keys_given: d_keys[0] / d_ids[0] already hold (key, triangle id) of the n triangles of this tree
+// (partitioned multi-GPU build); otherwise K1 computes the keys of the whole mesh and ids are 0..n-1.
+int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd_params* p, bool keys_given = false) {
     cudaStream_t s = ctx->stream;
     const uint32_t n = b->n;
     b->params = *p;
     b->built = false;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
     int npass = 0;
-    if (n) {
+    if (n && !keys_given) {
         // K1
         uint32_t* d_bbox = nullptr;
         if (p->auto_box) {
             d_bbox = ctx->d_scalars;
             launch_bbox(m->d_verts, m->nverts, d_bbox, ctx->sm_count, s);
         }
-        launch_morton(m->d_verts, m->d_idx, n, *p, d_bbox, b->d_keys[0], s);
+        launch_morton(m->d_verts, m->d_idx, 0, n, *p, d_bbox, b->d_keys[0], s);
     }
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
     if (n) {
@@ -155,7 +165,7 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
         RadixPass passes[8];
         const int total_bits = (p->key_bits == 30) ? 30 : 63;
         for (int sh = 0; sh < total_bits; sh += 8) passes[npass++] = {sh, std::min(8, total_bits - sh)};
-        b->cur = radix_sort(b->d_keys, b->d_ids, n, passes, npass, /*iota*/ true, b->d_hist, b->d_tile_status,
+        b->cur = radix_sort(b->d_keys, b->d_ids, n, passes, npass, /*iota*/ !keys_given, b->d_hist, b->d_tile_status,
                             b->tile_status_words, ctx->sm_count, s);
     }
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
@@ -164,6 +174,8 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
                       b->d_root_box, b->d_build_scratch, s);  // K3+K4
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, cudaGetLastError());
+    b->id_space = keys_given ? m->ntris : n;
+    b->npairs = 0;
     ctx->stats.sort_passes = (uint32_t)npass;
     ctx->stats.ntris = n;
     ctx->stats.nverts = m->nverts;
@@ -245,7 +257,7 @@ API int b200cd_set_stream(b200cd_ctx* ctx, void* cuda_stream) {
     if (!ctx) return B200CD_E_INVALID;
     DeviceGuard g(ctx->device);
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = (cuda_stream == B200CD_PRIVATE_STREAM) ? ctx->own_stream : static_cast<cudaStream_t>(cuda_stream);
     return B200CD_OK;
 }
 
@@ -599,6 +611,123 @@ API int b200cd_bvh_alloc_like(b200cd_ctx* ctx, uint32_t ntris, b200cd_bvh** out)
     return B200CD_OK;
 }
 
+// ------------------------------------------------------------------ partitioned (multi-GPU) build
+
+API int b200cd_morton_keys_device(b200cd_ctx* ctx, const b200cd_mesh* mesh, const b200cd_params* params, uint32_t first,
+                                  uint32_t count, void* d_keys_out) {
+    if (!ctx || !mesh || (count && !d_keys_out)) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    int rc = check_params(ctx, params);
+    if (rc != B200CD_OK) return rc;
+    if (params->auto_box) return set_error(ctx, B200CD_E_INVALID, "auto_box is not available for a partitioned build: pass the box");
+    if ((uint64_t)first + count > mesh->ntris) return set_error(ctx, B200CD_E_INVALID, "triangle slice out of range");
+    DeviceGuard g(ctx->device);
+    launch_morton(mesh->d_verts, mesh->d_idx, first, count, *params, nullptr, static_cast<uint64_t*>(d_keys_out), ctx->stream);
+    CD_CUDA(ctx, cudaGetLastError());
+    return B200CD_OK;
+}
+
+API int b200cd_key_histogram_device(b200cd_ctx* ctx, const void* d_keys, uint32_t count, int32_t shift, void* d_hist65536) {
+    if (!ctx || (count && !d_keys) || !d_hist65536 || shift < 0 || shift > 63) return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    DeviceGuard g(ctx->device);
+    launch_key_hist16(static_cast<const uint64_t*>(d_keys), count, shift, static_cast<uint32_t*>(d_hist65536), ctx->sm_count,
+                      ctx->stream);
+    CD_CUDA(ctx, cudaGetLastError());
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_alloc_partial(b200cd_ctx* ctx, uint32_t capacity, uint64_t ghost_capacity, uint32_t max_peers,
+                                 b200cd_bvh** out) {
+    if (!ctx || !out || max_peers > 32) return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    *out = nullptr;
+    if (capacity > (1u << B200CD_MAX_TRIS_LOG2) || capacity + ghost_capacity > (1ull << 31))
+        return set_error(ctx, B200CD_E_TOOBIG, "partial BVH too large");
+    DeviceGuard g(ctx->device);
+    b200cd_bvh* b = nullptr;
+    int rc = alloc_bvh(ctx, capacity, 0, true, &b, ghost_capacity, max_peers);
+    if (rc != B200CD_OK) return rc;
+    b->n = 0;
+    *out = b;
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_key_buffers(b200cd_ctx* ctx, b200cd_bvh* bvh, void** d_keys, void** d_ids, uint32_t* capacity) {
+    if (!ctx || !bvh || !bvh->d_keys[0]) return set_error(ctx, B200CD_E_INVALID, "BVH has no key buffers");
+    if (d_keys) *d_keys = bvh->d_keys[0];
+    if (d_ids) *d_ids = bvh->d_ids[0];
+    if (capacity) *capacity = bvh->cap;
+    return B200CD_OK;
+}
+
+API int b200cd_partition_keys_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_keys, uint32_t first_id, uint32_t count,
+                                     const void* d_splitters, uint32_t nsplit, void* d_keys_out, void* d_ids_out,
+                                     uint64_t* counts_out) {
+    if (!ctx || !bvh || !counts_out || (count && (!d_keys || !d_keys_out || !d_ids_out)) || (nsplit && !d_splitters) || nsplit > 15)
+        return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    if (radix_tile_status_words(count, 1) > bvh->tile_status_words) return set_error(ctx, B200CD_E_INVALID, "slice larger than the BVH's scratch");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    radix_partition(static_cast<const uint64_t*>(d_keys), nullptr, first_id, static_cast<uint64_t*>(d_keys_out),
+                    static_cast<uint32_t*>(d_ids_out), count, static_cast<const uint64_t*>(d_splitters), (int)nsplit, bvh->d_hist,
+                    bvh->d_tile_status, ctx->sm_count, s);
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, bvh->d_hist + 256, sizeof(uint32_t) * (nsplit + 1), cudaMemcpyDeviceToHost, s));
+    CD_CUDA(ctx, cudaStreamSynchronize(s));
+    CD_CUDA(ctx, cudaGetLastError());
+    for (uint32_t d = 0; d <= nsplit; ++d) counts_out[d] = ctx->h_scalars[d];
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_build_partial(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh, const b200cd_params* params,
+                                 uint32_t count) {
+    if (!ctx || !bvh || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (!bvh->d_keys[0] || count > bvh->cap) return set_error(ctx, B200CD_E_CAPACITY, "more triangles than the partial BVH was allocated for");
+    int rc = check_params(ctx, params);
+    if (rc != B200CD_OK) return rc;
+    DeviceGuard g(ctx->device);
+    bvh->n = count;
+    bvh->nverts = mesh->nverts;
+    return run_build(ctx, bvh, mesh, params, /*keys_given*/ true);
+}
+
+API int b200cd_bvh_chunk_boxes_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t K, void* d_boxes_out) {
+    if (!ctx || !bvh || !d_boxes_out || K == 0 || K > (uint32_t)ghost_max_k()) return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    if (!bvh->built) return set_error(ctx, B200CD_E_INVALID, "BVH not built");
+    DeviceGuard g(ctx->device);
+    launch_chunk_boxes(bvh->d_leaves, bvh->n, K, static_cast<float*>(d_boxes_out), ctx->stream);
+    CD_CUDA(ctx, cudaGetLastError());
+    return B200CD_OK;
+}
+
+API int b200cd_select_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_peer_boxes, uint32_t npeers, uint32_t K,
+                                    uint32_t peer_mask, const void** d_ghosts_out, uint64_t* stride_out, uint64_t* counts_out) {
+    if (!ctx || !bvh || !d_peer_boxes || !counts_out || npeers == 0 || npeers > 32 || K == 0 || K > (uint32_t)ghost_max_k())
+        return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    if (!bvh->built || !bvh->d_ghost_out) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(ctx->d_scalars);  // 32 x u64 = 64 words
+    launch_ghosts(bvh->d_leaves, bvh->n, static_cast<const float*>(d_peer_boxes), npeers, K, peer_mask, bvh->d_ghost_out,
+                  bvh->ghost_out_cap, d_counts, s);
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, d_counts, sizeof(unsigned long long) * npeers, cudaMemcpyDeviceToHost, s));
+    CD_CUDA(ctx, cudaStreamSynchronize(s));
+    CD_CUDA(ctx, cudaGetLastError());
+    bool over = false;
+    for (uint32_t p = 0; p < npeers; ++p) {
+        counts_out[p] = reinterpret_cast<unsigned long long*>(ctx->h_scalars)[p];
+        over = over || counts_out[p] > bvh->ghost_out_cap;
+    }
+    if (d_ghosts_out) *d_ghosts_out = bvh->d_ghost_out;
+    if (stride_out) *stride_out = bvh->ghost_out_cap;
+    if (over) return set_error(ctx, B200CD_E_CAPACITY, "ghost list larger than ghost_capacity");
+    return B200CD_OK;
+}
+
+API int b200cd_bvh_ghost_buffer(b200cd_ctx* ctx, b200cd_bvh* bvh, void** d_ptr, uint64_t* capacity) {
+    if (!ctx || !bvh || !d_ptr) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    *d_ptr = bvh->d_leaves + bvh->n;  // right after the local leaves of the CURRENT build
+    if (capacity) *capacity = bvh->ghost_cap + (bvh->cap - bvh->n);
+    return B200CD_OK;
+}
+
 // ------------------------------------------------------------------ query
 
 namespace {
@@ -686,8 +815,8 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
     for (int attempt = 0; attempt < 4; ++attempt) {
         if (need_broad) {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
-            launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, shard, nshards, chunk, nquery, b->d_entries, b->d_entry_count, b->d_cand,
-                         b->cand_cap, b->d_counters, s);
+            launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, shard, nshards, chunk, nquery, /*foreign*/ 0, b->d_entries,
+                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
         } else {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), s));
@@ -719,11 +848,12 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
         ctx->stats.nodes_visited = b->h_counters[3];
         ctx->stats.warp_steps = b->h_counters[4];
         ctx->stats.start_entries = b->h_counters[5];
+        b->npairs = npair;
         *count_out = npair;
         if (sorted && npair > 1) {
             rc = grow(ctx, &b->d_out_tmp, &b->out_tmp_cap, b->out_cap);
             if (rc != B200CD_OK) return rc;
-            rc = sort_pairs_impl(ctx, &b->d_out, &b->d_out_tmp, npair, id_bits_for(n), &b->d_hist, &b->d_tile_status,
+            rc = sort_pairs_impl(ctx, &b->d_out, &b->d_out_tmp, npair, id_bits_for(b->id_space ? b->id_space : n), &b->d_hist, &b->d_tile_status,
                                  &b->tile_status_words, s);
             if (rc != B200CD_OK) return rc;
         }
@@ -739,7 +869,82 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
     return set_error(ctx, B200CD_E_CUDA, "query did not converge after growing its buffers");
 }
 
+// Ghost queries of a partitioned build: the nghost records stored after the local leaves are
+// tested against the whole local tree. keep != 0 appends to the pair list of the last local query.
+int run_ghost_query(b200cd_ctx* ctx, b200cd_bvh* b, uint64_t nghost, int keep, uint64_t* count_out) {
+    if (!b->built) return set_error(ctx, B200CD_E_INVALID, "BVH not built");
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = b->n;
+    const uint64_t base = keep ? b->npairs : 0;
+    *count_out = base;
+    if (nghost > b->ghost_cap + (b->cap - n)) return set_error(ctx, B200CD_E_CAPACITY, "more ghosts than the BVH has room for");
+    if (nghost == 0 || n == 0) return B200CD_OK;
+    if (nghost > 0xffffff00ull) return set_error(ctx, B200CD_E_TOOBIG, "too many ghost queries");
+    const uint32_t nquery = (uint32_t)nghost;
+    int rc = grow(ctx, &b->d_cand, &b->cand_cap, std::max<uint64_t>(b->cand_cap, 4ull * nquery + 4096));
+    if (rc != B200CD_OK) return rc;
+    auto grow_out_keep = [&](uint64_t want) -> int {  // enlarge d_out without losing the first `base` pairs
+        if (b->out_cap >= want && b->d_out) return B200CD_OK;
+        uint2* bigger = nullptr;
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&bigger), want * sizeof(uint2)));
+        if (base && b->d_out) {
+            cudaError_t e = cudaMemcpyAsync(bigger, b->d_out, base * sizeof(uint2), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(bigger); CD_CUDA(ctx, e); }
+        }
+        cudaFree(b->d_out);
+        b->d_out = bigger;
+        b->out_cap = want;
+        return B200CD_OK;
+    };
+    rc = grow_out_keep(base + nquery / 2 + 4096);
+    if (rc != B200CD_OK) return rc;
+    bool need_broad = true;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (need_broad) CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
+        b->h_counters[7] = base;
+        CD_CUDA(ctx, cudaMemcpyAsync(b->d_counters + 1, b->h_counters + 7, sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        if (need_broad)
+            launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, 0, 1, B200CD_QUERY_BLOCK, nquery, /*foreign*/ 1, b->d_entries,
+                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s);
+        launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s);
+        CD_CUDA(ctx, cudaMemcpyAsync(b->h_counters, b->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CD_CUDA(ctx, cudaStreamSynchronize(s));
+        CD_CUDA(ctx, cudaGetLastError());
+        const uint64_t ncand = b->h_counters[0], npair = b->h_counters[1];
+        if (b->h_counters[2] & 1ull)
+            return set_error(ctx, B200CD_E_DEPTH, "traversal stack of " + std::to_string(B200CD_MAX_STACK) + " entries exhausted");
+        if (ncand > b->cand_cap) {
+            rc = grow(ctx, &b->d_cand, &b->cand_cap, ncand + ncand / 16);
+            if (rc != B200CD_OK) return rc;
+            need_broad = true;
+            continue;
+        }
+        if (npair > b->out_cap) {
+            rc = grow_out_keep(npair + npair / 16);
+            if (rc != B200CD_OK) return rc;
+            need_broad = false;
+            continue;
+        }
+        ctx->stats.candidates += ncand;
+        ctx->stats.pairs = npair;
+        b->npairs = npair;
+        *count_out = npair;
+        return B200CD_OK;
+    }
+    return set_error(ctx, B200CD_E_CUDA, "ghost query did not converge after growing its buffers");
+}
+
 }  // namespace
+
+API int b200cd_collide_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint64_t nghost, int keep_pairs,
+                                     const void** d_pairs_out, uint64_t* count_out) {
+    if (!ctx || !bvh || !count_out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    DeviceGuard g(ctx->device);
+    int rc = run_ghost_query(ctx, bvh, nghost, keep_pairs, count_out);
+    if (d_pairs_out) *d_pairs_out = (rc == B200CD_OK) ? bvh->d_out : nullptr;
+    return rc;
+}
 
 API int b200cd_self_collide_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t shard, uint32_t nshards, uint32_t chunk,
                                    int sorted, const void** d_pairs_out, uint64_t* count_out) {

@@ -162,10 +162,10 @@ entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_
 
 // ---------------------------------------------------------------- K5b: traversal
 __global__ void __launch_bounds__(BR_THREADS)
-broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, uint32_t n, uint32_t shard,
-             uint32_t nshards, uint32_t chunk, uint32_t nquery, const Node32* __restrict__ entries,
-             const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand, uint64_t cand_cap,
-             unsigned long long* __restrict__ counters) {
+broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, const float* __restrict__ root_box,
+             uint32_t n, uint32_t shard, uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign,
+             const Node32* __restrict__ entries, const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand,
+             uint64_t cand_cap, unsigned long long* __restrict__ counters) {
     __shared__ uint2 queue[BR_WARPS][BR_QUEUE];
     __shared__ Child s_entry[BR_ENTRIES];
     __shared__ float s_red[BR_WARPS][6];
@@ -178,10 +178,18 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
 
     // this thread's query (sorted leaf position)
     const uint32_t t = blockIdx.x * BR_THREADS + threadIdx.x;
+    // q = where the query's record lives (and what the candidate list reports); qcmp = the position
+    // the "only leaves after me" rule compares against (-1 for a ghost query: every local leaf counts)
     uint32_t q = 0xffffffffu;
+    int qcmp = 0x7fffffff;
     if (t < nquery) {
-        const uint64_t qq = query_position(t, shard, nshards, chunk);
-        if (qq + 1 < n) q = (uint32_t)qq;  // the last leaf has no partner with a larger position
+        if (foreign) {
+            q = n + t;
+            qcmp = -1;
+        } else {
+            const uint64_t qq = query_position(t, shard, nshards, chunk);
+            if (qq + 1 < n) { q = (uint32_t)qq; qcmp = (int)qq; }  // the last leaf has no partner with a larger position
+        }
     }
     const float inf = __int_as_float(0x7f800000);
     float qlo[3] = {inf, inf, inf}, qhi[3] = {-inf, -inf, -inf};
@@ -214,10 +222,19 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
         for (int w = 1; w < BR_WARPS; ++w) { ulo[k] = fminf(ulo[k], s_red[w][k]); uhi[k] = fmaxf(uhi[k], s_red[w][3 + k]); }
     }
     // keep the entries whose box overlaps the union box (order is irrelevant)
-    const uint32_t nent = __ldg(entry_count + blockIdx.x);
+    const uint32_t nent = foreign ? (n > 1 ? 2u : 1u) : __ldg(entry_count + blockIdx.x);
     if (threadIdx.x < nent) {
         Child c;
-        ld256_nc(entries + (size_t)blockIdx.x * BR_ENTRIES + threadIdx.x, c.a, c.b);
+        if (!foreign) {
+            ld256_nc(entries + (size_t)blockIdx.x * BR_ENTRIES + threadIdx.x, c.a, c.b);
+        } else if (n > 1) {  // ghost queries start at the root: its two children, ext = last leaf
+            const int root = reinterpret_cast<const int*>(root_box)[6];
+            ld256_nc(&pairs[root].c[threadIdx.x], c.a, c.b);
+            if (threadIdx.x == 0) c.b.w = __int_as_float(root);
+        } else {             // a one-leaf tree has no internal node: the leaf itself is the only entry
+            c.a = make_float4(root_box[0], root_box[1], root_box[2], root_box[3]);
+            c.b = make_float4(root_box[4], root_box[5], __int_as_float(~0), __int_as_float(0));
+        }
         if (overlap(ulo, uhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y)) s_entry[atomicAdd(&s_nentry, 1u)] = c;
     }
     __syncthreads();
@@ -252,7 +269,7 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
     // start points: every kept entry that ends after q and overlaps q's box (warp-uniform loop)
     for (uint32_t e = 0; e < nkeep; ++e) {
         const Child c = s_entry[e];
-        const bool hit = q != 0xffffffffu && c.ext() > (int)q &&
+        const bool hit = q != 0xffffffffu && c.ext() > qcmp &&
                          overlap(qlo, qhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y);
         const int link = c.link();
         if (hit && link >= 0) {
@@ -273,8 +290,8 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
             load_children(pairs, node, l, r);
             const int linkL = l.link(), linkR = r.link();
             // left child = leaves [.., node], right child = leaves [node+1, r.ext]: skip what ends at or before q
-            const bool hitL = node > (int)q && overlap(qlo, qhi, l.a.x, l.a.y, l.a.z, l.a.w, l.b.x, l.b.y);
-            const bool hitR = r.ext() > (int)q && overlap(qlo, qhi, r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y);
+            const bool hitL = node > qcmp && overlap(qlo, qhi, l.a.x, l.a.y, l.a.z, l.a.w, l.b.x, l.b.y);
+            const bool hitR = r.ext() > qcmp && overlap(qlo, qhi, r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y);
             candL = hitL && linkL < 0; leafL = ~linkL;
             candR = hitR && linkR < 0; leafR = ~linkR;
             const bool goL = hitL && linkL >= 0, goR = hitR && linkR >= 0;
@@ -480,14 +497,18 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
 }  // namespace
 
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
-                  uint32_t nshards, uint32_t chunk, uint32_t nquery, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
-                  uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s) {
-    if (n < 2 || nquery == 0) return;
+                  uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, Node32* d_entries,
+                  uint32_t* d_entry_count, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
+                  cudaStream_t s) {
+    if (nquery == 0 || n == 0 || (!foreign && n < 2)) return;
     const uint32_t blocks = (nquery + BR_THREADS - 1) / BR_THREADS;
-    entry_kernel<<<(blocks + 127) / 128, 128, 0, s>>>(d_pairs, d_root_box, n, shard, nshards, chunk, blocks, d_entries, d_entry_count);
-    count_launch();
-    broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, d_entries,
-                                               d_entry_count, d_cand, cand_cap, d_counters);
+    if (!foreign) {
+        entry_kernel<<<(blocks + 127) / 128, 128, 0, s>>>(d_pairs, d_root_box, n, shard, nshards, chunk, blocks, d_entries,
+                                                          d_entry_count);
+        count_launch();
+    }
+    broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery, foreign,
+                                               d_entries, d_entry_count, d_cand, cand_cap, d_counters);
     count_launch();
 }
 

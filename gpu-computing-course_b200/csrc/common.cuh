@@ -10,6 +10,7 @@
 #define B200CD_MAX_STACK 96  // traversal stack entries per query (tree depth <= 60 key bits + tie-break)
 #define B200CD_QUERY_BLOCK 256  // consecutive sorted leaves per traversal block (query chunks are multiples of this)
 #define B200CD_MAX_ENTRIES 64   // start subtrees recorded per traversal block
+#define B200CD_MAX_TRIS_LOG2 30 // at most 2^30 triangles / vertices per mesh
 
 namespace b200cd {
 
@@ -71,7 +72,11 @@ struct b200cd_mesh {
 
 struct b200cd_bvh {
     b200cd_ctx* ctx = nullptr;
-    uint32_t n = 0;         // triangles
+    uint32_t n = 0;         // triangles (leaves) currently in the tree
+    uint32_t cap = 0;       // leaves the buffers were sized for (== n except for partitioned builds)
+    uint64_t ghost_cap = 0; // ghost leaf records that fit after the local leaves in d_leaves
+    b200cd::LeafRec* d_ghost_out = nullptr;   // [peers][ghost_out_cap] outgoing ghost lists
+    uint64_t ghost_out_cap = 0;
     uint32_t nverts = 0;
     bool built = false;
     b200cd_params params{};
@@ -95,6 +100,8 @@ struct b200cd_bvh {
     uint2* d_cand = nullptr;  uint64_t cand_cap = 0;
     uint2* d_out = nullptr;   uint64_t out_cap = 0;
     uint2* d_out_tmp = nullptr; uint64_t out_tmp_cap = 0;
+    uint64_t npairs = 0;     // pairs currently in d_out (last local query + appended ghost queries)
+    uint32_t id_space = 0;   // triangle ids are < id_space (mesh size for a partitioned build, else n)
     unsigned long long* d_counters = nullptr;  // [0] candidates, [1] pairs, [2] error flags
     unsigned long long* h_counters = nullptr;  // pinned
 };
@@ -149,7 +156,7 @@ inline int set_error(b200cd_ctx* ctx, int code, const std::string& msg) {
 void launch_expand_verts(const float* d_xyz, float4* d_verts, uint32_t nverts, cudaStream_t s);
 void launch_check_idx(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, uint32_t* d_flag, int sms, cudaStream_t s);
 void launch_bbox(const float4* d_verts, uint32_t nverts, uint32_t* d_bbox6 /*ordered-uint min3,max3*/, int sms, cudaStream_t s);
-void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t n, const b200cd_params& p,
+void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t first, uint32_t n, const b200cd_params& p,
                    const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s);
 // radix_sort.cu
 struct RadixPass { int shift; int bits; };
@@ -158,6 +165,11 @@ struct RadixPass { int shift; int bits; };
 int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
                bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words,
                int sms, cudaStream_t s);
+// stable range partition (multi-GPU): bucket = number of device-resident splitters <= key; needs
+// d_hist >= 2*256+1 words and d_tile_status >= radix_tile_status_words(n, 1); counts land in d_hist[256..]
+void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t iota_base, uint64_t* keys_out,
+                     uint32_t* vals_out, uint32_t n, const uint64_t* d_splitters, int nsplit, uint32_t* d_hist,
+                     uint32_t* d_tile_status, int sms, cudaStream_t s);
 uint64_t radix_tile_status_words(uint32_t n, int npass);
 uint32_t radix_hist_words(int npass);
 // lbvh.cu
@@ -171,9 +183,18 @@ void launch_export_nodes(const NodePair* d_pairs, const float* d_root_box, uint3
                          b200cd_node32* d_nodes_out, cudaStream_t s);
 void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, const uint64_t* d_keys,
                      uint32_t n, uint32_t nverts, uint32_t* d_scratch, uint32_t* d_checks9, cudaStream_t s);
+// partition.cu (partitioned multi-GPU build)
+void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist65536, int sms, cudaStream_t s);
+void launch_chunk_boxes(const LeafRec* d_leaves, uint32_t n, uint32_t K, float* d_boxes, cudaStream_t s);
+int ghost_max_k();
+void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
+                   uint32_t peer_mask, LeafRec* d_ghosts, uint64_t cap_per_peer, unsigned long long* d_counts,
+                   cudaStream_t s);
 // collide.cu
+// foreign != 0: the queries are the nquery ghost records stored after the n local leaves; they start at the
+// root and are tested against every local leaf (no "only later positions" rule)
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
-                  uint32_t nshards, uint32_t chunk, uint32_t nquery, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
+                  uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
                   uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s);
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s);

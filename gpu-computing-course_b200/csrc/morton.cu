@@ -124,10 +124,12 @@ struct MortonBox {
 
 template <int KEY_BITS>
 __global__ void __launch_bounds__(256)
-morton_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx, uint32_t n, MortonBox box,
+morton_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx, uint32_t first, uint32_t n, MortonBox box,
               const uint32_t* __restrict__ bbox6, uint64_t* __restrict__ keys) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+    // triangles first .. first+n-1 (a slice when the build is partitioned over GPUs); keys[] is slice-relative
+    const uint32_t tl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tl >= n) return;
+    const uint32_t t = first + tl;
     if (bbox6) {  // auto box: origin = bbox.lo, extent = hi - lo (1 if degenerate)
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -157,10 +159,10 @@ morton_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx
         uint64_t zz = spread21(trunc_u64(nz * 1048576.0));
         key = (xx << 2) | (yy << 1) | zz;
     }
-    keys[t] = key;
+    keys[tl] = key;
 }
 
-void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t n, const b200cd_params& p,
+void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t first, uint32_t n, const b200cd_params& p,
                    const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s) {
     if (!n) return;
     MortonBox box;
@@ -170,9 +172,9 @@ void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t n, con
     }
     uint32_t blocks = (n + 255) / 256;
     if (p.key_bits == 30)
-        morton_kernel<30><<<blocks, 256, 0, s>>>(d_verts, d_idx, n, box, d_bbox6_or_null, d_keys);
+        morton_kernel<30><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys);
     else
-        morton_kernel<63><<<blocks, 256, 0, s>>>(d_verts, d_idx, n, box, d_bbox6_or_null, d_keys);
+        morton_kernel<63><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys);
     count_launch();
 }
 

@@ -1,0 +1,172 @@
+// partition.cu — kernels of the PARTITIONED multi-GPU build (one Morton range of triangles per GPU).
+//
+// The reference is single-GPU and has nothing like this. With the BVH
+// replicated, every GPU repeats the whole build and 8 GPUs cannot beat ~2x; here each rank builds
+// and queries only its own Morton range and exchanges the thin layer of triangles that can touch
+// another rank's range ("ghosts"):
+//   key_hist16_kernel   65536-bin histogram of the keys' top bits -> all-reduce -> range splitters
+//   (radix_partition, radix_sort.cu: stable bucketing of (key, id) by splitter)
+//   chunk_box_kernel    K coarse boxes per rank: AABBs of K equal runs of its sorted leaves
+//   ghost_kernel        leaves whose box overlaps any coarse box of a peer -> that peer's ghost list
+// The pair SET is unchanged: {a,b} with both triangles on one rank is found by that rank's own
+// query; a cross pair is found exactly once, by the higher rank, when the lower rank's triangle
+// arrives there as a ghost query (its box overlaps the partner's box, hence the partner's coarse box).
+#include "common.cuh"
+
+namespace b200cd {
+
+namespace {
+
+__global__ void __launch_bounds__(256) key_hist16_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+                                                        uint32_t* __restrict__ hist) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)(__ldg(keys + i) >> shift) & 0xffffu;
+        // clustered meshes put whole warps into one bin: aggregate before touching L2
+        const uint32_t peers = __match_any_sync(__activemask(), b);
+        if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(hist + b, (uint32_t)__popc(peers));
+    }
+}
+
+__device__ __forceinline__ void leaf_box(const LeafRec* __restrict__ leaves, uint32_t j, float lo[3], float hi[3]) {
+    float4 r0, r1, r2, r3;
+    ld256_nc(leaves + j, r0, r1);
+    ld256_nc(reinterpret_cast<const float4*>(leaves + j) + 2, r2, r3);
+    // v0 = r0.xyz, v1 = (r0.w, r1.x, r1.y), v2 = (r1.z, r1.w, r2.x)
+    lo[0] = fminf(fminf(r0.x, r0.w), r1.z); hi[0] = fmaxf(fmaxf(r0.x, r0.w), r1.z);
+    lo[1] = fminf(fminf(r0.y, r1.x), r1.w); hi[1] = fmaxf(fmaxf(r0.y, r1.x), r1.w);
+    lo[2] = fminf(fminf(r0.z, r1.y), r2.x); hi[2] = fmaxf(fmaxf(r0.z, r1.y), r2.x);
+}
+
+// one block per run of `run` consecutive sorted leaves; boxes[k] = {lo xyz, hi xyz}; an empty run gives lo > hi
+__global__ void __launch_bounds__(256) chunk_box_kernel(const LeafRec* __restrict__ leaves, uint32_t n, uint32_t run,
+                                                       float* __restrict__ boxes) {
+    __shared__ float s_red[8][6];
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    const uint64_t first = (uint64_t)blockIdx.x * run;
+    const uint64_t last = min(first + run, (uint64_t)n);
+    for (uint64_t j = first + threadIdx.x; j < last; j += blockDim.x) {
+        float l[3], h[3];
+        leaf_box(leaves, (uint32_t)j, l, h);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], l[a]); hi[a] = fmaxf(hi[a], h[a]); }
+    }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { s_red[warp][a] = lo[a]; s_red[warp][3 + a] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = s_red[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, s_red[w][threadIdx.x]) : fmaxf(v, s_red[w][threadIdx.x]);
+        boxes[6 * (size_t)blockIdx.x + threadIdx.x] = v;
+    }
+}
+
+constexpr int GH_MAXK = 256;
+
+constexpr int GH_GROUP = 16;  // coarse boxes per super box
+
+// Each thread owns one local leaf; for every selected peer it tests the leaf's box (strict overlap,
+// like the traversal) against that peer's coarse boxes - first the peer's overall box, then super
+// boxes of 16 consecutive coarse boxes, then the coarse boxes of the super boxes it overlaps - and,
+// on the first hit, appends the leaf's 64-byte record to the peer's ghost list (warp-aggregated atomic).
+__global__ void __launch_bounds__(256)
+ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __restrict__ peer_boxes, uint32_t npeers,
+             uint32_t K, uint32_t peer_mask, LeafRec* __restrict__ ghosts, uint64_t cap_per_peer,
+             unsigned long long* __restrict__ counts) {
+    __shared__ float s_box[GH_MAXK][6];
+    __shared__ float s_sup[GH_MAXK / GH_GROUP + 1][6];  // super boxes; the last used slot + 1 .. : [nsup] = overall box
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    float4 r0, r1, r2, r3;
+    const bool valid = j < n;
+    if (valid) {
+        ld256_nc(leaves + j, r0, r1);
+        ld256_nc(reinterpret_cast<const float4*>(leaves + j) + 2, r2, r3);
+        lo[0] = fminf(fminf(r0.x, r0.w), r1.z); hi[0] = fmaxf(fmaxf(r0.x, r0.w), r1.z);
+        lo[1] = fminf(fminf(r0.y, r1.x), r1.w); hi[1] = fmaxf(fmaxf(r0.y, r1.x), r1.w);
+        lo[2] = fminf(fminf(r0.z, r1.y), r2.x); hi[2] = fmaxf(fmaxf(r0.z, r1.y), r2.x);
+    }
+    const uint32_t nsup = (K + GH_GROUP - 1) / GH_GROUP;
+    auto hits = [&](const float* b) {
+        return lo[0] < b[3] && b[0] < hi[0] && lo[1] < b[4] && b[1] < hi[1] && lo[2] < b[5] && b[2] < hi[2];
+    };
+    for (uint32_t p = 0; p < npeers; ++p) {
+        if (!((peer_mask >> p) & 1u)) continue;  // uniform
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < K * 6; i += blockDim.x) (&s_box[0][0])[i] = __ldg(peer_boxes + (size_t)p * K * 6 + i);
+        __syncthreads();
+        if (threadIdx.x < nsup * 6) {  // super box g, component c (empty runs hold lo = +inf, hi = -inf and drop out)
+            const uint32_t g = threadIdx.x / 6, c = threadIdx.x % 6;
+            float v = c < 3 ? inf : -inf;
+            for (uint32_t k = g * GH_GROUP; k < min(K, (g + 1) * GH_GROUP); ++k)
+                v = c < 3 ? fminf(v, s_box[k][c]) : fmaxf(v, s_box[k][c]);
+            s_sup[g][c] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            const uint32_t c = threadIdx.x;
+            float v = c < 3 ? inf : -inf;
+            for (uint32_t g = 0; g < nsup; ++g) v = c < 3 ? fminf(v, s_sup[g][c]) : fmaxf(v, s_sup[g][c]);
+            s_sup[nsup][c] = v;
+        }
+        __syncthreads();
+        bool hit = false;
+        if (valid && hits(s_sup[nsup])) {
+            for (uint32_t g = 0; g < nsup && !hit; ++g) {
+                if (!hits(s_sup[g])) continue;
+                for (uint32_t k = g * GH_GROUP; k < min(K, (g + 1) * GH_GROUP) && !hit; ++k) hit = hits(s_box[k]);
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(counts + p, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+            if (hit && base < cap_per_peer) {
+                LeafRec* dst = ghosts + (size_t)p * cap_per_peer + base;
+                st256(dst, r0, r1);
+                st256(reinterpret_cast<float4*>(dst) + 2, r2, r3);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist, int sms, cudaStream_t s) {
+    if (!n) return;
+    const uint32_t blocks = min((n + 255u) / 256u, (uint32_t)sms * 16u);
+    key_hist16_kernel<<<blocks, 256, 0, s>>>(d_keys, n, shift, d_hist);
+    count_launch();
+}
+
+void launch_chunk_boxes(const LeafRec* d_leaves, uint32_t n, uint32_t K, float* d_boxes, cudaStream_t s) {
+    if (!K) return;
+    const uint32_t run = (uint32_t)(((uint64_t)n + K - 1) / K);
+    chunk_box_kernel<<<K, 256, 0, s>>>(d_leaves, n, run ? run : 1u, d_boxes);
+    count_launch();
+}
+
+int ghost_max_k() { return GH_MAXK; }
+
+void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
+                   uint32_t peer_mask, LeafRec* d_ghosts, uint64_t cap_per_peer, unsigned long long* d_counts,
+                   cudaStream_t s) {
+    cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * npeers, s);
+    if (!n || !npeers || !peer_mask) return;
+    ghost_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, d_ghosts, cap_per_peer,
+                                                d_counts);
+    count_launch();
+}
+
+}  // namespace b200cd

@@ -42,8 +42,65 @@ struct PassList {
     uint32_t mask[RS_MAX_PASS];
 };
 
+// Digit of a key: a bit field (radix passes) or, for the multi-GPU range partition, the number of
+// splitters <= key (splitters ascending, at most RS_MAX_SPLIT of them, read from device memory
+// because they are computed on the device).
+constexpr int RS_MAX_SPLIT = 15;
+template <bool SPLIT>
+struct Digit;
+template <>
+struct Digit<false> {  // bit field
+    int shift;
+    uint32_t mask;
+    __device__ __forceinline__ uint32_t operator()(uint64_t k) const { return (uint32_t)((k >> shift) & mask); }
+};
+template <>
+struct Digit<true> {   // range partition
+    int nsplit;
+    uint64_t split[RS_MAX_SPLIT];
+    __device__ __forceinline__ uint32_t operator()(uint64_t k) const {
+        uint32_t d = 0;
+#pragma unroll
+        for (int j = 0; j < RS_MAX_SPLIT; ++j) d += (j < nsplit && split[j] <= k) ? 1u : 0u;
+        return d;
+    }
+};
+template <bool SPLIT>
+__device__ __forceinline__ Digit<SPLIT> make_digit(int shift, uint32_t mask, const uint64_t* __restrict__ splitters, int nsplit);
+template <>
+__device__ __forceinline__ Digit<false> make_digit<false>(int shift, uint32_t mask, const uint64_t* __restrict__, int) {
+    Digit<false> dg;
+    dg.shift = shift; dg.mask = mask;
+    return dg;
+}
+template <>
+__device__ __forceinline__ Digit<true> make_digit<true>(int, uint32_t, const uint64_t* __restrict__ splitters, int nsplit) {
+    Digit<true> dg;
+    dg.nsplit = nsplit;
+#pragma unroll
+    for (int j = 0; j < RS_MAX_SPLIT; ++j) dg.split[j] = (j < nsplit) ? __ldg(splitters + j) : ~0ull;
+    return dg;
+}
+
 // ---- 1. histograms of every pass in one sweep
 constexpr int RH_THREADS = 256;
+// histogram of ONE custom digit (range partition by splitters)
+__global__ void __launch_bounds__(RH_THREADS) rs_histogram_split(const uint64_t* __restrict__ keys, uint32_t n,
+                                                                 const uint64_t* __restrict__ splitters, int nsplit,
+                                                                 uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[RS_MAX_SPLIT + 1];
+    if (threadIdx.x <= RS_MAX_SPLIT) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const Digit<true> dg = make_digit<true>(0, 0, splitters, nsplit);
+    for (uint32_t i = blockIdx.x * RH_THREADS + threadIdx.x; i < n; i += gridDim.x * RH_THREADS) {
+        const uint32_t d = dg(__ldg(keys + i));
+        const uint32_t peers = __match_any_sync(__activemask(), d);
+        if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x <= RS_MAX_SPLIT && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
 __global__ void __launch_bounds__(RH_THREADS) rs_histogram(const uint64_t* __restrict__ keys, uint32_t n,
                                                            PassList pl, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[RS_MAX_PASS * RS_RADIX];
@@ -103,10 +160,11 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
 
 // 512 threads x 8 items, two CTAs per SM (<= 64 registers): 32 resident warps hide the
 // load -> rank -> look-back -> scatter latency chain of each tile behind the other tile's.
-template <bool HAS_VALUES>
+template <bool HAS_VALUES, bool SPLIT>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
-        uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values,
+        uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values, uint32_t iota_base,
+        const uint64_t* __restrict__ splitters, int nsplit,
         const uint32_t* __restrict__ digit_base_g,  // [256] exclusive global digit offsets of this pass
         uint32_t* __restrict__ status,              // [ntiles][256] look-back words of this pass
         uint32_t* __restrict__ ticket) {
@@ -121,6 +179,7 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
     uint32_t& s_tile = warp_tot[RS_RADIX / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Digit<SPLIT> digit_of = make_digit<SPLIT>(shift, mask, splitters, nsplit);
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < RS_WARPS * (RS_RADIX + 1); i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
     __syncthreads();
@@ -141,7 +200,7 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
 #pragma unroll
         for (int k = 0; k < RS_IPT; ++k) {
             const uint32_t g = my_base + 32 * k;
-            val[k] = iota_values ? g : ((g < n) ? __ldg(vals_in + g) : 0u);
+            val[k] = iota_values ? iota_base + g : ((g < n) ? __ldg(vals_in + g) : 0u);
         }
     }
 
@@ -152,7 +211,7 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
         const uint32_t g = my_base + 32 * k;
-        const uint32_t d = (g < n) ? (uint32_t)((key[k] >> shift) & mask) : (uint32_t)RS_RADIX;
+        const uint32_t d = (g < n) ? digit_of(key[k]) : (uint32_t)RS_RADIX;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
         uint32_t prev = 0;
@@ -227,7 +286,7 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
     for (int k = 0; k < RS_IPT; ++k) {
         const uint32_t g = my_base + 32 * k;
         if (g < n) {
-            const uint32_t d = (uint32_t)((key[k] >> shift) & mask);
+            const uint32_t d = digit_of(key[k]);
             const uint32_t slot = wh[d] + rank[k];
             stage_k[slot] = key[k];
             if (HAS_VALUES) stage_v[slot] = val[k];
@@ -240,7 +299,7 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         const uint32_t r = i * RS_THREADS + tid;
         if (r < tile_items) {
             const uint64_t kk = stage_k[r];
-            const uint32_t pos = digit_base[(uint32_t)((kk >> shift) & mask)] + r;
+            const uint32_t pos = digit_base[digit_of(kk)] + r;
             keys_out[pos] = kk;
             if (HAS_VALUES) vals_out[pos] = stage_v[r];
         }
@@ -276,8 +335,8 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaFuncSetAttribute(rs_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
-        cudaFuncSetAttribute(rs_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false));
+        cudaFuncSetAttribute(rs_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+        cudaFuncSetAttribute(rs_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     uint32_t* d_ticket = d_hist + npass * RS_RADIX;
@@ -292,16 +351,46 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     for (int p = 0; p < npass; ++p) {
         uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
         if (vals)
-            rs_pass<true><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n,
-                                                       pl.shift[p], pl.mask[p], (iota_values && p == 0) ? 1 : 0,
+            rs_pass<true, false><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n,
+                                                       pl.shift[p], pl.mask[p], (iota_values && p == 0) ? 1 : 0, 0u, nullptr, 0,
                                                        d_hist + p * RS_RADIX, status, d_ticket + p);
         else
-            rs_pass<false><<<tiles, RS_THREADS, rs_smem_bytes(false), s>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, pl.shift[p],
-                                                        pl.mask[p], 0, d_hist + p * RS_RADIX, status, d_ticket + p);
+            rs_pass<false, false><<<tiles, RS_THREADS, rs_smem_bytes(false), s>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, pl.shift[p],
+                                                        pl.mask[p], 0, 0u, nullptr, 0, d_hist + p * RS_RADIX, status, d_ticket + p);
         count_launch();
         cur ^= 1;
     }
     return cur;
+}
+
+// Stable partition of (key, value) by key range: item goes to bucket d = #splitters <= key.
+// d_splitters: nsplit ascending keys in device memory. The per-bucket counts are left in
+// d_hist[256 .. 256+nsplit] (d_hist[0..] holds the exclusive bucket offsets). values_in may be null:
+// value = iota_base + index.
+void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t iota_base, uint64_t* keys_out,
+                     uint32_t* vals_out, uint32_t n, const uint64_t* d_splitters, int nsplit, uint32_t* d_hist,
+                     uint32_t* d_tile_status, int sms, cudaStream_t s) {
+    if (n == 0) {
+        cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * 2 * RS_RADIX, s);
+        return;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaFuncSetAttribute(rs_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t* d_ticket = d_hist + 2 * RS_RADIX;
+    cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * (2 * RS_RADIX + 1), s);
+    cudaMemsetAsync(d_tile_status, 0, sizeof(uint32_t) * (size_t)tiles * RS_RADIX, s);
+    const uint32_t hblocks = min((n + RH_THREADS - 1) / RH_THREADS, (uint32_t)sms * 8u);
+    rs_histogram_split<<<hblocks, RH_THREADS, 0, s>>>(keys_in, n, d_splitters, nsplit, d_hist);
+    count_launch();
+    cudaMemcpyAsync(d_hist + RS_RADIX, d_hist, sizeof(uint32_t) * RS_RADIX, cudaMemcpyDeviceToDevice, s);  // keep the counts
+    rs_scan<<<1, RS_RADIX, 0, s>>>(d_hist);
+    count_launch();
+    rs_pass<true, true><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys_in, keys_out, vals_in, vals_out, n, 0, 0u,
+                                                                vals_in ? 0 : 1, iota_base, d_splitters, nsplit, d_hist,
+                                                                d_tile_status, d_ticket);
+    count_launch();
 }
 
 }  // namespace b200cd

@@ -120,8 +120,11 @@ typedef struct b200cd_checks {
 /* Replaces the implicit "device 0, default stream" of main.cu. */
 int b200cd_create(int device, b200cd_ctx** out);
 int b200cd_destroy(b200cd_ctx* ctx);
-/* Run all of the context's work on a caller-owned cudaStream_t (e.g. the stream
- * a benchmark records its CUDA events on). NULL restores the private stream. */
+/* Run all of the context's work on a caller-owned cudaStream_t (e.g. the stream a benchmark
+ * records its CUDA events on, or the one NCCL transfers are ordered against). NULL is the legacy
+ * default stream (where the reference runs everything, main.cu:92-142);
+ * B200CD_PRIVATE_STREAM restores the context's own non-blocking stream. */
+#define B200CD_PRIVATE_STREAM ((void*)(intptr_t)-1)
 int b200cd_set_stream(b200cd_ctx* ctx, void* cuda_stream);
 int b200cd_synchronize(b200cd_ctx* ctx);
 int b200cd_get_stats(const b200cd_ctx* ctx, b200cd_stats* out);
@@ -230,6 +233,55 @@ typedef struct b200cd_bvh_view {
 } b200cd_bvh_view;
 int b200cd_bvh_view_get(b200cd_ctx* ctx, b200cd_bvh* bvh, b200cd_bvh_view* out);
 int b200cd_bvh_alloc_like(b200cd_ctx* ctx, uint32_t ntris, b200cd_bvh** out);
+
+/* ---- partitioned multi-GPU build ------------------------------------------
+ * The reference is single-GPU (no collective anywhere). With a replicated BVH
+ * every rank repeats the whole build; these entry points let each rank (one process per GPU,
+ * NCCL through the caller's torch.distributed) own ONE Morton range of the triangles: it builds
+ * and queries only that range and exchanges the thin layer of triangles whose boxes reach into
+ * another rank's range ("ghosts"). gpu-computing-course_b200/multigpu.py drives the sequence;
+ * the pair set is identical to b200cd_self_collide on one GPU.
+ *   1. b200cd_morton_keys_device      keys of this rank's slice of the INPUT triangles
+ *   2. b200cd_key_histogram_device    65536-bin histogram of the keys' top bits (all-reduced by the caller -> splitters)
+ *   3. b200cd_partition_keys_device   (key, id) bucketed by destination rank; caller all-to-alls them
+ *                                     into b200cd_bvh_key_buffers of the receiving rank
+ *   4. b200cd_bvh_build_partial       sort + tree over the received triangles
+ *   5. b200cd_self_collide_device     pairs inside the rank
+ *   6. b200cd_bvh_chunk_boxes_device  K coarse boxes of the rank (all-gathered by the caller)
+ *   7. b200cd_select_ghosts_device    local leaves overlapping a peer's coarse boxes -> per-peer lists;
+ *                                     caller sends them into the peer's b200cd_bvh_ghost_buffer
+ *   8. b200cd_collide_ghosts_device   received ghosts against the local tree, pairs appended
+ * All pointers named d_* are device memory on the context's GPU; work is enqueued on the context's stream. */
+int b200cd_morton_keys_device(b200cd_ctx* ctx, const b200cd_mesh* mesh, const b200cd_params* params, uint32_t first,
+                              uint32_t count, void* d_keys_out /* count x u64 */);
+int b200cd_key_histogram_device(b200cd_ctx* ctx, const void* d_keys, uint32_t count, int32_t shift,
+                                void* d_hist65536 /* 65536 x u32, accumulated into */);
+/* BVH with room for `capacity` local triangles, `ghost_capacity` received ghost records and
+ * `max_peers` outgoing ghost lists of `ghost_capacity` records each. */
+int b200cd_bvh_alloc_partial(b200cd_ctx* ctx, uint32_t capacity, uint64_t ghost_capacity, uint32_t max_peers,
+                             b200cd_bvh** out);
+int b200cd_bvh_key_buffers(b200cd_ctx* ctx, b200cd_bvh* bvh, void** d_keys, void** d_ids, uint32_t* capacity);
+/* Stable bucketing: bucket = number of splitters <= key (nsplit <= 15 ascending u64 keys in device
+ * memory); ids are first_id + position. counts_out[nsplit + 1] (host) receives the bucket sizes. */
+int b200cd_partition_keys_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_keys, uint32_t first_id, uint32_t count,
+                                 const void* d_splitters, uint32_t nsplit, void* d_keys_out, void* d_ids_out,
+                                 uint64_t* counts_out);
+/* Sort + tree over the `count` (key, triangle id) items already placed in b200cd_bvh_key_buffers. */
+int b200cd_bvh_build_partial(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh, const b200cd_params* params,
+                             uint32_t count);
+/* K <= 256 boxes (lo xyz, hi xyz floats): AABBs of K equal runs of the sorted leaves. */
+int b200cd_bvh_chunk_boxes_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t K, void* d_boxes_out /* K x 6 floats */);
+/* d_peer_boxes: [npeers][K][6] floats. For every peer p with bit p set in peer_mask, the local
+ * leaves whose box strictly overlaps one of p's boxes are copied (64-byte records) to
+ * (*d_ghosts_out) + p * (*stride_out) records; counts_out[npeers] (host). */
+int b200cd_select_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_peer_boxes, uint32_t npeers, uint32_t K,
+                                uint32_t peer_mask, const void** d_ghosts_out, uint64_t* stride_out, uint64_t* counts_out);
+/* Where received ghost records go (64 bytes each), valid until the next build of this BVH. */
+int b200cd_bvh_ghost_buffer(b200cd_ctx* ctx, b200cd_bvh* bvh, void** d_ptr, uint64_t* capacity);
+/* The first nghost records of the ghost buffer are queried against the local tree; keep_pairs != 0
+ * appends to the list of the preceding b200cd_self_collide_device call. */
+int b200cd_collide_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint64_t nghost, int keep_pairs,
+                                 const void** d_pairs_out, uint64_t* count_out);
 
 #ifdef __cplusplus
 }

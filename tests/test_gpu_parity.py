@@ -209,3 +209,25 @@ def test_bad_vertex_index_is_rejected(cd, ctx):
     with pytest.raises(cd.B200cdError) as e:
         ctx.mesh_from_arrays(xyz, np.array([[0, 1, 3]], np.uint32))
     assert e.value.status == cd.E_INVALID
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_partitioned_build_emulated_ranks_equal_single_gpu(cd, co, ctx, mg, world):
+    """multi-GPU partitioned build (one Morton range per rank + ghost exchange) with the ranks emulated
+    on one GPU: the merged pair list must equal the single-GPU list bit for bit"""
+    import importlib
+    mgpu = importlib.import_module("gpu-computing-course_b200.multigpu")
+    for name, (xyz, idx), box in (("soup", mg.soup(60000, seed=17), UNIT), ("cloth", mg.cloth_fold(120, 120), None),
+                                  ("sheets", mg.two_sheets(100), UNIT)):
+        p = cd.make_params(**box) if box else cd.default_params()
+        mesh = ctx.mesh_from_arrays(xyz, idx)
+        bvh = ctx.bvh_build(mesh, p)
+        full = ctx.self_collide(bvh, sorted=True)
+        bvh.destroy()
+        got, stats = mgpu.partitioned_self_collision_emulated(cd, ctx, mesh, p, world)
+        assert sum(s["local_triangles"] for s in stats) == len(idx)
+        assert np.array_equal(got, full), (name, world, stats)
+        if world > 1:
+            assert sum(s["ghosts"] for s in stats) > 0
+        mesh.destroy()
+    ctx.set_stream(None)
