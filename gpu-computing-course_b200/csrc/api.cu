@@ -69,6 +69,7 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_pairs);
     cudaFree(b->d_leaves);
     cudaFree(b->d_ghost_out);
+    cudaFree(b->d_cut_scratch);
     cudaFree(b->d_root_box);
     cudaFree(b->d_cand);
     cudaFree(b->d_entries);
@@ -116,6 +117,7 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
     if (max_peers) {
         b->ghost_out_cap = ghost_cap;
         A(dev_alloc(ctx, &b->d_ghost_out, (uint64_t)max_peers * ghost_cap));
+        A(dev_alloc(ctx, &b->d_cut_scratch, (uint64_t)ghost_max_k() * 6 + 1));
     }
     A(dev_alloc(ctx, &b->d_root_box, 8));
     A(dev_alloc(ctx, &b->d_counters, 8));
@@ -692,7 +694,8 @@ API int b200cd_bvh_chunk_boxes_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t
     if (!ctx || !bvh || !d_boxes_out || K == 0 || K > (uint32_t)ghost_max_k()) return set_error(ctx, B200CD_E_INVALID, "bad argument");
     if (!bvh->built) return set_error(ctx, B200CD_E_INVALID, "BVH not built");
     DeviceGuard g(ctx->device);
-    launch_chunk_boxes(bvh->d_leaves, bvh->n, K, static_cast<float*>(d_boxes_out), ctx->stream);
+    if (!bvh->d_cut_scratch) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
+    launch_chunk_boxes(bvh->d_pairs, bvh->d_root_box, bvh->n, K, bvh->d_cut_scratch, static_cast<float*>(d_boxes_out), ctx->stream);
     CD_CUDA(ctx, cudaGetLastError());
     return B200CD_OK;
 }

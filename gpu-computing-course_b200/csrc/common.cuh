@@ -76,6 +76,7 @@ struct b200cd_bvh {
     uint32_t cap = 0;       // leaves the buffers were sized for (== n except for partitioned builds)
     uint64_t ghost_cap = 0; // ghost leaf records that fit after the local leaves in d_leaves
     b200cd::LeafRec* d_ghost_out = nullptr;   // [peers][ghost_out_cap] outgoing ghost lists
+    uint32_t* d_cut_scratch = nullptr;        // coarse-box reduction scratch (256*6+1 words)
     uint64_t ghost_out_cap = 0;
     uint32_t nverts = 0;
     bool built = false;
@@ -185,7 +186,9 @@ void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const flo
                      uint32_t n, uint32_t nverts, uint32_t* d_scratch, uint32_t* d_checks9, cudaStream_t s);
 // partition.cu (partitioned multi-GPU build)
 void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist65536, int sms, cudaStream_t s);
-void launch_chunk_boxes(const LeafRec* d_leaves, uint32_t n, uint32_t K, float* d_boxes, cudaStream_t s);
+// d_scratch: K*6 + 1 words
+void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t K, uint32_t* d_scratch,
+                        float* d_boxes, cudaStream_t s);
 int ghost_max_k();
 void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                    uint32_t peer_mask, LeafRec* d_ghosts, uint64_t cap_per_peer, unsigned long long* d_counts,

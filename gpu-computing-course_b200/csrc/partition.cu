@@ -20,53 +20,65 @@ namespace {
 __global__ void __launch_bounds__(256) key_hist16_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
                                                         uint32_t* __restrict__ hist) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t b = (uint32_t)(__ldg(keys + i) >> shift) & 0xffffu;
+        const uint32_t b = (uint32_t)min(__ldg(keys + i) >> shift, (uint64_t)0xffffull);  // keys beyond 2^(shift+16) share the last bin
         // clustered meshes put whole warps into one bin: aggregate before touching L2
         const uint32_t peers = __match_any_sync(__activemask(), b);
         if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(hist + b, (uint32_t)__popc(peers));
     }
 }
 
-__device__ __forceinline__ void leaf_box(const LeafRec* __restrict__ leaves, uint32_t j, float lo[3], float hi[3]) {
-    float4 r0, r1, r2, r3;
-    ld256_nc(leaves + j, r0, r1);
-    ld256_nc(reinterpret_cast<const float4*>(leaves + j) + 2, r2, r3);
-    // v0 = r0.xyz, v1 = (r0.w, r1.x, r1.y), v2 = (r1.z, r1.w, r2.x)
-    lo[0] = fminf(fminf(r0.x, r0.w), r1.z); hi[0] = fmaxf(fmaxf(r0.x, r0.w), r1.z);
-    lo[1] = fminf(fminf(r0.y, r1.x), r1.w); hi[1] = fmaxf(fmaxf(r0.y, r1.x), r1.w);
-    lo[2] = fminf(fminf(r0.z, r1.y), r2.x); hi[2] = fmaxf(fmaxf(r0.z, r1.y), r2.x);
+// Coarse boxes of a rank = a CUT through its tree: the subtrees with at most T leaves whose parent
+// has more than T. They are disjoint, cover every leaf and - being subtrees of a Morton radix tree -
+// are octree cells, so their boxes are tight (a fixed run of consecutive leaves can straddle a jump of
+// the Morton curve and balloon). One thread per internal node: a node with more than T leaves emits
+// the children that have at most T; the child's box sits right there in pairs[s]. If a degenerate
+// tree yields more than K cut nodes the surplus is merged into the last box (looser, still covering).
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
-// one block per run of `run` consecutive sorted leaves; boxes[k] = {lo xyz, hi xyz}; an empty run gives lo > hi
-__global__ void __launch_bounds__(256) chunk_box_kernel(const LeafRec* __restrict__ leaves, uint32_t n, uint32_t run,
-                                                       float* __restrict__ boxes) {
-    __shared__ float s_red[8][6];
-    const float inf = __int_as_float(0x7f800000);
-    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
-    const uint64_t first = (uint64_t)blockIdx.x * run;
-    const uint64_t last = min(first + run, (uint64_t)n);
-    for (uint64_t j = first + threadIdx.x; j < last; j += blockDim.x) {
-        float l[3], h[3];
-        leaf_box(leaves, (uint32_t)j, l, h);
+__global__ void cut_box_init_kernel(uint32_t* __restrict__ boxes_ord, uint32_t K) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K * 6) boxes_ord[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+    else if (i == K * 6) boxes_ord[i] = 0u;  // cut-node counter
+}
+
+// boxes_ord: K x 6 order-preserving uint images of floats (lo xyz init 0xffffffff, hi xyz init 0)
+__global__ void __launch_bounds__(256)
+cut_box_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_box, uint32_t n, uint32_t T, uint32_t K,
+               uint32_t* __restrict__ boxes_ord, uint32_t* __restrict__ counter) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n - 1) return;
+    const Node32 l = pairs[s].c[0], r = pairs[s].c[1];
+    const uint32_t F = (uint32_t)l.ext, L = (uint32_t)r.ext;
+    if (L - F + 1 <= T) return;  // not above the cut
+    const uint32_t size[2] = {s - F + 1, L - s};
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], l[a]); hi[a] = fmaxf(hi[a], h[a]); }
-    }
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int side = 0; side < 2; ++side) {
+        if (size[side] > T) continue;
+        const Node32& c = side ? r : l;
+        const uint32_t slot = min(atomicAdd(counter, 1u), K - 1);
+        uint32_t* b = boxes_ord + 6 * (size_t)slot;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(b + a, f2ord(c.lo[a]));
+            atomicMax(b + 3 + a, f2ord(c.hi[a]));
         }
-        if (lane == 0) { s_red[warp][a] = lo[a]; s_red[warp][3 + a] = hi[a]; }
     }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        float v = s_red[0][threadIdx.x];
-        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, s_red[w][threadIdx.x]) : fmaxf(v, s_red[w][threadIdx.x]);
-        boxes[6 * (size_t)blockIdx.x + threadIdx.x] = v;
-    }
+}
+
+__global__ void cut_box_finish_kernel(const uint32_t* __restrict__ boxes_ord, const float* __restrict__ root_box, uint32_t n,
+                                      uint32_t T, uint32_t K, float* __restrict__ boxes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * 6) return;
+    float v = ord2f(boxes_ord[i]);                 // untouched slots decode to lo = NaN-free +max / hi = -max patterns:
+    if (boxes_ord[i] == ((i % 6) < 3 ? 0xffffffffu : 0u)) v = (i % 6) < 3 ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+    if (n <= T && i < 6) v = root_box[i];          // the whole tree is below the cut: one box, the root's
+    boxes[i] = v;
 }
 
 constexpr int GH_MAXK = 256;
@@ -150,10 +162,19 @@ void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* 
     count_launch();
 }
 
-void launch_chunk_boxes(const LeafRec* d_leaves, uint32_t n, uint32_t K, float* d_boxes, cudaStream_t s) {
+// d_scratch: K*6 + 1 words
+void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t K, uint32_t* d_scratch,
+                        float* d_boxes, cudaStream_t s) {
     if (!K) return;
-    const uint32_t run = (uint32_t)(((uint64_t)n + K - 1) / K);
-    chunk_box_kernel<<<K, 256, 0, s>>>(d_leaves, n, run ? run : 1u, d_boxes);
+    uint32_t* counter = d_scratch + 6 * (size_t)K;
+    const uint32_t T = (uint32_t)(((uint64_t)n + K / 2 - 1) / max(K / 2, 1u));  // at most ~K cut nodes on a balanced tree
+    cut_box_init_kernel<<<(K * 6 + 1 + 255) / 256, 256, 0, s>>>(d_scratch, K);
+    count_launch();
+    if (n > 1) {
+        cut_box_kernel<<<(n - 1 + 255) / 256, 256, 0, s>>>(d_pairs, d_root_box, n, T ? T : 1u, K, d_scratch, counter);
+        count_launch();
+    }
+    cut_box_finish_kernel<<<(K * 6 + 255) / 256, 256, 0, s>>>(d_scratch, d_root_box, n, T ? T : 1u, K, d_boxes);
     count_launch();
 }
 

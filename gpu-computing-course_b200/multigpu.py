@@ -189,9 +189,9 @@ class PartitionedRank:
         self.lo, self.hi = rank * n // world, (rank + 1) * n // world  # my slice of the INPUT triangles
         self.cnt = self.hi - self.lo
         self.cap = min(n, int(n / world * slack) + 65536)
-        self.ghost_cap = max(n // world // 4, 65536)
+        self.ghost_cap = max(n // world // 2, 65536)
         self.bvh = ctx.bvh_alloc_partial(self.cap, self.ghost_cap, world)
-        self.shift = int(params.key_bits) - 16
+        self.shift = 44 if int(params.key_bits) == 63 else 14  # top 16 of the 60 / 30 bits in-box keys use
         self.keys = torch.empty(max(self.cnt, 1), dtype=torch.int64, device=self.dev)
         self.pkeys = torch.empty(max(self.cnt, 1), dtype=torch.int64, device=self.dev)
         self.pids = torch.empty(max(self.cnt, 1), dtype=torch.int32, device=self.dev)
@@ -237,12 +237,15 @@ class PartitionedRank:
         self.nlocal = total
         return views
 
-    # -- phase 3: sort + tree + pairs inside my range, then my coarse boxes
-    def build_and_collide(self):
+    # -- phase 3: sort + tree over my range, then my coarse boxes
+    def build(self):
         self.ctx.bvh_build_partial(self.bvh, self.mesh, self.params, self.nlocal)
-        self.ctx.self_collide_device(self.bvh, sorted=False)
         self.ctx.bvh_chunk_boxes_device(self.bvh, PARTITION_BOXES, self.boxes.data_ptr())
         return self.boxes
+
+    # -- phase 4b (while the ghosts travel): pairs inside my range
+    def collide_local(self):
+        self.ctx.self_collide_device(self.bvh, sorted=False)
 
     # -- phase 4: my leaves that reach into a HIGHER rank's coarse boxes
     def select_ghosts(self, all_boxes):
@@ -265,26 +268,32 @@ class PartitionedRank:
         self.nghost = total
         return views
 
-    # -- phase 5: ghosts against my tree; returns all my pairs (packed int64 words)
+    # -- phase 5: ghosts against my tree, appended to my local pairs; returns all of them (packed int64 words)
     def collide_ghosts(self):
         ptr, count = self.ctx.collide_ghosts_device(self.bvh, self.nghost, keep_pairs=True)
         return device_pairs_as_tensor(ptr, count, self.dev)
 
 
-def _exchange(rank, world, send, recv, group=None):
-    """variable all-to-all: send[p] -> rank p, recv[p] <- rank p (tensors of matching sizes); grouped P2P"""
-    recv[rank].copy_(send[rank])
+def _exchange_start(rank, world, send_lists, recv_lists, group=None):
+    """variable all-to-all, several buffers at once: send_lists[k][p] -> rank p, recv_lists[k][p] <- rank p
+    (tensors of matching sizes). ONE grouped launch of point-to-point operations (ncclSend/ncclRecv under
+    the nccl backend); returns the work handles - the transfer proceeds while the caller enqueues kernels."""
     ops = []
-    for p in range(world):
-        if p == rank:
-            continue
-        if send[p].numel():
-            ops.append(dist.P2POp(dist.isend, send[p], p, group=group))
-        if recv[p].numel():
-            ops.append(dist.P2POp(dist.irecv, recv[p], p, group=group))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+    for send, recv in zip(send_lists, recv_lists):
+        recv[rank].copy_(send[rank])
+        for p in range(world):
+            if p == rank:
+                continue
+            if send[p].numel():
+                ops.append(dist.P2POp(dist.isend, send[p], p, group=group))
+            if recv[p].numel():
+                ops.append(dist.P2POp(dist.irecv, recv[p], p, group=group))
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+def _exchange_wait(works):
+    for w in works:
+        w.wait()
 
 
 def _all_counts(counts, device, group=None):
@@ -330,22 +339,26 @@ class PartitionedSelfCollision:
         allc = _all_counts(counts, self.device, g) if w > 1 else [counts]
         views = p.key_recv_views([allc[src][r] for src in range(w)])
         if w > 1:
-            _exchange(r, w, [k for k, _ in pieces], [k for k, _ in views], g)
-            _exchange(r, w, [i for _, i in pieces], [i for _, i in views], g)
+            _exchange_wait(_exchange_start(r, w, [[k for k, _ in pieces], [i for _, i in pieces]],
+                                           [[k for k, _ in views], [i for _, i in views]], g))
         else:
             views[0][0].copy_(pieces[0][0])
             views[0][1].copy_(pieces[0][1])
         mark("key exchange")
-        boxes = p.build_and_collide()
-        mark("build+local query")
+        boxes = p.build()
+        mark("build")
+        works = []
         if w > 1:
             allb = torch.empty(w * boxes.numel(), dtype=boxes.dtype, device=self.device)
             dist.all_gather_into_tensor(allb, boxes, group=g)
             gcounts, gpieces = p.select_ghosts(allb)
             gall = _all_counts(gcounts, self.device, g)
             gviews = p.ghost_recv_views([gall[src][r] for src in range(w)])
-            _exchange(r, w, gpieces, gviews, g)
-        mark("ghost select+exchange")
+            works = _exchange_start(r, w, [gpieces], [gviews], g)  # travels while the local query runs
+        mark("ghost select")
+        p.collide_local()
+        mark("local query")
+        _exchange_wait(works)
         local = p.collide_ghosts()
         mark("ghost query")
         self.stats = {"local_triangles": p.nlocal, "ghosts": p.nghost, "local_pairs": int(local.numel())}
@@ -379,12 +392,14 @@ def partitioned_self_collision_emulated(cd, ctx, mesh, params, world, slack=1.5)
         for src in range(world):
             views[src][0].copy_(parts[src][1][dst][0])
             views[src][1].copy_(parts[src][1][dst][1])
-    allb = torch.cat([p.build_and_collide().clone() for p in ranks])
+    allb = torch.cat([p.build().clone() for p in ranks])
     ghosts = [p.select_ghosts(allb) for p in ranks]
     for dst, p in enumerate(ranks):
         views = p.ghost_recv_views([ghosts[src][0][dst] for src in range(world)])
         for src in range(world):
             views[src].copy_(ghosts[src][1][dst])
+    for p in ranks:
+        p.collide_local()
     lists = [p.collide_ghosts().clone() for p in ranks]
     merged = torch.cat(lists)
     if merged.numel() > 1:

@@ -247,7 +247,7 @@ int b200cd_bvh_alloc_like(b200cd_ctx* ctx, uint32_t ntris, b200cd_bvh** out);
  *                                     into b200cd_bvh_key_buffers of the receiving rank
  *   4. b200cd_bvh_build_partial       sort + tree over the received triangles
  *   5. b200cd_self_collide_device     pairs inside the rank
- *   6. b200cd_bvh_chunk_boxes_device  K coarse boxes of the rank (all-gathered by the caller)
+ *   6. b200cd_bvh_chunk_boxes_device  K coarse boxes of the rank = a cut through its tree (all-gathered by the caller)
  *   7. b200cd_select_ghosts_device    local leaves overlapping a peer's coarse boxes -> per-peer lists;
  *                                     caller sends them into the peer's b200cd_bvh_ghost_buffer
  *   8. b200cd_collide_ghosts_device   received ghosts against the local tree, pairs appended
@@ -269,7 +269,8 @@ int b200cd_partition_keys_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d
 /* Sort + tree over the `count` (key, triangle id) items already placed in b200cd_bvh_key_buffers. */
 int b200cd_bvh_build_partial(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh, const b200cd_params* params,
                              uint32_t count);
-/* K <= 256 boxes (lo xyz, hi xyz floats): AABBs of K equal runs of the sorted leaves. */
+/* K <= 256 boxes (lo xyz, hi xyz floats) covering every local leaf: the boxes of a cut through the tree
+ * (subtrees of at most ~2n/K leaves; unused slots hold lo = +inf, hi = -inf). */
 int b200cd_bvh_chunk_boxes_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t K, void* d_boxes_out /* K x 6 floats */);
 /* d_peer_boxes: [npeers][K][6] floats. For every peer p with bit p set in peer_mask, the local
  * leaves whose box strictly overlaps one of p's boxes are copied (64-byte records) to
