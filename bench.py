@@ -266,7 +266,7 @@ def run_gpu_arm(args, workload):
     partitioned = world > 1 and args.mode == "partitioned"
     if partitioned:
         # each rank owns one Morton range: distributed sort, local tree + query, ghost exchange (multigpu.py)
-        prunner = mgpu.PartitionedSelfCollision(cd, ctx, mesh, params)
+        prunner = mgpu.PartitionedSelfCollision(cd, ctx, mesh, params, peer_memory=not args.no_peer_memory)
         bvh = prunner.part.bvh
 
         class _Step:
@@ -419,6 +419,10 @@ def run_gpu_arm(args, workload):
                                     "host_cores_available": info["host_cores_available"]}
         print(json.dumps(line), flush=True)
 
+    if partitioned:
+        torch.cuda.synchronize()
+        dist.barrier()
+        prunner.close()
     bvh.destroy()
     mesh.destroy()
     if world > 1:
@@ -435,6 +439,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="partitioned", choices=["partitioned", "replicated"],
                     help="N > 1: one Morton range per rank (default) or replicated BVH with sharded queries")
+    ap.add_argument("--no-peer-memory", action="store_true",
+                    help="partitioned mode: exchange (key, id) and ghosts with NCCL send/recv instead of peer-memory stores")
     ap.add_argument("--chunk", type=int, default=1 << 14, help="sorted leaves per block-cyclic query chunk (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 21, help="triangles in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -32,6 +32,9 @@ SYMBOLS = [
     "b200cd_morton_keys_device", "b200cd_key_histogram_device", "b200cd_bvh_alloc_partial", "b200cd_bvh_key_buffers",
     "b200cd_partition_keys_device", "b200cd_bvh_build_partial", "b200cd_bvh_chunk_boxes_device",
     "b200cd_select_ghosts_device", "b200cd_bvh_ghost_buffer", "b200cd_collide_ghosts_device",
+    "b200cd_ipc_export", "b200cd_ipc_open", "b200cd_ipc_close", "b200cd_bvh_set_peers", "b200cd_partition_counts_device",
+    "b200cd_partition_to_peers_device", "b200cd_send_ghosts_to_peers_device", "b200cd_ghost_counter_reset",
+    "b200cd_ghost_counter_read",
 ]
 
 
@@ -359,6 +362,47 @@ class Context:
         self._chk(lib().b200cd_collide_ghosts_device(self.h, bvh.h, C.c_uint64(nghost), C.c_int(1 if keep_pairs else 0),
                                                      C.byref(ptr), C.byref(cnt)), "collide_ghosts_device")
         return ptr.value, int(cnt.value)
+
+    # ---- peer-memory variant (CUDA IPC between the ranks' processes)
+    def ipc_export(self, bvh):
+        handles = (C.c_uint8 * 256)()
+        offsets = (C.c_uint64 * 4)()
+        self._chk(lib().b200cd_ipc_export(self.h, bvh.h, handles, offsets), "ipc_export")
+        return bytes(handles), [int(o) for o in offsets]
+
+    def ipc_open(self, handle64):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle64)
+        ptr = C.c_void_p()
+        self._chk(lib().b200cd_ipc_open(self.h, buf, C.byref(ptr)), "ipc_open")
+        return ptr.value
+
+    def ipc_close(self, ptr):
+        lib().b200cd_ipc_close(self.h, C.c_void_p(ptr))
+
+    def bvh_set_peers(self, bvh, nranks, my_rank, peers):
+        arr = (C.c_void_p * (4 * nranks))(*[C.c_void_p(p) for p in peers])
+        self._chk(lib().b200cd_bvh_set_peers(self.h, bvh.h, C.c_uint32(nranks), C.c_uint32(my_rank), arr), "bvh_set_peers")
+
+    def partition_counts_device(self, d_keys, count, d_splitters, nsplit, d_counts_out):
+        self._chk(lib().b200cd_partition_counts_device(self.h, C.c_void_p(d_keys), C.c_uint32(count), C.c_void_p(d_splitters),
+                                                       C.c_uint32(nsplit), C.c_void_p(d_counts_out)), "partition_counts_device")
+
+    def partition_to_peers_device(self, bvh, d_keys, first_id, count, d_splitters, nsplit, d_recv_offsets):
+        self._chk(lib().b200cd_partition_to_peers_device(self.h, bvh.h, C.c_void_p(d_keys), C.c_uint32(first_id), C.c_uint32(count),
+                                                         C.c_void_p(d_splitters), C.c_uint32(nsplit), C.c_void_p(d_recv_offsets)),
+                  "partition_to_peers_device")
+
+    def send_ghosts_to_peers_device(self, bvh, d_peer_boxes, npeers, K, peer_mask):
+        self._chk(lib().b200cd_send_ghosts_to_peers_device(self.h, bvh.h, C.c_void_p(d_peer_boxes), C.c_uint32(npeers),
+                                                           C.c_uint32(K), C.c_uint32(peer_mask)), "send_ghosts_to_peers_device")
+
+    def ghost_counter_reset(self, bvh):
+        self._chk(lib().b200cd_ghost_counter_reset(self.h, bvh.h), "ghost_counter_reset")
+
+    def ghost_counter_read(self, bvh):
+        cnt = C.c_uint64()
+        self._chk(lib().b200cd_ghost_counter_read(self.h, bvh.h, C.byref(cnt)), "ghost_counter_read")
+        return int(cnt.value)
 
     def sort_pairs_device(self, d_ptr, count, id_bits=0):
         self._chk(lib().b200cd_sort_pairs_device(self.h, C.c_void_p(d_ptr), C.c_uint64(count), C.c_uint32(id_bits)),

@@ -14,9 +14,26 @@
 #include <new>
 #include <vector>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 using namespace b200cd;
+
+// base address of the allocation a device pointer belongs to. The driver entry point is fetched
+// through the runtime, so the library does not link libcuda (it must load on machines without a driver).
+static int cuMemGetAddressRange_shim(void** base, size_t* size, void* ptr) {
+    typedef CUresult (*fn_t)(CUdeviceptr*, size_t*, CUdeviceptr);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return 1;
+    CUdeviceptr b = 0;
+    size_t s = 0;
+    CUresult r = reinterpret_cast<fn_t>(fn)(&b, &s, (CUdeviceptr)ptr);
+    *base = (void*)b;
+    *size = s;
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
 
 #define API extern "C" __attribute__((visibility("default")))
 
@@ -70,6 +87,8 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_leaves);
     cudaFree(b->d_ghost_out);
     cudaFree(b->d_cut_scratch);
+    cudaFree(b->d_peers);
+    cudaFree(b->d_ghost_in_count);
     cudaFree(b->d_root_box);
     cudaFree(b->d_cand);
     cudaFree(b->d_entries);
@@ -118,6 +137,8 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
         b->ghost_out_cap = ghost_cap;
         A(dev_alloc(ctx, &b->d_ghost_out, (uint64_t)max_peers * ghost_cap));
         A(dev_alloc(ctx, &b->d_cut_scratch, (uint64_t)ghost_max_k() * 6 + 1));
+        A(dev_alloc(ctx, &b->d_peers, 1));
+        A(dev_alloc(ctx, &b->d_ghost_in_count, 2));
     }
     A(dev_alloc(ctx, &b->d_root_box, 8));
     A(dev_alloc(ctx, &b->d_counters, 8));
@@ -726,8 +747,126 @@ API int b200cd_select_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void
 
 API int b200cd_bvh_ghost_buffer(b200cd_ctx* ctx, b200cd_bvh* bvh, void** d_ptr, uint64_t* capacity) {
     if (!ctx || !bvh || !d_ptr) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
-    *d_ptr = bvh->d_leaves + bvh->n;  // right after the local leaves of the CURRENT build
-    if (capacity) *capacity = bvh->ghost_cap + (bvh->cap - bvh->n);
+    *d_ptr = bvh->d_leaves + bvh->cap;  // fixed place: after the room for local leaves
+    if (capacity) *capacity = bvh->ghost_cap;
+    return B200CD_OK;
+}
+
+// ---- peer memory (NVLink): ranks write (key, id) and ghost records straight into each other's buffers
+
+API int b200cd_ipc_export(b200cd_ctx* ctx, b200cd_bvh* bvh, uint8_t* handles_out /* 4 x 64 bytes */, uint64_t* offsets_out /* 4 */) {
+    if (!ctx || !bvh || !handles_out || !offsets_out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (!bvh->d_peers) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
+    DeviceGuard g(ctx->device);
+    void* ptrs[4] = {bvh->d_keys[0], bvh->d_ids[0], bvh->d_leaves, bvh->d_ghost_in_count};
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    for (int i = 0; i < 4; ++i) {
+        cudaIpcMemHandle_t h;
+        CD_CUDA(ctx, cudaIpcGetMemHandle(&h, ptrs[i]));
+        memcpy(handles_out + 64 * i, &h, 64);
+        // cudaIpcOpenMemHandle maps the whole allocation: remember where inside it the buffer starts
+        void* base = nullptr;
+        size_t size = 0;
+        if (cuMemGetAddressRange_shim(&base, &size, ptrs[i]) != 0) return set_error(ctx, B200CD_E_CUDA, "address range query failed");
+        offsets_out[i] = (uint64_t)((char*)ptrs[i] - (char*)base);
+    }
+    offsets_out[2] += sizeof(LeafRec) * (uint64_t)bvh->cap;  // peers address my GHOST records
+    return B200CD_OK;
+}
+
+API int b200cd_ipc_open(b200cd_ctx* ctx, const uint8_t* handle64, void** d_ptr_out) {
+    if (!ctx || !handle64 || !d_ptr_out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CD_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200CD_OK;
+}
+
+API int b200cd_ipc_close(b200cd_ctx* ctx, void* d_ptr) {
+    if (!ctx) return B200CD_E_INVALID;
+    DeviceGuard g(ctx->device);
+    CD_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return B200CD_OK;
+}
+
+/* peers[4 * r + {0,1,2,3}] = rank r's key buffer, id buffer, ghost records, ghost counter as seen from THIS GPU
+ * (the rank's own entries = its local buffers; pass NULLs for r == my_rank to have them filled in). */
+API int b200cd_bvh_set_peers(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t nranks, uint32_t my_rank, void* const* peers) {
+    if (!ctx || !bvh || !peers || nranks == 0 || nranks > RS_MAX_SPLIT_P1 || my_rank >= nranks)
+        return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    if (!bvh->d_peers) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
+    DeviceGuard g(ctx->device);
+    PeerTable t;
+    memset(&t, 0, sizeof t);
+    for (uint32_t r = 0; r < nranks; ++r) {
+        if (r == my_rank) {
+            t.keys[r] = bvh->d_keys[0];
+            t.ids[r] = bvh->d_ids[0];
+            t.ghosts[r] = bvh->d_leaves + bvh->cap;
+            t.ghost_count[r] = bvh->d_ghost_in_count;
+        } else {
+            t.keys[r] = static_cast<uint64_t*>(peers[4 * r + 0]);
+            t.ids[r] = static_cast<uint32_t*>(peers[4 * r + 1]);
+            t.ghosts[r] = static_cast<LeafRec*>(peers[4 * r + 2]);
+            t.ghost_count[r] = static_cast<unsigned long long*>(peers[4 * r + 3]);
+        }
+    }
+    t.ghost_cap = bvh->ghost_cap;
+    CD_CUDA(ctx, cudaMemcpyAsync(bvh->d_peers, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200CD_OK;
+}
+
+API int b200cd_partition_counts_device(b200cd_ctx* ctx, const void* d_keys, uint32_t count, const void* d_splitters,
+                                       uint32_t nsplit, void* d_counts_out) {
+    if (!ctx || !d_counts_out || (count && !d_keys) || (nsplit && !d_splitters) || nsplit > 15) return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    DeviceGuard g(ctx->device);
+    radix_partition_counts(static_cast<const uint64_t*>(d_keys), count, static_cast<const uint64_t*>(d_splitters), (int)nsplit,
+                           static_cast<uint32_t*>(d_counts_out), ctx->sm_count, ctx->stream);
+    CD_CUDA(ctx, cudaGetLastError());
+    return B200CD_OK;
+}
+
+API int b200cd_partition_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_keys, uint32_t first_id, uint32_t count,
+                                         const void* d_splitters, uint32_t nsplit, const void* d_recv_offsets) {
+    if (!ctx || !bvh || !d_recv_offsets || (count && !d_keys) || (nsplit && !d_splitters) || nsplit > 15) return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    if (!bvh->d_peers) return set_error(ctx, B200CD_E_INVALID, "b200cd_bvh_set_peers has not been called");
+    if (radix_tile_status_words(count, 1) > bvh->tile_status_words) return set_error(ctx, B200CD_E_INVALID, "slice larger than the BVH's scratch");
+    DeviceGuard g(ctx->device);
+    radix_partition_to_peers(static_cast<const uint64_t*>(d_keys), first_id, count, static_cast<const uint64_t*>(d_splitters),
+                             (int)nsplit, bvh->d_peers, static_cast<const uint32_t*>(d_recv_offsets), bvh->d_hist,
+                             bvh->d_tile_status, ctx->stream);
+    CD_CUDA(ctx, cudaGetLastError());
+    return B200CD_OK;
+}
+
+API int b200cd_ghost_counter_reset(b200cd_ctx* ctx, b200cd_bvh* bvh) {
+    if (!ctx || !bvh || !bvh->d_ghost_in_count) return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    DeviceGuard g(ctx->device);
+    CD_CUDA(ctx, cudaMemsetAsync(bvh->d_ghost_in_count, 0, sizeof(unsigned long long), ctx->stream));
+    return B200CD_OK;
+}
+
+API int b200cd_ghost_counter_read(b200cd_ctx* ctx, b200cd_bvh* bvh, uint64_t* count_out) {
+    if (!ctx || !bvh || !count_out || !bvh->d_ghost_in_count) return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    DeviceGuard g(ctx->device);
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, bvh->d_ghost_in_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *count_out = *reinterpret_cast<unsigned long long*>(ctx->h_scalars);
+    if (*count_out > bvh->ghost_cap) return set_error(ctx, B200CD_E_CAPACITY, "more ghosts arrived than ghost_capacity");
+    return B200CD_OK;
+}
+
+API int b200cd_send_ghosts_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_peer_boxes, uint32_t npeers, uint32_t K,
+                                           uint32_t peer_mask) {
+    if (!ctx || !bvh || !d_peer_boxes || npeers == 0 || npeers > RS_MAX_SPLIT_P1 || K == 0 || K > (uint32_t)ghost_max_k())
+        return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    if (!bvh->built || !bvh->d_peers) return set_error(ctx, B200CD_E_INVALID, "BVH not built / peers not set");
+    DeviceGuard g(ctx->device);
+    launch_ghosts_to_peers(bvh->d_leaves, bvh->n, static_cast<const float*>(d_peer_boxes), npeers, K, peer_mask, bvh->d_peers,
+                           ctx->stream);
+    CD_CUDA(ctx, cudaGetLastError());
     return B200CD_OK;
 }
 
@@ -818,7 +957,7 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
     for (int attempt = 0; attempt < 4; ++attempt) {
         if (need_broad) {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
-            launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, shard, nshards, chunk, nquery, /*foreign*/ 0, b->d_entries,
+            launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, shard, nshards, chunk, nquery, /*foreign*/ 0, 0u, b->d_entries,
                          b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
         } else {
@@ -880,7 +1019,7 @@ int run_ghost_query(b200cd_ctx* ctx, b200cd_bvh* b, uint64_t nghost, int keep, u
     const uint32_t n = b->n;
     const uint64_t base = keep ? b->npairs : 0;
     *count_out = base;
-    if (nghost > b->ghost_cap + (b->cap - n)) return set_error(ctx, B200CD_E_CAPACITY, "more ghosts than the BVH has room for");
+    if (nghost > b->ghost_cap) return set_error(ctx, B200CD_E_CAPACITY, "more ghosts than the BVH has room for");
     if (nghost == 0 || n == 0) return B200CD_OK;
     if (nghost > 0xffffff00ull) return set_error(ctx, B200CD_E_TOOBIG, "too many ghost queries");
     const uint32_t nquery = (uint32_t)nghost;
@@ -908,7 +1047,7 @@ int run_ghost_query(b200cd_ctx* ctx, b200cd_bvh* b, uint64_t nghost, int keep, u
         b->h_counters[7] = base;
         CD_CUDA(ctx, cudaMemcpyAsync(b->d_counters + 1, b->h_counters + 7, sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
         if (need_broad)
-            launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, 0, 1, B200CD_QUERY_BLOCK, nquery, /*foreign*/ 1, b->d_entries,
+            launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, 0, 1, B200CD_QUERY_BLOCK, nquery, /*foreign*/ 1, b->cap, b->d_entries,
                          b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s);
         launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s);
         CD_CUDA(ctx, cudaMemcpyAsync(b->h_counters, b->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

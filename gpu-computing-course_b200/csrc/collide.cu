@@ -163,7 +163,7 @@ entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_
 // ---------------------------------------------------------------- K5b: traversal
 __global__ void __launch_bounds__(BR_THREADS)
 broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, const float* __restrict__ root_box,
-             uint32_t n, uint32_t shard, uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign,
+             uint32_t n, uint32_t shard, uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base,
              const Node32* __restrict__ entries, const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand,
              uint64_t cand_cap, unsigned long long* __restrict__ counters) {
     __shared__ uint2 queue[BR_WARPS][BR_QUEUE];
@@ -184,7 +184,7 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
     int qcmp = 0x7fffffff;
     if (t < nquery) {
         if (foreign) {
-            q = n + t;
+            q = ghost_base + t;
             qcmp = -1;
         } else {
             const uint64_t qq = query_position(t, shard, nshards, chunk);
@@ -497,7 +497,7 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
 }  // namespace
 
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
-                  uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, Node32* d_entries,
+                  uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries,
                   uint32_t* d_entry_count, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
                   cudaStream_t s) {
     if (nquery == 0 || n == 0 || (!foreign && n < 2)) return;
@@ -508,7 +508,7 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
         count_launch();
     }
     broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery, foreign,
-                                               d_entries, d_entry_count, d_cand, cand_cap, d_counters);
+                                               ghost_base, d_entries, d_entry_count, d_cand, cand_cap, d_counters);
     count_launch();
 }
 

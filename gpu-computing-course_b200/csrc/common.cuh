@@ -70,6 +70,10 @@ struct b200cd_mesh {
     float* d_stage = nullptr;    // nverts * 3: H2D landing area of b200cd_mesh_update (kept between frames)
 };
 
+namespace b200cd {
+struct PeerTable;
+}
+
 struct b200cd_bvh {
     b200cd_ctx* ctx = nullptr;
     uint32_t n = 0;         // triangles (leaves) currently in the tree
@@ -77,6 +81,8 @@ struct b200cd_bvh {
     uint64_t ghost_cap = 0; // ghost leaf records that fit after the local leaves in d_leaves
     b200cd::LeafRec* d_ghost_out = nullptr;   // [peers][ghost_out_cap] outgoing ghost lists
     uint32_t* d_cut_scratch = nullptr;        // coarse-box reduction scratch (256*6+1 words)
+    b200cd::PeerTable* d_peers = nullptr;     // peer-memory destinations (b200cd_bvh_set_peers)
+    unsigned long long* d_ghost_in_count = nullptr;  // ghosts appended to MY ghost records by the peers (and by me)
     uint64_t ghost_out_cap = 0;
     uint32_t nverts = 0;
     bool built = false;
@@ -171,6 +177,23 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
 void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t iota_base, uint64_t* keys_out,
                      uint32_t* vals_out, uint32_t n, const uint64_t* d_splitters, int nsplit, uint32_t* d_hist,
                      uint32_t* d_tile_status, int sms, cudaStream_t s);
+#define RS_MAX_SPLIT_P1 16  // ranks a partitioned build can address
+// Peer-memory destinations of a partitioned build (own memory for the rank itself, cudaIpc-mapped
+// memory of the other ranks' GPUs otherwise; kernels store / atomically append through them over NVLink):
+// bucket d of the range partition goes into rank d's (key, id) receive buffers, ghosts for rank d are
+// appended to its ghost records under its counter.
+struct PeerTable {
+    uint64_t* keys[RS_MAX_SPLIT_P1];
+    uint32_t* ids[RS_MAX_SPLIT_P1];
+    LeafRec* ghosts[RS_MAX_SPLIT_P1];
+    unsigned long long* ghost_count[RS_MAX_SPLIT_P1];
+    unsigned long long ghost_cap;
+};
+void radix_partition_counts(const uint64_t* keys_in, uint32_t n, const uint64_t* d_splitters, int nsplit, uint32_t* d_counts,
+                            int sms, cudaStream_t s);
+void radix_partition_to_peers(const uint64_t* keys_in, uint32_t iota_base, uint32_t n, const uint64_t* d_splitters, int nsplit,
+                              const PeerTable* d_peers, const uint32_t* d_recv_offsets, uint32_t* d_hist,
+                              uint32_t* d_tile_status, cudaStream_t s);
 uint64_t radix_tile_status_words(uint32_t n, int npass);
 uint32_t radix_hist_words(int npass);
 // lbvh.cu
@@ -193,11 +216,14 @@ int ghost_max_k();
 void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                    uint32_t peer_mask, LeafRec* d_ghosts, uint64_t cap_per_peer, unsigned long long* d_counts,
                    cudaStream_t s);
+// same selection, but the records are appended straight into the peers' ghost buffers (remote atomics + stores)
+void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
+                            uint32_t peer_mask, const PeerTable* d_peers, cudaStream_t s);
 // collide.cu
-// foreign != 0: the queries are the nquery ghost records stored after the n local leaves; they start at the
+// foreign != 0: the queries are the nquery ghost records stored at leaves[ghost_base ...]; they start at the
 // root and are tested against every local leaf (no "only later positions" rule)
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
-                  uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
+                  uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
                   uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s);
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s);

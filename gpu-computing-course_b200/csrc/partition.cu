@@ -89,10 +89,11 @@ constexpr int GH_GROUP = 16;  // coarse boxes per super box
 // like the traversal) against that peer's coarse boxes - first the peer's overall box, then super
 // boxes of 16 consecutive coarse boxes, then the coarse boxes of the super boxes it overlaps - and,
 // on the first hit, appends the leaf's 64-byte record to the peer's ghost list (warp-aggregated atomic).
+template <bool REMOTE>
 __global__ void __launch_bounds__(256)
 ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __restrict__ peer_boxes, uint32_t npeers,
              uint32_t K, uint32_t peer_mask, LeafRec* __restrict__ ghosts, uint64_t cap_per_peer,
-             unsigned long long* __restrict__ counts) {
+             unsigned long long* __restrict__ counts, const PeerTable* __restrict__ peers) {
     __shared__ float s_box[GH_MAXK][6];
     __shared__ float s_sup[GH_MAXK / GH_GROUP + 1][6];  // super boxes; the last used slot + 1 .. : [nsup] = overall box
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,11 +142,15 @@ ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __rest
         }
         const uint32_t m = __ballot_sync(0xffffffffu, hit);
         if (m) {
+            // one atomic per warp reserves the slots: on my own list, or (REMOTE) on peer p's ghost counter
+            // over NVLink, followed by 256-bit stores into peer p's ghost records
+            unsigned long long* ctr = REMOTE ? peers->ghost_count[p] : counts + p;
+            const unsigned long long cap = REMOTE ? peers->ghost_cap : (unsigned long long)cap_per_peer;
             unsigned long long base = 0;
-            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(counts + p, (unsigned long long)__popc(m));
+            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(ctr, (unsigned long long)__popc(m));
             base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
-            if (hit && base < cap_per_peer) {
-                LeafRec* dst = ghosts + (size_t)p * cap_per_peer + base;
+            if (hit && base < cap) {
+                LeafRec* dst = REMOTE ? peers->ghosts[p] + base : ghosts + (size_t)p * cap_per_peer + base;
                 st256(dst, r0, r1);
                 st256(reinterpret_cast<float4*>(dst) + 2, r2, r3);
             }
@@ -185,8 +190,16 @@ void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxe
                    cudaStream_t s) {
     cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * npeers, s);
     if (!n || !npeers || !peer_mask) return;
-    ghost_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, d_ghosts, cap_per_peer,
-                                                d_counts);
+    ghost_kernel<false><<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, d_ghosts,
+                                                       cap_per_peer, d_counts, nullptr);
+    count_launch();
+}
+
+void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
+                            uint32_t peer_mask, const PeerTable* d_peers, cudaStream_t s) {
+    if (!n || !npeers || !peer_mask) return;
+    ghost_kernel<true><<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, nullptr, 0, nullptr,
+                                                      d_peers);
     count_launch();
 }
 

@@ -45,7 +45,7 @@ struct PassList {
 // Digit of a key: a bit field (radix passes) or, for the multi-GPU range partition, the number of
 // splitters <= key (splitters ascending, at most RS_MAX_SPLIT of them, read from device memory
 // because they are computed on the device).
-constexpr int RS_MAX_SPLIT = 15;
+constexpr int RS_MAX_SPLIT = 15;  // == RS_MAX_SPLIT_P1 - 1 (common.cuh)
 template <bool SPLIT>
 struct Digit;
 template <>
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
 rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
         uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values, uint32_t iota_base,
         const uint64_t* __restrict__ splitters, int nsplit,
+        const PeerTable* __restrict__ peers,        // non-null: bucket d is written into peer d's buffers (NVLink stores)
         const uint32_t* __restrict__ digit_base_g,  // [256] exclusive global digit offsets of this pass
         uint32_t* __restrict__ status,              // [ntiles][256] look-back words of this pass
         uint32_t* __restrict__ ticket) {
@@ -300,8 +301,14 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         if (r < tile_items) {
             const uint64_t kk = stage_k[r];
             const uint32_t pos = digit_base[digit_of(kk)] + r;
-            keys_out[pos] = kk;
-            if (HAS_VALUES) vals_out[pos] = stage_v[r];
+            if (SPLIT && peers) {  // pos is relative to the start of my segment in the destination rank's buffer
+                const uint32_t d = digit_of(kk);
+                peers->keys[d][pos] = kk;
+                if (HAS_VALUES) peers->ids[d][pos] = stage_v[r];
+            } else {
+                keys_out[pos] = kk;
+                if (HAS_VALUES) vals_out[pos] = stage_v[r];
+            }
         }
     }
 }
@@ -352,11 +359,11 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
         uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
         if (vals)
             rs_pass<true, false><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n,
-                                                       pl.shift[p], pl.mask[p], (iota_values && p == 0) ? 1 : 0, 0u, nullptr, 0,
+                                                       pl.shift[p], pl.mask[p], (iota_values && p == 0) ? 1 : 0, 0u, nullptr, 0, nullptr,
                                                        d_hist + p * RS_RADIX, status, d_ticket + p);
         else
             rs_pass<false, false><<<tiles, RS_THREADS, rs_smem_bytes(false), s>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, pl.shift[p],
-                                                        pl.mask[p], 0, 0u, nullptr, 0, d_hist + p * RS_RADIX, status, d_ticket + p);
+                                                        pl.mask[p], 0, 0u, nullptr, 0, nullptr, d_hist + p * RS_RADIX, status, d_ticket + p);
         count_launch();
         cur ^= 1;
     }
@@ -388,8 +395,37 @@ void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t 
     rs_scan<<<1, RS_RADIX, 0, s>>>(d_hist);
     count_launch();
     rs_pass<true, true><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys_in, keys_out, vals_in, vals_out, n, 0, 0u,
-                                                                vals_in ? 0 : 1, iota_base, d_splitters, nsplit, d_hist,
-                                                                d_tile_status, d_ticket);
+                                                                vals_in ? 0 : 1, iota_base, d_splitters, nsplit, nullptr,
+                                                                d_hist, d_tile_status, d_ticket);
+    count_launch();
+}
+
+// Fused partition + exchange, step 1: how many of my keys go to each rank (u32 counts[nsplit+1] in device memory).
+void radix_partition_counts(const uint64_t* keys_in, uint32_t n, const uint64_t* d_splitters, int nsplit, uint32_t* d_counts,
+                            int sms, cudaStream_t s) {
+    cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (nsplit + 1), s);
+    if (n == 0) return;
+    const uint32_t hblocks = min((n + RH_THREADS - 1) / RH_THREADS, (uint32_t)sms * 8u);
+    rs_histogram_split<<<hblocks, RH_THREADS, 0, s>>>(keys_in, n, d_splitters, nsplit, d_counts);
+    count_launch();
+}
+
+// Step 2: one pass over my keys; every (key, id) is stored directly into its owner's receive buffer
+// (d_peers, device-resident PeerTable) at d_recv_offsets[d] + its stable rank inside my bucket d.
+// The stores to other ranks travel over NVLink while the tile is still being ranked.
+void radix_partition_to_peers(const uint64_t* keys_in, uint32_t iota_base, uint32_t n, const uint64_t* d_splitters, int nsplit,
+                              const PeerTable* d_peers, const uint32_t* d_recv_offsets, uint32_t* d_hist,
+                              uint32_t* d_tile_status, cudaStream_t s) {
+    if (n == 0) return;
+    cudaFuncSetAttribute(rs_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t* d_ticket = d_hist + 2 * RS_RADIX;
+    // digit bases = where my segment starts in each destination buffer; unused digits stay 0
+    cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * (2 * RS_RADIX + 1), s);
+    cudaMemcpyAsync(d_hist, d_recv_offsets, sizeof(uint32_t) * (nsplit + 1), cudaMemcpyDeviceToDevice, s);
+    cudaMemsetAsync(d_tile_status, 0, sizeof(uint32_t) * (size_t)tiles * RS_RADIX, s);
+    rs_pass<true, true><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys_in, nullptr, nullptr, nullptr, n, 0, 0u, 1, iota_base,
+                                                                d_splitters, nsplit, d_peers, d_hist, d_tile_status, d_ticket);
     count_launch();
 }
 

@@ -210,12 +210,16 @@ class PartitionedRank:
         self.ctx.key_histogram_device(self.keys.data_ptr(), self.cnt, self.shift, self.hist.data_ptr())
         return self.hist
 
-    # -- phase 2: splitters from the GLOBAL histogram, bucket my (key, id) by owner
-    def partition(self, global_hist):
+    def splitters_from(self, global_hist):
         csum = torch.cumsum(global_hist.to(torch.int64), 0)
         targets = (torch.arange(1, self.world, device=self.dev, dtype=torch.int64) * csum[-1]) // self.world
         bins = torch.searchsorted(csum, targets)                     # first bin whose cumulative count reaches the target
         self.splitters = ((bins + 1) << self.shift).contiguous()     # keys >= splitter r-1 belong to rank >= r
+        return self.splitters
+
+    # -- phase 2: splitters from the GLOBAL histogram, bucket my (key, id) by owner
+    def partition(self, global_hist):
+        self.splitters_from(global_hist)
         counts = self.ctx.partition_keys_device(self.bvh, self.keys.data_ptr(), self.lo, self.cnt,
                                                 self.splitters.data_ptr() if self.world > 1 else 0, self.world - 1,
                                                 self.pkeys.data_ptr(), self.pids.data_ptr())
@@ -306,9 +310,15 @@ def _all_counts(counts, device, group=None):
 
 
 class PartitionedSelfCollision:
-    """Per-rank driver of the partitioned build + query over torch.distributed (one process per GPU)."""
+    """Per-rank driver of the partitioned build + query over torch.distributed (one process per GPU).
 
-    def __init__(self, cd, ctx, mesh, params, group=None, slack=1.5):
+    peer_memory=True (default for world > 1): the two data exchanges are not NCCL calls but part of the
+    kernels that produce the data - the range-partition kernel stores every (key, id) straight into the
+    owning rank's buffer and the ghost-selection kernel appends records to the peers' ghost buffers, both
+    through CUDA-IPC mapped peer memory over NVLink. NCCL carries only the small collectives (histogram
+    all-reduce, count / box all-gathers, 1-word barriers) and the final gather of the pair lists."""
+
+    def __init__(self, cd, ctx, mesh, params, group=None, slack=1.5, peer_memory=True):
         self.cd, self.ctx, self.group = cd, ctx, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -317,11 +327,90 @@ class PartitionedSelfCollision:
         self.part = PartitionedRank(cd, ctx, mesh, params, self.rank, self.world, slack)
         self.counts = [0] * self.world
         self.stats = {}
+        self.peer_memory = bool(peer_memory) and self.world > 1
+        self._mapped = []
+        if self.peer_memory:
+            handles, offsets = ctx.ipc_export(self.part.bvh)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, (handles, offsets), group=group)
+            peers = [0] * (4 * self.world)
+            for r, (h, off) in enumerate(everyone):
+                if r == self.rank:
+                    continue
+                for i in range(4):
+                    base = ctx.ipc_open(h[64 * i:64 * i + 64])
+                    self._mapped.append(base)
+                    peers[4 * r + i] = base + off[i]
+            ctx.bvh_set_peers(self.part.bvh, self.world, self.rank, peers)
+            self._counts_dev = torch.zeros(self.world, dtype=torch.int32, device=self.device)
+            self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+            dist.barrier(group=group)
+
+    def _barrier(self):
+        dist.all_reduce(self._token, group=self.group)  # stream-ordered: everybody's preceding kernels have finished
+
+    def close(self):
+        for base in self._mapped:
+            self.ctx.ipc_close(base)
+        self._mapped = []
+
+    def _step_peer_memory(self, profile):
+        import time
+        p, r, w, g, ctx = self.part, self.rank, self.world, self.group, self.ctx
+        marks = []
+
+        def mark(name):
+            if profile:
+                torch.cuda.synchronize(self.device)
+                marks.append((name, time.perf_counter()))
+        mark("start")
+        ctx.ghost_counter_reset(p.bvh)
+        hist = p.keys_and_histogram()
+        dist.all_reduce(hist, group=g)  # also orders every rank's counter reset before any ghost append of this step
+        mark("keys+hist+allreduce")
+        splitters = p.splitters_from(hist)
+        ctx.partition_counts_device(p.keys.data_ptr(), p.cnt, splitters.data_ptr(), w - 1, self._counts_dev.data_ptr())
+        allc = torch.empty(w * w, dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(allc, self._counts_dev, group=g)
+        allc = allc.view(w, w)                                         # [source rank][owner rank]
+        recv_off = allc[:r].sum(0, dtype=torch.int32).contiguous()     # my segment's start in every owner's buffer
+        nlocal_t = allc[:, r].sum()
+        ctx.partition_to_peers_device(p.bvh, p.keys.data_ptr(), p.lo, p.cnt, splitters.data_ptr(), w - 1, recv_off.data_ptr())
+        p.nlocal = int(nlocal_t.item())
+        if p.nlocal > p.cap:
+            raise RuntimeError(f"rank {r}: {p.nlocal} triangles in my Morton range, capacity {p.cap}")
+        self._barrier()                                                # all (key, id) stores have landed
+        mark("partition+exchange (fused)")
+        boxes = p.build()
+        mark("build")
+        allb = torch.empty(w * boxes.numel(), dtype=boxes.dtype, device=self.device)
+        dist.all_gather_into_tensor(allb, boxes, group=g)
+        mask = 0
+        for q in range(r + 1, w):
+            mask |= 1 << q
+        ctx.send_ghosts_to_peers_device(p.bvh, allb.data_ptr(), w, PARTITION_BOXES, mask)  # appends travel during the local query
+        mark("ghost select+send (fused)")
+        p.collide_local()
+        mark("local query")
+        self._barrier()                                                # all ghost appends have landed
+        p.nghost = ctx.ghost_counter_read(p.bvh)
+        local = p.collide_ghosts()
+        mark("ghost query")
+        self.stats = {"local_triangles": p.nlocal, "ghosts": p.nghost, "local_pairs": int(local.numel()), "peer_memory": True}
+        merged, self.counts = gather_pairs(local, 0, g)
+        if r == 0 and merged.numel() > 1:
+            ctx.sort_pairs_device(merged.data_ptr(), merged.numel(), id_bits=max(1, int(p.n - 1).bit_length()))
+        mark("gather+sort")
+        if profile:
+            self.stats["phase_ms"] = {b[0]: round(1e3 * (b[1] - a[1]), 3) for a, b in zip(marks, marks[1:])}
+        return merged
 
     def step(self, profile=False):
         """one distributed build + query; rank 0 gets the sorted packed pair list (device tensor).
         profile=True synchronises after every phase and records wall-clock phase times in self.stats."""
         import time
+        if self.peer_memory:
+            return self._step_peer_memory(profile)
         p, r, w, g = self.part, self.rank, self.world, self.group
         marks = []
 

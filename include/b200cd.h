@@ -284,6 +284,33 @@ int b200cd_bvh_ghost_buffer(b200cd_ctx* ctx, b200cd_bvh* bvh, void** d_ptr, uint
 int b200cd_collide_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint64_t nghost, int keep_pairs,
                                  const void** d_pairs_out, uint64_t* count_out);
 
+/* ---- peer memory (NVLink / NVSwitch) variant of steps 3 and 7 -----------------
+ * One process per GPU: each rank exports its receive buffers with CUDA IPC once
+ * (b200cd_ipc_export -> exchange the bytes -> b200cd_ipc_open -> b200cd_bvh_set_peers). After that
+ *   b200cd_partition_to_peers_device    ranks and scatters the (key, id) pairs of the range partition
+ *                                       in ONE kernel whose stores land directly in the owning rank's
+ *                                       buffers over NVLink (fused partition + all-to-all);
+ *   b200cd_send_ghosts_to_peers_device  appends ghost records to the peers' ghost buffers with remote
+ *                                       atomics + 256-bit stores (fused selection + exchange).
+ * The caller separates the phases with a collective on the same stream (e.g. a 1-word all-reduce). */
+/* handles_out: 4 x 64 bytes (key buffer, id buffer, leaf/ghost buffer, ghost counter);
+ * offsets_out[4]: byte offset of each buffer inside the mapping b200cd_ipc_open returns */
+int b200cd_ipc_export(b200cd_ctx* ctx, b200cd_bvh* bvh, uint8_t* handles_out, uint64_t* offsets_out);
+int b200cd_ipc_open(b200cd_ctx* ctx, const uint8_t* handle64, void** d_ptr_out);
+int b200cd_ipc_close(b200cd_ctx* ctx, void* d_ptr);
+/* peers[4 * r + i]: rank r's buffer i (mapped pointer + offset); the entries of my_rank are ignored */
+int b200cd_bvh_set_peers(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t nranks, uint32_t my_rank, void* const* peers);
+/* u32 counts[nsplit + 1] (device): how many of my keys each rank owns */
+int b200cd_partition_counts_device(b200cd_ctx* ctx, const void* d_keys, uint32_t count, const void* d_splitters,
+                                   uint32_t nsplit, void* d_counts_out);
+/* d_recv_offsets: u32[nsplit + 1] (device): where my segment starts in each rank's receive buffers */
+int b200cd_partition_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_keys, uint32_t first_id, uint32_t count,
+                                     const void* d_splitters, uint32_t nsplit, const void* d_recv_offsets);
+int b200cd_send_ghosts_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_peer_boxes, uint32_t npeers, uint32_t K,
+                                       uint32_t peer_mask);
+int b200cd_ghost_counter_reset(b200cd_ctx* ctx, b200cd_bvh* bvh);
+int b200cd_ghost_counter_read(b200cd_ctx* ctx, b200cd_bvh* bvh, uint64_t* count_out);
+
 #ifdef __cplusplus
 }
 #endif
