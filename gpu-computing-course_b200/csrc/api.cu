@@ -940,7 +940,7 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
     if (rc == B200CD_OK) rc = grow(ctx, &b->d_out, &b->out_cap, std::max<uint64_t>(b->out_cap, std::max<uint64_t>(nquery / 2 + 4096, hint)));
     if (rc == B200CD_OK && sorted) rc = grow(ctx, &b->d_out_tmp, &b->out_tmp_cap, b->out_cap);
     if (rc != B200CD_OK) return rc;
-    const uint64_t qblocks = ((uint64_t)nquery + B200CD_QUERY_BLOCK - 1) / B200CD_QUERY_BLOCK;
+    const uint64_t qblocks = ((uint64_t)nquery + B200CD_QUERY_GROUP - 1) / B200CD_QUERY_GROUP;  // entry lists
     if (qblocks > b->entry_blocks) {
         cudaFree(b->d_entries);
         cudaFree(b->d_entry_count);
@@ -948,7 +948,8 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
         b->d_entry_count = nullptr;
         b->entry_blocks = 0;
         CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entries), qblocks * B200CD_MAX_ENTRIES * sizeof(Node32)));
-        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entry_count), qblocks * sizeof(uint32_t)));
+        // counts, then (32-byte aligned) one 8-float union box per group
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entry_count), (((qblocks + 7) & ~7ull) + 8 * qblocks) * sizeof(uint32_t)));
         b->entry_blocks = qblocks;
     }
 

@@ -29,6 +29,8 @@
 //     survivors compacted through a per-warp shared-memory queue, then the other 15 axes).
 //   - results are appended the same way (warp-aggregated atomic).
 // -fmad=false: every double operation rounds separately, like the host reference.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200cd {
@@ -37,8 +39,7 @@ namespace {
 
 constexpr int BR_THREADS = B200CD_QUERY_BLOCK;  // one block = 256 CONSECUTIVE sorted leaves
 constexpr int BR_WARPS = BR_THREADS / 32;
-constexpr int BR_QUEUE = 128;   // per-warp candidate staging (uint2 each)
-constexpr int BR_FLUSH = 64;    // flush when at least this many are staged (<= 64 arrive per step)
+constexpr int BR_FLUSH = 64;    // flush the per-warp candidate staging when at least this many are waiting (<= 64 arrive per step)
 constexpr int BR_ENTRIES = B200CD_MAX_ENTRIES;
 
 constexpr unsigned long long ERR_STACK = 1ull;
@@ -83,22 +84,29 @@ __device__ __forceinline__ void load_children(const NodePair* __restrict__ pairs
 // per-query rule (subtree end > q, strict box overlap) is applied to each entry and below it.
 __global__ void __launch_bounds__(128)
 entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_box, uint32_t n, uint32_t shard,
-             uint32_t nshards, uint32_t chunk, uint32_t nblocks, Node32* __restrict__ entries,
-             uint32_t* __restrict__ entry_count) {
+             uint32_t nshards, uint32_t chunk, uint32_t gsize, uint32_t nblocks, Node32* __restrict__ entries,
+             uint32_t* __restrict__ entry_count /* [nblocks] counts, then [nblocks][8] floats: union box of the group's own leaves */) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
-    const uint64_t p0 = query_position(b * BR_THREADS, shard, nshards, chunk);
+    const uint64_t p0 = query_position(b * gsize, shard, nshards, chunk);
     const int root = reinterpret_cast<const int*>(root_box)[6];
     uint32_t cnt = 0;
     bool overflow = false;
     Child* out = reinterpret_cast<Child*>(entries + (size_t)b * BR_ENTRIES);
-    auto add = [&](Child c, int last) {  // entries carry the LAST leaf of their subtree in ext
+    const float inf = __int_as_float(0x7f800000);
+    float ulo[3] = {inf, inf, inf}, uhi[3] = {-inf, -inf, -inf};  // union box of the group's own leaves [q0, q1]
+    auto grow = [&](const Child& c) {
+        ulo[0] = fminf(ulo[0], c.a.x); ulo[1] = fminf(ulo[1], c.a.y); ulo[2] = fminf(ulo[2], c.a.z);
+        uhi[0] = fmaxf(uhi[0], c.a.w); uhi[1] = fmaxf(uhi[1], c.b.x); uhi[2] = fmaxf(uhi[2], c.b.y);
+    };
+    auto add = [&](Child c, int last, bool inside) {  // entries carry the LAST leaf of their subtree in ext
         c.b.w = __int_as_float(last);
+        if (inside) grow(c);  // subtrees inside the group's range tile it (together with leaf q0)
         if (cnt < (uint32_t)BR_ENTRIES) { st256(out + cnt, c.a, c.b); ++cnt; } else overflow = true;
     };
     if (p0 + 1 < n) {  // the very last leaf has no partner after it
         const int q0 = (int)p0;
-        const int q1 = (int)min((uint64_t)n - 1, p0 + BR_THREADS - 1);
+        const int q1 = (int)min((uint64_t)n - 1, p0 + gsize - 1);
         int node = root, F = 0, L = (int)n - 1;  // current node = split index; its leaf range [F, L]
         Child l, r;
         bool split_found = false;
@@ -107,12 +115,12 @@ entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_
             load_children(pairs, node, l, r);
             const int g = node;
             if (q1 <= g) {            // both ends in the left child: the right child lies entirely beyond q1
-                add(r, L);
-                if (l.link() < 0) break;
+                add(r, L, false);
+                if (l.link() < 0) { grow(l); break; }  // the group is the single leaf q0 = q1
                 node = l.link();
                 L = g;
             } else if (q0 > g) {      // both ends in the right child: the left child lies entirely before q0
-                if (r.link() < 0) break;
+                if (r.link() < 0) { grow(r); break; }
                 node = r.link();
                 F = g + 1;
             } else {                  // q0 <= g < q1: paths part here
@@ -127,12 +135,12 @@ entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_
             int curF = F, curL = g;
             while (true) {
                 if (curF >= q0 || cur.link() < 0) {  // whole subtree inside the block's range (leaf q0 itself: harmless)
-                    add(cur, curL);
+                    add(cur, curL, true);
                     break;
                 }
                 const int m = cur.link();
                 load_children(pairs, m, a, c);
-                if (q0 <= m) { add(c, curL); cur = a; curL = m; }
+                if (q0 <= m) { add(c, curL, true); cur = a; curL = m; }
                 else { curF = m + 1; cur = c; }
             }
             // walk towards q1 inside the right child [g+1, L]: left siblings lie inside the range, right siblings beyond it
@@ -140,33 +148,216 @@ entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_
             curL = L;
             while (true) {
                 if (curL <= q1 || cur.link() < 0) {
-                    add(cur, curL);
+                    add(cur, curL, true);
                     break;
                 }
                 const int m = cur.link();
                 load_children(pairs, m, a, c);
-                if (q1 <= m) { add(c, curL); cur = a; curL = m; }
-                else { add(a, m); cur = c; }
+                if (q1 <= m) { add(c, curL, false); cur = a; curL = m; }
+                else { add(a, m, true); cur = c; }
             }
         }
         if (overflow) {  // pathologically deep tree: fall back to "start at the root" (two entries = the root's children)
             load_children(pairs, root, l, r);
             cnt = 0;
             overflow = false;
-            add(l, root);
-            add(r, (int)n - 1);
+            add(l, root, true);
+            add(r, (int)n - 1, true);
         }
     }
     entry_count[b] = cnt;
+    float4* ub = reinterpret_cast<float4*>(entry_count + ((nblocks + 7u) & ~7u)) + 2 * (size_t)b;  // 32-byte aligned rows
+    st256(ub, make_float4(ulo[0], ulo[1], ulo[2], uhi[0]), make_float4(uhi[1], uhi[2], 0.f, 0.f));
 }
 
-// ---------------------------------------------------------------- K5b: traversal
+// ---------------------------------------------------------------- K5b (variant 2): persistent lanes
+// Persistent lanes (after Aila & Laine 2009). With one query per thread the warp loops as long as
+// its busiest lane (measured lane utilisation on the 16 M soup: 0.40). Here a block owns 1024
+// consecutive queries (four 256-leaf groups, each with its entry list) and every warp works
+// through its own 128 of them: whenever at least BR_REFILL lanes have run out of work, the idle
+// lanes take the warp's next queries (their records were prefetched at the previous refill), scan
+// the group's entry list and rejoin the traversal loop. Lanes of a warp still walk neighbouring
+// queries, so node fetches stay coherent. Shared memory is kept small on purpose: the unified
+// L1 is what serves ~70 % of the node fetches (a first version that staged the 1024 query boxes in
+// 24 KB of shared memory dropped the L1 hit rate from 68 % to 4 % and ran slower, profiles/r01_*).
+constexpr int BR_PER_WARP = 128;                       // queries per warp = one group (one entry list)
+constexpr int BR_GROUPS = BR_WARPS;                    // groups per block
+constexpr int BR_QB = BR_GROUPS * BR_PER_WARP;         // 1024 queries per block
+constexpr int BR_REFILL = 16;                          // refill when this many lanes are idle
+constexpr int BR_KEEP = 32;                            // start subtrees kept per group after the union-box filter
+constexpr int BR_CQ = 128;                             // candidate staging per warp: < 64 carried + <= 64 new per step
+
 __global__ void __launch_bounds__(BR_THREADS)
-broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, const float* __restrict__ root_box,
+broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, uint32_t n, uint32_t shard,
+             uint32_t nshards, uint32_t chunk, uint32_t nquery, uint32_t ngroups, int refill, const Node32* __restrict__ entries,
+             const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand, uint64_t cand_cap,
+             unsigned long long* __restrict__ counters) {
+    __shared__ uint2 s_cq[BR_WARPS][BR_CQ];
+    __shared__ Child s_entry[BR_GROUPS][BR_KEEP];
+    __shared__ uint32_t s_nkeep[BR_GROUPS];
+    __shared__ uint32_t s_spill[BR_GROUPS];             // a group kept more than BR_KEEP entries: read the rest from global
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint2* wq = s_cq[warp];
+    uint32_t staged = 0;  // warp-uniform
+    if (tid < BR_GROUPS) { s_nkeep[tid] = 0; s_spill[tid] = 0; }
+    const float inf = __int_as_float(0x7f800000);
+    const uint32_t qbase = blockIdx.x * BR_QB;         // first query slot of this block
+    __syncthreads();
+
+    // query slot t -> sorted leaf position
+    auto slot_position = [&](uint32_t t) -> uint32_t {
+        if (t >= nquery) return 0xffffffffu;
+        const uint64_t qq = query_position(t, shard, nshards, chunk);
+        return qq + 1 < n ? (uint32_t)qq : 0xffffffffu;  // the last leaf has no partner with a larger position
+    };
+
+    // ---- entry lists: thread (g, e) keeps entry e of group g if it overlaps the group's union box
+    for (uint32_t ge = tid; ge < BR_GROUPS * BR_ENTRIES; ge += BR_THREADS) {
+        const uint32_t g = ge / BR_ENTRIES, e = ge % BR_ENTRIES;
+        const uint32_t eb = blockIdx.x * BR_GROUPS + g;             // the group's entry list
+        if (eb < ngroups && e < __ldg(entry_count + eb)) {
+            float4 u0, u1;
+            ld256_nc(reinterpret_cast<const float4*>(entry_count + ((ngroups + 7u) & ~7u)) + 2 * (size_t)eb, u0, u1);
+            const float ulo[3] = {u0.x, u0.y, u0.z}, uhi[3] = {u0.w, u1.x, u1.y};
+            Child c;
+            ld256_nc(entries + (size_t)eb * BR_ENTRIES + e, c.a, c.b);
+            if (overlap(ulo, uhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y)) {
+                const uint32_t at = atomicAdd(&s_nkeep[g], 1u);
+                if (at < (uint32_t)BR_KEEP) s_entry[g][at] = c; else s_spill[g] = 1;
+            }
+        }
+    }
+    __syncthreads();
+
+    int stack[B200CD_MAX_STACK];
+    int sp = 0;
+    bool overflow = false;
+
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counters + 0, (unsigned long long)staged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < staged; i += 32)
+            if (base + i < cand_cap) __stcs(cand + base + i, wq[i]);
+        staged = 0;
+        __syncwarp();
+    };
+    // stage (q, leaf) candidates of the whole warp: positions by ballot, no atomics
+    auto stage2 = [&](uint32_t q, bool candL, int leafL, bool candR, int leafR) {
+        const uint32_t bL = __ballot_sync(0xffffffffu, candL), bR = __ballot_sync(0xffffffffu, candR);
+        if (bL | bR) {
+            const uint32_t nL = __popc(bL);
+            if (candL) wq[staged + __popc(bL & lt)] = make_uint2(q, (uint32_t)leafL);
+            if (candR) wq[staged + nL + __popc(bR & lt)] = make_uint2(q, (uint32_t)leafR);
+            staged += nL + __popc(bR);
+            __syncwarp();
+            if (staged >= BR_FLUSH) flush();
+        }
+    };
+
+    // ---- this warp's 128 queries
+    const uint32_t wfirst = warp * BR_PER_WARP;          // block-relative slots [wfirst, wend)
+    const uint32_t wend = min(wfirst + BR_PER_WARP, nquery > qbase ? nquery - qbase : 0u);
+    const uint32_t g = warp;                             // the warp's group (entry list)
+    const uint32_t eb = blockIdx.x * BR_GROUPS + g;
+    const bool spilled = s_spill[g] != 0;
+    const uint32_t nkeep = spilled ? __ldg(entry_count + eb) : s_nkeep[g];  // spilled: scan the unfiltered global list
+    uint32_t next = wfirst;                              // warp-uniform
+    int q = 0x7fffffff;                                  // this lane's query position ("none": nothing ends after it)
+    float qlo[3] = {inf, inf, inf}, qhi[3] = {-inf, -inf, -inf};
+    int node = -1;
+    uint32_t visits = 0, iters = 0;  // traversal statistics (b200cd_stats::nodes_visited / warp_steps)
+    // the first refill's records
+    {
+        const uint32_t p0 = slot_position(qbase + wfirst + lane);
+        if (wfirst + lane < wend && p0 != 0xffffffffu) asm volatile("prefetch.global.L2 [%0];" ::"l"(leaves + p0));
+    }
+
+    while (true) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, node < 0);
+        if (next < wend && (__popc(idle) >= refill || idle == 0xffffffffu)) {
+            // ---- refill: idle lanes take the warp's next queries and collect their start subtrees
+            const uint32_t slot = next + __popc(idle & lt);
+            bool take = node < 0 && slot < wend;
+            next = min(wend, next + (uint32_t)__popc(idle));
+            if (take) {
+                const uint32_t p = slot_position(qbase + slot);
+                take = p != 0xffffffffu;
+                if (take) {
+                    float4 r0, r1, r2, r3;
+                    ld256_nc(leaves + p, r0, r1);
+                    ld256_nc(reinterpret_cast<const float4*>(leaves + p) + 2, r2, r3);
+                    // v0 = r0.xyz, v1 = (r0.w, r1.x, r1.y), v2 = (r1.z, r1.w, r2.x); box.cuh:13-22
+                    qlo[0] = min3_ref(r0.x, r0.w, r1.z); qhi[0] = max3_ref(r0.x, r0.w, r1.z);
+                    qlo[1] = min3_ref(r0.y, r1.x, r1.w); qhi[1] = max3_ref(r0.y, r1.x, r1.w);
+                    qlo[2] = min3_ref(r0.z, r1.y, r2.x); qhi[2] = max3_ref(r0.z, r1.y, r2.x);
+                    q = (int)p;
+                }
+            }
+            {   // records of the NEXT refill (it takes at most 32 slots starting at `next`)
+                const uint32_t pn = slot_position(qbase + next + lane);
+                if (next + lane < wend && pn != 0xffffffffu) asm volatile("prefetch.global.L2 [%0];" ::"l"(leaves + pn));
+            }
+            for (uint32_t e = 0; e < nkeep; ++e) {
+                Child c;
+                if (!spilled) c = s_entry[g][e];
+                else ld256_nc(entries + (size_t)eb * BR_ENTRIES + e, c.a, c.b);
+                const bool hit = take && c.ext() > q && overlap(qlo, qhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y);
+                const int link = c.link();
+                if (hit && link >= 0) {
+                    if (sp < B200CD_MAX_STACK) stack[sp++] = link; else overflow = true;
+                }
+                stage2((uint32_t)q, hit && link < 0, ~link, false, 0);
+            }
+            if (take) node = sp > 0 ? stack[--sp] : -1;
+            continue;
+        }
+        if (idle == 0xffffffffu) break;  // nothing left to take, nobody working
+        ++iters;
+        bool candL = false, candR = false;
+        int leafL = 0, leafR = 0;
+        if (node >= 0) {
+            ++visits;
+            Child l, r;
+            load_children(pairs, node, l, r);
+            const int linkL = l.link(), linkR = r.link();
+            // left child = leaves [.., node], right child = leaves [node+1, r.ext]: skip what ends at or before q
+            const bool hitL = node > q && overlap(qlo, qhi, l.a.x, l.a.y, l.a.z, l.a.w, l.b.x, l.b.y);
+            const bool hitR = r.ext() > q && overlap(qlo, qhi, r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y);
+            candL = hitL && linkL < 0; leafL = ~linkL;
+            candR = hitR && linkR < 0; leafR = ~linkR;
+            const bool goL = hitL && linkL >= 0, goR = hitR && linkR >= 0;
+            if (goL) {
+                node = linkL;
+                if (goR) {
+                    if (sp < B200CD_MAX_STACK) stack[sp++] = linkR; else overflow = true;
+                }
+            } else if (goR) {
+                node = linkR;
+            } else {
+                node = sp > 0 ? stack[--sp] : -1;
+            }
+        }
+        stage2((uint32_t)q, candL, leafL, candR, leafR);
+    }
+    if (staged) flush();
+    if (overflow) atomicOr(counters + 2, ERR_STACK);
+    visits = __reduce_add_sync(0xffffffffu, visits);
+    if (lane == 0) {
+        atomicAdd(counters + 3, (unsigned long long)visits);
+        atomicAdd(counters + 4, (unsigned long long)iters);
+        atomicAdd(counters + 5, (unsigned long long)nkeep);
+    }
+}
+
+// ---------------------------------------------------------------- K5b (variant 1): one query per thread
+__global__ void __launch_bounds__(BR_THREADS)
+broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, const float* __restrict__ root_box,
              uint32_t n, uint32_t shard, uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base,
              const Node32* __restrict__ entries, const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand,
              uint64_t cand_cap, unsigned long long* __restrict__ counters) {
-    __shared__ uint2 queue[BR_WARPS][BR_QUEUE];
+    __shared__ uint2 queue[BR_WARPS][BR_CQ];
     __shared__ Child s_entry[BR_ENTRIES];
     __shared__ float s_red[BR_WARPS][6];
     __shared__ uint32_t s_nentry;
@@ -393,22 +584,6 @@ __device__ __forceinline__ bool sat_stage_b(const SatInput& t) {
     return true;
 }
 
-struct Tri {
-    D3 v0, v1, v2;
-    uint32_t i0, i1, i2, id;
-};
-__device__ __forceinline__ Tri load_tri(const LeafRec* __restrict__ leaves, uint32_t pos) {
-    float4 r0, r1, r2, r3;
-    ld256_nc(leaves + pos, r0, r1);
-    ld256_nc(reinterpret_cast<const float4*>(leaves + pos) + 2, r2, r3);
-    Tri t;
-    t.v0 = {(double)r0.x, (double)r0.y, (double)r0.z};
-    t.v1 = {(double)r0.w, (double)r1.x, (double)r1.y};
-    t.v2 = {(double)r1.z, (double)r1.w, (double)r2.x};
-    t.i0 = __float_as_uint(r2.y); t.i1 = __float_as_uint(r2.z); t.i2 = __float_as_uint(r2.w);
-    t.id = __float_as_uint(r3.x);
-    return t;
-}
 // vertices only (stage B re-reads the two records; they are L1/L2-hot)
 __device__ __forceinline__ void load_verts(const LeafRec* __restrict__ leaves, uint32_t pos, D3& v0, D3& v1, D3& v2,
                                            uint32_t& id) {
@@ -471,14 +646,28 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
         uint2 entry = make_uint2(0, 0);
         if (i < total) {
             const uint2 c = __ldcs(cand + i);
-            const Tri a = load_tri(leaves, c.x), b = load_tri(leaves, c.y);
+            // the vertex indices and the ID sit in the SECOND 32 bytes of a record: on meshes most candidates are
+            // vertex-sharing neighbours, rejected here for one sector per triangle instead of two
+            float4 a2, a3, b2, b3;
+            ld256_nc(reinterpret_cast<const float4*>(leaves + c.x) + 2, a2, a3);
+            ld256_nc(reinterpret_cast<const float4*>(leaves + c.y) + 2, b2, b3);
+            const uint32_t ai0 = __float_as_uint(a2.y), ai1 = __float_as_uint(a2.z), ai2 = __float_as_uint(a2.w);
+            const uint32_t bi0 = __float_as_uint(b2.y), bi1 = __float_as_uint(b2.z), bi2 = __float_as_uint(b2.w);
+            const uint32_t aid = __float_as_uint(a3.x), bid = __float_as_uint(b3.x);
             // triangle.cuh:18-30: neighborCount >= 1 <=> any vertex index shared
-            const bool shared = a.i0 == b.i0 || a.i0 == b.i1 || a.i0 == b.i2 || a.i1 == b.i0 || a.i1 == b.i1 ||
-                                a.i1 == b.i2 || a.i2 == b.i0 || a.i2 == b.i1 || a.i2 == b.i2;
-            if (!shared && a.id != b.id) {
+            const bool shared = ai0 == bi0 || ai0 == bi1 || ai0 == bi2 || ai1 == bi0 || ai1 == bi1 || ai1 == bi2 ||
+                                ai2 == bi0 || ai2 == bi1 || ai2 == bi2;
+            if (!shared && aid != bid) {
+                float4 a0, a1, b0, b1;
+                ld256_nc(leaves + c.x, a0, a1);
+                ld256_nc(leaves + c.y, b0, b1);
+                const D3 av0 = {(double)a0.x, (double)a0.y, (double)a0.z}, av1 = {(double)a0.w, (double)a1.x, (double)a1.y},
+                         av2 = {(double)a1.z, (double)a1.w, (double)a2.x};
+                const D3 bv0 = {(double)b0.x, (double)b0.y, (double)b0.z}, bv1 = {(double)b0.w, (double)b1.x, (double)b1.y},
+                         bv2 = {(double)b1.z, (double)b1.w, (double)b2.x};
                 // tri_contact.cuh:81-86: P is the lower-ID triangle
-                if (a.id < b.id) { alive = sat_stage_a(sat_input(a.v0, a.v1, a.v2, b.v0, b.v1, b.v2)); entry = make_uint2(c.x, c.y); }
-                else             { alive = sat_stage_a(sat_input(b.v0, b.v1, b.v2, a.v0, a.v1, a.v2)); entry = make_uint2(c.y, c.x); }
+                if (aid < bid) { alive = sat_stage_a(sat_input(av0, av1, av2, bv0, bv1, bv2)); entry = make_uint2(c.x, c.y); }
+                else           { alive = sat_stage_a(sat_input(bv0, bv1, bv2, av0, av1, av2)); entry = make_uint2(c.y, c.x); }
             }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, alive);
@@ -496,19 +685,44 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
 
 }  // namespace
 
+// B200CD_TRAVERSAL=1: one query per thread; 2: persistent lanes (tuning knob, read once)
+static int traversal_variant() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("B200CD_TRAVERSAL");
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
+
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
                   uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries,
                   uint32_t* d_entry_count, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
                   cudaStream_t s) {
     if (nquery == 0 || n == 0 || (!foreign && n < 2)) return;
-    const uint32_t blocks = (nquery + BR_THREADS - 1) / BR_THREADS;
+    const bool persistent = traversal_variant() == 2 && !foreign;  // ghost queries (few, no tree over them) use the simple kernel
+    const uint32_t gsize = persistent ? BR_PER_WARP : BR_THREADS;  // consecutive queries per entry list
+    const uint32_t groups = (nquery + gsize - 1) / gsize;
     if (!foreign) {
-        entry_kernel<<<(blocks + 127) / 128, 128, 0, s>>>(d_pairs, d_root_box, n, shard, nshards, chunk, blocks, d_entries,
+        entry_kernel<<<(groups + 127) / 128, 128, 0, s>>>(d_pairs, d_root_box, n, shard, nshards, chunk, gsize, groups, d_entries,
                                                           d_entry_count);
         count_launch();
     }
-    broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery, foreign,
-                                               ghost_base, d_entries, d_entry_count, d_cand, cand_cap, d_counters);
+    if (persistent) {
+        const uint32_t blocks = (nquery + BR_QB - 1) / BR_QB;
+        static int refill = 0;
+        if (!refill) {
+            const char* e = getenv("B200CD_REFILL");
+            refill = e ? atoi(e) : BR_REFILL;
+            if (refill < 1 || refill > 32) refill = BR_REFILL;
+        }
+        broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill, d_entries,
+                                                   d_entry_count, d_cand, cand_cap, d_counters);
+    } else {
+        broad_kernel_simple<<<groups, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery,
+                                                          foreign, ghost_base, d_entries, d_entry_count, d_cand, cand_cap,
+                                                          d_counters);
+    }
     count_launch();
 }
 

@@ -9,7 +9,8 @@
 
 #define B200CD_MAX_STACK 96  // traversal stack entries per query (tree depth <= 60 key bits + tie-break)
 #define B200CD_QUERY_BLOCK 256  // consecutive sorted leaves per traversal block (query chunks are multiples of this)
-#define B200CD_MAX_ENTRIES 64   // start subtrees recorded per traversal block
+#define B200CD_QUERY_GROUP 128  // smallest run of consecutive sorted leaves that shares one list of start subtrees
+#define B200CD_MAX_ENTRIES 64   // start subtrees recorded per group
 #define B200CD_MAX_TRIS_LOG2 30 // at most 2^30 triangles / vertices per mesh
 
 namespace b200cd {
