@@ -323,7 +323,10 @@ def run_gpu_arm(args, workload):
     barrier()
     ev2.record()
     for _ in range(args.steps):
-        mesh.update_from_ptr(xyz_ptr, idx_ptr)            # b200cd_mesh_update: H2D of vertices + indices
+        if world == 1:
+            mesh.update_from_ptr(xyz_ptr, idx_ptr)        # b200cd_mesh_update: H2D of vertices + indices
+        else:                                             # 1/world of the mesh per PCIe link + NVLink all-gather
+            mgpu.upload_mesh_sharded(ctx, mesh, xyz_ptr, idx_ptr)
         if world == 1:
             ctx.bvh_rebuild(bvh, mesh, params)            # b200cd_bvh_rebuild
             cnt = ctx.self_collide_into(bvh, host_pairs.data_ptr(), host_pairs.numel(), sorted=True)  # + D2H

@@ -34,7 +34,7 @@ SYMBOLS = [
     "b200cd_select_ghosts_device", "b200cd_bvh_ghost_buffer", "b200cd_collide_ghosts_device",
     "b200cd_ipc_export", "b200cd_ipc_open", "b200cd_ipc_close", "b200cd_bvh_set_peers", "b200cd_partition_counts_device",
     "b200cd_partition_to_peers_device", "b200cd_send_ghosts_to_peers_device", "b200cd_ghost_counter_reset",
-    "b200cd_ghost_counter_read",
+    "b200cd_ghost_counter_read", "b200cd_mesh_update_slice", "b200cd_mesh_device_buffers",
 ]
 
 
@@ -138,6 +138,17 @@ class Mesh:
         self.ctx._chk(lib().b200cd_mesh_update(self.ctx.h, self.h, C.c_void_p(xyz_ptr or None),
                                                C.c_void_p(idx_ptr or None), C.c_int(1 if on_device else 0)),
                       "mesh_update")
+
+    def update_slice_from_ptr(self, xyz_ptr, first_vert, nverts, idx_ptr, first_tri, ntris):
+        """raw host pointers to the slice's first vertex / triangle"""
+        self.ctx._chk(lib().b200cd_mesh_update_slice(self.ctx.h, self.h, C.c_void_p(xyz_ptr or None), C.c_uint32(first_vert),
+                                                     C.c_uint32(nverts), C.c_void_p(idx_ptr or None), C.c_uint32(first_tri),
+                                                     C.c_uint32(ntris)), "mesh_update_slice")
+
+    def device_buffers(self):
+        v, i = C.c_void_p(), C.c_void_p()
+        self.ctx._chk(lib().b200cd_mesh_device_buffers(self.ctx.h, self.h, C.byref(v), C.byref(i)), "mesh_device_buffers")
+        return v.value, i.value
 
     def download(self):
         xyz = np.empty((self.nverts, 3), np.float32)

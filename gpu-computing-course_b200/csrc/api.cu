@@ -335,8 +335,9 @@ int new_mesh(b200cd_ctx* ctx, uint32_t nverts, uint32_t ntris, b200cd_mesh** out
     m->ctx = ctx;
     m->nverts = nverts;
     m->ntris = ntris;
-    int rc = dev_alloc(ctx, &m->d_verts, nverts);
-    if (rc == B200CD_OK) rc = dev_alloc(ctx, &m->d_idx, 3ull * ntris);
+    // + 16 elements of padding: a multi-GPU caller all-gathers equal chunks of ceil(n / ranks) in place
+    int rc = dev_alloc(ctx, &m->d_verts, (uint64_t)nverts + 16);
+    if (rc == B200CD_OK) rc = dev_alloc(ctx, &m->d_idx, 3ull * ((uint64_t)ntris + 16));
     if (rc != B200CD_OK) {
         cudaFree(m->d_verts);
         cudaFree(m->d_idx);
@@ -419,6 +420,43 @@ API int b200cd_mesh_update(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz,
     if (!ctx || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
     DeviceGuard g(ctx->device);
     return upload(ctx, mesh, xyz, tri_idx, on_device != 0, true);
+}
+
+// Partial upload for multi-GPU callers: every rank sends 1/ranks of the mesh over PCIe and the ranks
+// all-gather the device buffers over NVLink (b200cd_mesh_device_buffers), instead of every rank
+// pulling the whole mesh through the host.
+API int b200cd_mesh_update_slice(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, uint32_t first_vert, uint32_t nverts,
+                                 const uint32_t* tri_idx, uint32_t first_tri, uint32_t ntris) {
+    if (!ctx || !mesh || (nverts && !xyz) || (ntris && !tri_idx)) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if ((uint64_t)first_vert + nverts > mesh->nverts || (uint64_t)first_tri + ntris > mesh->ntris)
+        return set_error(ctx, B200CD_E_INVALID, "slice out of range");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    if (nverts && !mesh->d_stage) CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&mesh->d_stage), 12ull * mesh->nverts));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_U0], s));
+    if (nverts) {
+        CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_stage, xyz, 12ull * nverts, cudaMemcpyHostToDevice, s));
+        launch_expand_verts(mesh->d_stage, mesh->d_verts + first_vert, nverts, s);
+    }
+    if (ntris) {
+        CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_idx + 3ull * first_tri, tri_idx, 12ull * ntris, cudaMemcpyHostToDevice, s));
+        launch_check_idx(mesh->d_idx + 3ull * first_tri, ntris, mesh->nverts, ctx->d_scalars + 32, ctx->sm_count, s);
+        CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + 32, ctx->d_scalars + 32, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_U1], s));
+    CD_CUDA(ctx, cudaStreamSynchronize(s));
+    CD_CUDA(ctx, cudaGetLastError());
+    ctx->stats.ms_upload = ev_ms(ctx, EV_U0, EV_U1);
+    if (ntris && ctx->h_scalars[32]) return set_error(ctx, B200CD_E_INVALID, "triangle references a vertex index >= nverts");
+    return B200CD_OK;
+}
+
+// device views of the mesh: float4[nverts + 16] vertices (xyz, w = 0) and uint32[3 * (ntris + 16)] indices
+API int b200cd_mesh_device_buffers(b200cd_ctx* ctx, b200cd_mesh* mesh, void** d_verts4, void** d_idx) {
+    if (!ctx || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (d_verts4) *d_verts4 = mesh->d_verts;
+    if (d_idx) *d_idx = mesh->d_idx;
+    return B200CD_OK;
 }
 
 API int b200cd_mesh_info(const b200cd_mesh* mesh, uint32_t* nverts, uint32_t* ntris) {

@@ -498,3 +498,23 @@ def partitioned_self_collision_emulated(cd, ctx, mesh, params, world, slack=1.5)
     for p in ranks:
         p.bvh.destroy()
     return unpack_pairs(merged), stats
+
+
+def upload_mesh_sharded(ctx, mesh, xyz_host_ptr, idx_host_ptr, group=None):
+    """Host -> all ranks: every rank pushes 1/world of the mesh over its own PCIe link, then the ranks
+    all-gather the device buffers in place over NVLink (instead of world copies of the whole mesh
+    crossing the host). xyz_host_ptr / idx_host_ptr: the WHOLE mesh in (pinned) host memory of this rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", ctx.device)
+    V, N = mesh.nverts, mesh.ntris
+    cv, ct = (V + world - 1) // world, (N + world - 1) // world
+    v0, t0 = min(cv * rank, V), min(ct * rank, N)
+    nv, nt = min(cv, V - v0), min(ct, N - t0)
+    mesh.update_slice_from_ptr(xyz_host_ptr + 12 * v0, v0, nv, idx_host_ptr + 12 * t0, t0, nt)
+    dv, di = mesh.device_buffers()
+    verts = device_view(dv, 4 * cv * world, "<f4", dev)
+    idx = device_view(di, 3 * ct * world, "<i4", dev)
+    dist.all_gather_into_tensor(verts, verts[4 * cv * rank:4 * cv * (rank + 1)], group=group)
+    dist.all_gather_into_tensor(idx, idx[3 * ct * rank:3 * ct * (rank + 1)], group=group)
+    return 12 * nv + 12 * nt

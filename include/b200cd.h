@@ -161,6 +161,13 @@ int b200cd_mesh_from_device(b200cd_ctx* ctx, const void* d_xyz, uint32_t nverts,
  * the steady-state upload path (no allocation). */
 int b200cd_mesh_update(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, const uint32_t* tri_idx,
                        int on_device);
+/* Multi-GPU upload: overwrite only vertices [first_vert, +nverts) and triangles [first_tri, +ntris)
+ * from host memory; the ranks then all-gather b200cd_mesh_device_buffers over NVLink (the buffers
+ * carry 16 elements of padding so equal chunks of ceil(n / ranks) fit). */
+int b200cd_mesh_update_slice(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, uint32_t first_vert, uint32_t nverts,
+                             const uint32_t* tri_idx, uint32_t first_tri, uint32_t ntris);
+/* float4[nverts + 16] (xyz, w = 0) and uint32[3 * (ntris + 16)] on the context's GPU */
+int b200cd_mesh_device_buffers(b200cd_ctx* ctx, b200cd_mesh* mesh, void** d_verts4, void** d_idx);
 int b200cd_mesh_info(const b200cd_mesh* mesh, uint32_t* nverts, uint32_t* ntris);
 int b200cd_mesh_download(b200cd_ctx* ctx, const b200cd_mesh* mesh, float* xyz, uint32_t* tri_idx);
 int b200cd_mesh_destroy(b200cd_mesh* mesh);
