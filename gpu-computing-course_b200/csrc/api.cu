@@ -182,12 +182,13 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     }
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
     if (n) {
-        // K2: 8-bit digits over the significant key bits (60 of 63: morton.h:15 masks 21 bits
+        // K2: radix_digit_bits()-wide digits over the significant key bits (60 of 63: morton.h:15 masks 21 bits
         // per axis but the 2^20 scale leaves bit 20 clear for in-box meshes; we still sort all
         // 63 so out-of-box meshes order exactly like the host sort)
         RadixPass passes[8];
         const int total_bits = (p->key_bits == 30) ? 30 : 63;
-        for (int sh = 0; sh < total_bits; sh += 8) passes[npass++] = {sh, std::min(8, total_bits - sh)};
+        const int db = radix_digit_bits();
+        for (int sh = 0; sh < total_bits; sh += db) passes[npass++] = {sh, std::min(db, total_bits - sh)};
         b->cur = radix_sort(b->d_keys, b->d_ids, n, passes, npass, /*iota*/ !keys_given, b->d_hist, b->d_tile_status,
                             b->tile_status_words, ctx->sm_count, s);
     }
@@ -730,7 +731,7 @@ API int b200cd_partition_keys_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const voi
     radix_partition(static_cast<const uint64_t*>(d_keys), nullptr, first_id, static_cast<uint64_t*>(d_keys_out),
                     static_cast<uint32_t*>(d_ids_out), count, static_cast<const uint64_t*>(d_splitters), (int)nsplit, bvh->d_hist,
                     bvh->d_tile_status, ctx->sm_count, s);
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, bvh->d_hist + 256, sizeof(uint32_t) * (nsplit + 1), cudaMemcpyDeviceToHost, s));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, bvh->d_hist + (1 << radix_digit_bits()), sizeof(uint32_t) * (nsplit + 1), cudaMemcpyDeviceToHost, s));
     CD_CUDA(ctx, cudaStreamSynchronize(s));
     CD_CUDA(ctx, cudaGetLastError());
     for (uint32_t d = 0; d <= nsplit; ++d) counts_out[d] = ctx->h_scalars[d];
@@ -929,8 +930,9 @@ int sort_pairs_impl(b200cd_ctx* ctx, uint2** d_pairs, uint2** d_tmp, uint64_t co
     // memory word of a pair {lo_id, hi_id} read as u64 = hi_id << 32 | lo_id: LSD order = hi_id digits, then lo_id digits
     RadixPass passes[8];
     int np = 0;
-    for (int sh = 0; sh < id_bits; sh += 8) passes[np++] = {32 + sh, std::min(8, id_bits - sh)};
-    for (int sh = 0; sh < id_bits; sh += 8) passes[np++] = {sh, std::min(8, id_bits - sh)};
+    const int db = radix_digit_bits();
+    for (int sh = 0; sh < id_bits; sh += db) passes[np++] = {32 + sh, std::min(db, id_bits - sh)};
+    for (int sh = 0; sh < id_bits; sh += db) passes[np++] = {sh, std::min(db, id_bits - sh)};
     uint64_t need = radix_tile_status_words((uint32_t)count, np);
     if (need > *status_words) {
         cudaFree(*d_status);

@@ -196,6 +196,7 @@ void radix_partition_to_peers(const uint64_t* keys_in, uint32_t iota_base, uint3
                               const PeerTable* d_peers, const uint32_t* d_recv_offsets, uint32_t* d_hist,
                               uint32_t* d_tile_status, cudaStream_t s);
 uint64_t radix_tile_status_words(uint32_t n, int npass);
+int radix_digit_bits();  // digit width of one pass (status / histogram rows hold 1 << bits words)
 uint32_t radix_hist_words(int npass);
 // lbvh.cu
 uint32_t build_tree_pending_capacity(uint32_t n);

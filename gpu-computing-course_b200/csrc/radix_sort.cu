@@ -23,18 +23,30 @@
 
 namespace b200cd {
 
+#ifdef RS_PROFILE  // scratch builds only: cycles per phase of rs_pass, summed over tiles (thread 0)
+__device__ unsigned long long g_rs_prof[16];
+extern "C" __attribute__((visibility("default"))) void b200cd_debug_rs_prof(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, g_rs_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_rs_prof, z, sizeof z); }
+}
+#define RS_MARK(i) do { if (threadIdx.x == 0) { long long t__ = clock64(); atomicAdd(&g_rs_prof[i], (unsigned long long)(t__ - t_prev)); t_prev = t__; } } while (0)
+#else
+#define RS_MARK(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_IPT = 8;                     // items per thread
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 items per tile
-constexpr int RS_RADIX = 256;
+constexpr int RS_BITS = 8;                    // digit width (9 bits = 7 passes was measured slower: 1.51 vs 1.29 ms at 16 M)
+constexpr int RS_RADIX = 1 << RS_BITS;
 constexpr uint32_t ST_PARTIAL = 1u << 30;     // status word = flag | count  (count < 2^30)
 constexpr uint32_t ST_INCLUSIVE = 2u << 30;
 constexpr uint32_t ST_MASK = (1u << 30) - 1;
 constexpr int RS_MAX_PASS = 8;
-constexpr int RS_LOOKBACK = 4;                // predecessor status words fetched per look-back round
+constexpr int RS_LOOKBACK = 8;                // predecessor status words fetched per look-back round
 
 struct PassList {
     int npass;
@@ -169,7 +181,7 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         const uint32_t* __restrict__ digit_base_g,  // [256] exclusive global digit offsets of this pass
         uint32_t* __restrict__ status,              // [ntiles][256] look-back words of this pass
         uint32_t* __restrict__ ticket) {
-    // dynamic shared memory (> 48 KiB): [stage_k 32 KiB][stage_v 16 KiB if values][warp_hist][digit_base][warp_tot][tile]
+    // dynamic shared memory (> 48 KiB): [stage_k 32 KiB][stage_v 16 KiB if values][warp_hist][digit_base][warp_tot][tile][tile_hist]
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t* stage_k = reinterpret_cast<uint64_t*>(rs_smem);
     uint32_t* stage_v = reinterpret_cast<uint32_t*>(rs_smem + RS_TILE * 8);
@@ -180,9 +192,13 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
     uint32_t& s_tile = warp_tot[RS_RADIX / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef RS_PROFILE
+    long long t_prev = clock64();
+#endif
     const Digit<SPLIT> digit_of = make_digit<SPLIT>(shift, mask, splitters, nsplit);
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < RS_WARPS * (RS_RADIX + 1); i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+    if (tid < RS_RADIX) (warp_tot + RS_RADIX / 32 + 1)[tid] = 0;  // tile_hist
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t tile_base = tile * RS_TILE;
@@ -205,37 +221,24 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         }
     }
 
-    // warp-level multi-split: rank of every key among the warp's keys with the same digit
-    uint32_t rank[RS_IPT];
-    uint32_t* wh = warp_hist[warp];
-    const uint32_t lt = (1u << lane) - 1u;
+    RS_MARK(0);  // ticket + zero + issue loads
+    // ---- early counts (onesweep): the tile's digit histogram first, so that its PARTIAL status is out and its
+    // look-back is done BEFORE the (long) ranking. Tiles start in ticket order; with the inclusive prefixes
+    // published this early a tile rarely has to look further back than a few predecessors. (Ranking first
+    // - the previous version - delayed every tile's inclusive word by the ranking time and the look-back
+    // chains grew to the number of co-resident tiles: 15 us per tile, measured.)
+    uint32_t* tile_hist = warp_tot + RS_RADIX / 32 + 1;  // [RS_RADIX]
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
         const uint32_t g = my_base + 32 * k;
-        const uint32_t d = (g < n) ? digit_of(key[k]) : (uint32_t)RS_RADIX;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t prev = 0;
-        if ((int)lane == leader) {
-            prev = wh[d];
-            wh[d] = prev + __popc(peers);
-        }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[k] = prev + __popc(peers & lt);
-        __syncwarp();
+        if (g < n) atomicAdd(&tile_hist[digit_of(key[k])], 1u);
     }
     __syncthreads();
-
-    // per digit: exclusive prefix over warps, tile count, look-back
+    RS_MARK(1);  // keys arrive + tile histogram
     uint32_t sum = 0, excl = 0, incl = 0;
     if (tid < RS_RADIX) {
         const uint32_t d = tid;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const uint32_t c = warp_hist[w][d];
-            warp_hist[w][d] = sum;
-            sum += c;
-        }
+        sum = tile_hist[d];
         // publish this tile's count for digit d, then sum the counts of earlier tiles
         uint32_t* my_status = status + (size_t)tile * RS_RADIX + d;
         st_volatile(my_status, (tile == 0 ? ST_INCLUSIVE : ST_PARTIAL) | sum);
@@ -243,6 +246,9 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
             int t = (int)tile - 1;
             bool done = false;
             while (!done) {
+#ifdef RS_PROFILE
+                if (tid == 0) atomicAdd(&g_rs_prof[8], 1ull);  // look-back rounds
+#endif
                 // fetch several predecessors at once: their latencies overlap; consume in order
                 uint32_t sv[RS_LOOKBACK];
 #pragma unroll
@@ -251,7 +257,15 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
 #pragma unroll
                 for (int j = 0; j < RS_LOOKBACK; ++j) {
                     if (done) break;
-                    if ((sv[j] & ~ST_MASK) == 0) break;  // not published yet (tile is running: tickets are ordered) - refetch from here
+                    if ((sv[j] & ~ST_MASK) == 0) {  // not published yet (tile is running: tickets are ordered) - refetch from here
+#ifdef RS_PROFILE
+                        if (tid == 0) atomicAdd(&g_rs_prof[10], 1ull);  // rounds cut short by an unpublished predecessor
+#endif
+                        break;
+                    }
+#ifdef RS_PROFILE
+                    if (tid == 0) atomicAdd(&g_rs_prof[9], 1ull);  // predecessors consumed
+#endif
                     excl += sv[j] & ST_MASK;
                     --t;
                     if (sv[j] & ST_INCLUSIVE) done = true;
@@ -268,7 +282,40 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         }
         if (lane == 31) warp_tot[warp] = incl;
     }
+
+    RS_MARK(2);  // publish + look-back (thread 0's digit)
+    // ---- warp-level multi-split: rank of every key among the warp's keys with the same digit
+    uint32_t rank[RS_IPT];
+    uint32_t* wh = warp_hist[warp];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        const uint32_t g = my_base + 32 * k;
+        const uint32_t d = (g < n) ? digit_of(key[k]) : (uint32_t)RS_RADIX;
+        // lanes holding the same digit, from RS_BITS + 1 ballots (digit bits + "in range"). MATCH.ANY gives the same
+        // mask in one instruction but issues only about once per 130 cycles per SM sub-partition on B200
+        // (measured: 8.5 k of a tile's 30 k cycles went into 8 rounds of it).
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < RS_BITS + 1; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t vote = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? vote : ~vote;
+        }
+        const int leader = __ffs(peers) - 1;
+        uint32_t prev = 0;
+        if ((int)lane == leader) {
+            prev = wh[d];
+            wh[d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[k] = prev + __popc(peers & lt);
+        __syncwarp();
+    }
+    RS_MARK(3);  // ranking (warp 0)
     __syncthreads();
+    RS_MARK(4);  // wait for the other warps
+    // per digit: where the digit starts inside the tile, exclusive prefix over the warps
     if (tid < RS_RADIX) {
         const uint32_t d = tid;
         uint32_t wbase = 0;
@@ -277,11 +324,17 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         const uint32_t local_start = wbase + incl - sum;
         // final position of the item with in-tile slot r and digit d: digit_base[d] + r  (mod 2^32)
         digit_base[d] = __ldg(digit_base_g + d) + excl - local_start;
+        uint32_t run = local_start;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) warp_hist[w][d] += local_start;
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t c = warp_hist[w][d];
+            warp_hist[w][d] = run;
+            run += c;
+        }
     }
     __syncthreads();
 
+    RS_MARK(5);  // digit bases
     // stage keys (and values) in digit order
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
@@ -294,6 +347,7 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         }
     }
     __syncthreads();
+    RS_MARK(6);  // staging
     // write out: consecutive slots of one digit land on consecutive addresses
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
@@ -311,13 +365,16 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
             }
         }
     }
+    RS_MARK(7);  // write-out issue
 }
 
 constexpr size_t rs_smem_bytes(bool has_values) {
-    return (size_t)RS_TILE * 8 + (has_values ? (size_t)RS_TILE * 4 : 0) + sizeof(uint32_t) * (RS_WARPS * (RS_RADIX + 1) + RS_RADIX + RS_RADIX / 32 + 1);
+    return (size_t)RS_TILE * 8 + (has_values ? (size_t)RS_TILE * 4 : 0) + sizeof(uint32_t) * (RS_WARPS * (RS_RADIX + 1) + RS_RADIX + RS_RADIX / 32 + 1 + RS_RADIX);
 }
 
 }  // namespace
+
+int radix_digit_bits() { return RS_BITS; }
 
 uint32_t radix_hist_words(int npass) { return (uint32_t)(npass * RS_RADIX + RS_MAX_PASS); }  // + tickets
 
