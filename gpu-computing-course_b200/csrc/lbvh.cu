@@ -35,6 +35,17 @@
 
 namespace b200cd {
 
+#ifdef BT_PROFILE  // scratch builds only: cycles per phase of build_kernel (thread 0 of every block) / upper_kernel
+__device__ unsigned long long g_bt_prof[16];
+extern "C" __attribute__((visibility("default"))) void b200cd_debug_bt_prof(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, g_bt_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_bt_prof, z, sizeof z); }
+}
+#define BT_MARK(i) do { if (threadIdx.x == 0) { long long t__ = clock64(); atomicAdd(&g_bt_prof[i], (unsigned long long)(t__ - t_prev)); t_prev = t__; } } while (0)
+#else
+#define BT_MARK(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int BL = 256;  // sorted leaves per block
@@ -162,6 +173,9 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     const int B0 = blockIdx.x * BL;
     const int j = B0 + tid;
     const int Bend = min(B0 + BL, n) - 1;  // last leaf of this block
+#ifdef BT_PROFILE
+    long long t_prev = clock64();
+#endif
 
     // ---- leaf record + leaf box; similarities of the block's neighbours
     Carry c;
@@ -189,7 +203,9 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     }
     s_flag[tid] = 0;
     if (tid == 0) s_npend = 0;
+    BT_MARK(0);  // gathers + leaf record + similarities (thread 0)
     __syncthreads();
+    BT_MARK(1);  // wait for the block
 
     // ---- climb inside the block: splits s with both neighbours in the block, B0 <= s < Bend
     bool pending = false;  // holding a subtree whose parent split lies outside the block's shared-memory range
@@ -220,15 +236,21 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
                 if (old == 0u) break;  // first arrival: the deposit stays for the sibling
                 __threadfence_block();
                 const float4 sa = s_dep[ls][side ^ 1][0], sb = s_dep[ls][side ^ 1][1];
-                // both halves are here: write the finished node once (left child, right child)
-                st256(&pairs[s].c[side], a, b);
-                st256(&pairs[s].c[side ^ 1], sa, sb);
+                // both halves of node s now sit in s_dep[ls]: the finished nodes of the block are written out
+                // together after the climb (global stores inside this loop would make every fence wait for them)
                 merge_with(c, side, sa, sb, s);
             }
         }
     }
+    BT_MARK(2);  // shared-memory climb (thread 0)
     __syncthreads();
-
+    BT_MARK(3);  // wait for the block's longest climb
+    // ---- finished nodes (both children arrived in shared memory): pairs[B0 ...] is one contiguous run,
+    // written with full 32-byte sectors, two threads per node
+    for (int i = tid; i < 2 * (BL - 1); i += BL) {
+        const int ls = i >> 1, half = i & 1;
+        if (B0 + ls < Bend && s_flag[ls] == 3u) st256(&pairs[B0 + ls].c[half], s_dep[ls][half][0], s_dep[ls][half][1]);
+    }
     // ---- leftovers are parked for upper_kernel: (1) my own subtree if its parent split lies outside the
     // block, (2) split B0+tid if only one child arrived (the sibling reaches beyond the block)
     uint32_t f = 0;
@@ -240,6 +262,10 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     __syncthreads();
     if (tid == 0 && s_npend) s_base = atomicAdd(list_count, s_npend);
     __syncthreads();
+    BT_MARK(4);  // pending-list reservation
+#ifdef BT_PROFILE
+    if (tid == 0) atomicAdd(&g_bt_prof[8], (unsigned long long)s_npend);
+#endif
     if (!mine) return;
     at += s_base;
     if (pending) {
