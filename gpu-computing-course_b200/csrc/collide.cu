@@ -628,7 +628,7 @@ __device__ __forceinline__ void narrow_stage_b(const LeafRec* __restrict__ leave
 // So: stage A (filters + 2 axes) runs dense over the candidate list, its survivors are
 // compacted into a per-warp shared-memory queue by ballot, and stage B (15 axes) runs whenever
 // 32 survivors are waiting - both stages execute with (nearly) full warps.
-__global__ void __launch_bounds__(NR_THREADS, 2)
+__global__ void __launch_bounds__(NR_THREADS, 3)
 narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand, uint64_t cand_cap,
               uint2* __restrict__ out, uint64_t out_cap, unsigned long long* __restrict__ counters) {
     __shared__ uint2 queue[NR_WARPS][NR_QUEUE];
@@ -728,7 +728,7 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
 
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s) {
-    narrow_kernel<<<sms * 2 * 4, NR_THREADS, 0, s>>>(d_leaves, d_cand, cand_cap, d_out, out_cap, d_counters);
+    narrow_kernel<<<sms * 3 * 4, NR_THREADS, 0, s>>>(d_leaves, d_cand, cand_cap, d_out, out_cap, d_counters);
     count_launch();
 }
 

@@ -1,0 +1,45 @@
+"""torchrun --nproc-per-node N tests/run_multigpu_check.py  (needs N >= 2 B200s; not collected by pytest)
+
+Checks on real GPUs that the partitioned build (peer-memory and NCCL variants) and the sharded upload give
+exactly the replicated / single-GPU pair list."""
+import importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    del os.environ["NCCL_DEBUG"]
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); lr = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+cd = importlib.import_module("gpu-computing-course_b200.binding")
+mg = importlib.import_module("gpu-computing-course_b200.meshgen")
+mgpu = importlib.import_module("gpu-computing-course_b200.multigpu")
+ctx = cd.Context(lr)
+for name, (xyz, idx), box in (("soup4m", mg.soup(1 << 22, seed=5), ((0,0,0),(1,1,1))), ("sheets1024", mg.two_sheets(1024), ((0,0,0),(1,1,1))),
+                              ("cloth", mg.cloth_fold(500, 500), None)):
+    p = cd.make_params(*box) if box else cd.default_params()
+    mesh = ctx.mesh_from_arrays(np.zeros_like(xyz), np.zeros_like(idx))
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    xyz = np.ascontiguousarray(xyz, np.float32); idx = np.ascontiguousarray(idx, np.uint32)
+    mgpu.upload_mesh_sharded(ctx, mesh, xyz.ctypes.data, idx.ctypes.data)
+    torch.cuda.synchronize()
+    x2, i2 = mesh.download()
+    assert np.array_equal(x2, xyz) and np.array_equal(i2, idx), "sharded upload mismatch"
+    if rank == 0: print(name, "sharded upload OK", flush=True)
+    bvh = ctx.bvh_build(mesh, p)
+    sh = mgpu.ShardedSelfCollision(cd, ctx)
+    ref = sh.step(bvh, mesh, p)
+    ref_np = mgpu.unpack_pairs(ref) if rank == 0 else None
+    for pm in (True, False):
+        pr = mgpu.PartitionedSelfCollision(cd, ctx, mesh, p, peer_memory=pm)
+        for it in range(3):
+            got = pr.step()
+            if rank == 0:
+                g = mgpu.unpack_pairs(got)
+                ok = np.array_equal(g, ref_np)
+                print(name, "peer_memory" if pm else "nccl", "iter", it, "pairs", len(g), "ref", len(ref_np), "OK" if ok else "MISMATCH", pr.stats, flush=True)
+                assert ok
+        torch.cuda.synchronize(); dist.barrier()
+        pr.close(); pr.part.bvh.destroy()
+    bvh.destroy(); mesh.destroy()
+dist.barrier()
+dist.destroy_process_group()
