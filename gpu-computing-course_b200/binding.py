@@ -35,6 +35,7 @@ SYMBOLS = [
     "b200cd_ipc_export", "b200cd_ipc_open", "b200cd_ipc_close", "b200cd_bvh_set_peers", "b200cd_partition_counts_device",
     "b200cd_partition_to_peers_device", "b200cd_send_ghosts_to_peers_device", "b200cd_ghost_counter_reset",
     "b200cd_ghost_counter_read", "b200cd_mesh_update_slice", "b200cd_mesh_device_buffers",
+    "b200cd_obj_parse_host", "b200cd_host_array_free",
 ]
 
 
@@ -112,6 +113,23 @@ def make_params(origin=None, extent=None, key_bits=63, auto_box=False, pair_capa
 
 def _ptr(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def parse_obj(path):
+    """The library's OBJ parser on its own (host only; reference dialect, load_obj.h:24-103).
+    -> (xyz float32 [V,3], idx uint32 [N,3]); raises B200cdError(E_IO / E_PARSE) with the line number."""
+    xyz_p, idx_p = C.POINTER(C.c_float)(), C.POINTER(C.c_uint32)()
+    nv, nt = C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(256)
+    rc = lib().b200cd_obj_parse_host(os.fsencode(path), C.byref(xyz_p), C.byref(nv), C.byref(idx_p), C.byref(nt), err,
+                                     C.c_uint64(256))
+    if rc != OK:
+        raise B200cdError(rc, "obj_parse", err.value.decode(errors="replace"))
+    xyz = np.ctypeslib.as_array(xyz_p, shape=(max(nv.value, 1), 3))[:nv.value].copy()
+    idx = np.ctypeslib.as_array(idx_p, shape=(max(nt.value, 1), 3))[:nt.value].copy()
+    lib().b200cd_host_array_free(xyz_p)
+    lib().b200cd_host_array_free(idx_p)
+    return xyz, idx
 
 
 class Mesh:

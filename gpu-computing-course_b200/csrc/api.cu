@@ -494,52 +494,52 @@ API int b200cd_mesh_destroy(b200cd_mesh* mesh) {
     return B200CD_OK;
 }
 
-// OBJ ingest with the reference parser's dialect (load_obj.h:41-103).
+// OBJ ingest with the reference parser's dialect (load_obj.h:24-103); the parser itself is obj_parse.cu.
 API int b200cd_mesh_load_obj(b200cd_ctx* ctx, const char* path, b200cd_mesh** out) {
     if (!ctx || !path || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
     *out = nullptr;
-    FILE* fp = fopen(path, "rb");
-    if (!fp) return set_error(ctx, B200CD_E_IO, std::string("cannot open ") + path);  // load_obj.h:31-35
-    std::vector<char> text;
-    {
-        char chunk[1 << 16];
-        size_t got;
-        while ((got = fread(chunk, 1, sizeof chunk, fp)) > 0) text.insert(text.end(), chunk, chunk + got);
-        bool bad = ferror(fp) != 0;
-        fclose(fp);
-        if (bad) return set_error(ctx, B200CD_E_IO, std::string("read error on ") + path);
-    }
     std::vector<float> xyz;
     std::vector<uint32_t> idx;
-    size_t pos = 0, line_no = 0;
-    char buffer[256];
-    while (pos < text.size()) {
-        const char* nl = static_cast<const char*>(memchr(text.data() + pos, '\n', text.size() - pos));
-        if (!nl) break;  // last line without '\n' is dropped: load_obj.h:41 tests eof() after getline
-        size_t len = (size_t)(nl - (text.data() + pos));
-        ++line_no;
-        if (len >= 255)  // getline(buffer, 255) would set failbit and the reference never terminates
-            return set_error(ctx, B200CD_E_PARSE, "line " + std::to_string(line_no) + ": longer than 254 characters");
-        memcpy(buffer, text.data() + pos, len);
-        buffer[len] = '\0';
-        pos += len + 1;
-        if (buffer[0] == 'v' && buffer[1] == ' ') {  // load_obj.h:48-61
-            float f1, f2, f3;
-            if (sscanf(buffer, "v %f %f %f", &f1, &f2, &f3) != 3)
-                return set_error(ctx, B200CD_E_PARSE, "line " + std::to_string(line_no) + ": vertex not in 'v x y z' format");
-            xyz.push_back(f1); xyz.push_back(f2); xyz.push_back(f3);
-        } else if (buffer[0] == 'f' && buffer[1] == ' ') {  // load_obj.h:64-102
-            int v1, v2, v3, t1, t2, t3;
-            if (sscanf(buffer, "f %d/%d %d/%d %d/%d", &v1, &t1, &v2, &t2, &v3, &t3) != 6)
-                return set_error(ctx, B200CD_E_PARSE, "line " + std::to_string(line_no) + ": face not in 'f v/vt v/vt v/vt' format");
-            const int v_size = (int)(xyz.size() / 3) + 1;  // load_obj.h:76-79; faces must follow their vertices (:89)
-            if (v1 < 1 || v2 < 1 || v3 < 1 || v1 >= v_size || v2 >= v_size || v3 >= v_size)
-                return set_error(ctx, B200CD_E_PARSE, "line " + std::to_string(line_no) + ": face references a vertex not yet defined");
-            idx.push_back((uint32_t)(v1 - 1)); idx.push_back((uint32_t)(v2 - 1)); idx.push_back((uint32_t)(v3 - 1));
-        }
-    }
+    std::string err;
+    const int rc = obj_parse(path, xyz, idx, err);
+    if (rc != B200CD_OK) return set_error(ctx, rc, err);
     return b200cd_mesh_from_arrays(ctx, xyz.data(), (uint32_t)(xyz.size() / 3), idx.data(), (uint32_t)(idx.size() / 3), out);
 }
+
+// The same parser without a GPU: host arrays out (malloc'ed; release with b200cd_host_array_free).
+API int b200cd_obj_parse_host(const char* path, float** xyz_out, uint32_t* nverts_out, uint32_t** idx_out, uint32_t* ntris_out,
+                              char* err_out, uint64_t err_len) {
+    if (!path || !xyz_out || !nverts_out || !idx_out || !ntris_out) return B200CD_E_INVALID;
+    *xyz_out = nullptr;
+    *idx_out = nullptr;
+    *nverts_out = *ntris_out = 0;
+    std::vector<float> xyz;
+    std::vector<uint32_t> idx;
+    std::string err;
+    const int rc = obj_parse(path, xyz, idx, err);
+    if (err_out && err_len) {
+        const size_t k = std::min<size_t>(err.size(), (size_t)err_len - 1);
+        memcpy(err_out, err.data(), k);
+        err_out[k] = '\0';
+    }
+    if (rc != B200CD_OK) return rc;
+    float* x = static_cast<float*>(malloc(std::max<size_t>(xyz.size(), 1) * sizeof(float)));
+    uint32_t* t = static_cast<uint32_t*>(malloc(std::max<size_t>(idx.size(), 1) * sizeof(uint32_t)));
+    if (!x || !t) {
+        free(x);
+        free(t);
+        return B200CD_E_NOMEM;
+    }
+    if (!xyz.empty()) memcpy(x, xyz.data(), xyz.size() * sizeof(float));
+    if (!idx.empty()) memcpy(t, idx.data(), idx.size() * sizeof(uint32_t));
+    *xyz_out = x;
+    *idx_out = t;
+    *nverts_out = (uint32_t)(xyz.size() / 3);
+    *ntris_out = (uint32_t)(idx.size() / 3);
+    return B200CD_OK;
+}
+
+API void b200cd_host_array_free(void* p) { free(p); }
 
 // ------------------------------------------------------------------ build
 

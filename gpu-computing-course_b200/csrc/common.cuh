@@ -159,6 +159,12 @@ inline int set_error(b200cd_ctx* ctx, int code, const std::string& msg) {
                                      std::string(#expr) + ": " + cudaGetErrorString(e__));         \
     } while (0)
 
+// obj_parse.cu: multi-threaded host parser of the reference's OBJ dialect; returns a B200CD_* status
+}  // namespace b200cd
+#include <vector>
+namespace b200cd {
+int obj_parse(const char* path, std::vector<float>& xyz, std::vector<uint32_t>& idx, std::string& err);
+
 // kernels' host launchers (each enqueues on `s`, no synchronisation)
 // morton.cu
 void launch_expand_verts(const float* d_xyz, float4* d_verts, uint32_t nverts, cudaStream_t s);

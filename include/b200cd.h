@@ -148,6 +148,13 @@ int b200cd_host_free(void* p);
  * B200CD_E_PARSE instead of exit()/undefined behaviour. */
 int b200cd_mesh_load_obj(b200cd_ctx* ctx, const char* path, b200cd_mesh** out);
 
+/* The parser behind b200cd_mesh_load_obj on its own (host only, multi-threaded, no GPU needed):
+ * *xyz_out = nverts*3 floats, *idx_out = ntris*3 0-based indices, both malloc'ed - release with
+ * b200cd_host_array_free. err_out (optional) receives "line N: ..." on B200CD_E_PARSE / B200CD_E_IO. */
+int b200cd_obj_parse_host(const char* path, float** xyz_out, uint32_t* nverts_out, uint32_t** idx_out, uint32_t* ntris_out,
+                          char* err_out, uint64_t err_len);
+void b200cd_host_array_free(void* p);
+
 /* Array twin of the above: xyz = nverts*3 floats, tri_idx = ntris*3 0-based
  * indices, triangle ID = array order. Host pointers. */
 int b200cd_mesh_from_arrays(b200cd_ctx* ctx, const float* xyz, uint32_t nverts,

@@ -66,3 +66,21 @@ def test_obj_loader_quirks_and_errors(cd, ctx, tmp_path):
     with pytest.raises(cd.B200cdError) as e:
         ctx.mesh_load_obj(os.path.join(tmp_path, "missing.obj"))
     assert e.value.status == cd.E_IO
+
+
+def test_cli_prints_the_reference_output_format(cd, co, mg, tmp_path, capsys):
+    """python gpu-computing-course_b200/cli.py mesh.obj prints main.cu:147-154's lines: count, %07u pairs, ID set"""
+    import importlib
+    cli = importlib.import_module("gpu-computing-course_b200.cli")
+    g = np.load(os.path.join(GOLDEN, "cloth_20x20.npz"))
+    path = os.path.join(tmp_path, "cloth.obj")
+    mg.write_obj(path, g["xyz"], g["idx"])
+    assert cli.main([path, "--validate"]) == 0
+    out = capsys.readouterr().out
+    assert f"- contact val = {len(g['pairs'])}" in out
+    printed = [tuple(int(x) for x in l.split(" - ")) for l in out.splitlines() if " - " in l and l[:7].isdigit()]
+    assert printed == [tuple(p) for p in g["pairs"].tolist()]
+    ids = sorted(set(g["pairs"].reshape(-1).tolist()))
+    tail = out.split("points in total")[1].splitlines()[1:1 + len(ids)]
+    assert [int(t) for t in tail] == ids
+    assert "nullParentnum = 1, wrongBoundCount=0, nullChildCount=0" in out
