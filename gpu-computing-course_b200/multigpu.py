@@ -90,7 +90,7 @@ def gather_pairs(local, dst=0, group=None):
     cnt = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
     counts_t = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(counts_t, cnt, group=group)
-    counts = [int(c.item()) for c in counts_t]
+    counts = torch.cat(counts_t).cpu().tolist()  # one device -> host read for all ranks' counts
     if world == 1:
         return local, counts
     ops = []
@@ -214,6 +214,8 @@ class PartitionedRank:
         csum = torch.cumsum(global_hist.to(torch.int64), 0)
         targets = (torch.arange(1, self.world, device=self.dev, dtype=torch.int64) * csum[-1]) // self.world
         bins = torch.searchsorted(csum, targets)                     # first bin whose cumulative count reaches the target
+        bins = torch.clamp(bins, max=65534)                          # (keys beyond the histogram's range share the last bin)
+        self.split_bins = bins                                       # rank r owns the bins (bins[r-1], bins[r]]
         self.splitters = ((bins + 1) << self.shift).contiguous()     # keys >= splitter r-1 belong to rank >= r
         return self.splitters
 
@@ -366,10 +368,14 @@ class PartitionedSelfCollision:
         mark("start")
         ctx.ghost_counter_reset(p.bvh)
         hist = p.keys_and_histogram()
+        local_csum = torch.cumsum(hist, 0, dtype=torch.int64)  # my own keys per top-bits bin, before the all-reduce
         dist.all_reduce(hist, group=g)  # also orders every rank's counter reset before any ghost append of this step
         mark("keys+hist+allreduce")
         splitters = p.splitters_from(hist)
-        ctx.partition_counts_device(p.keys.data_ptr(), p.cnt, splitters.data_ptr(), w - 1, self._counts_dev.data_ptr())
+        # the splitters sit on bin boundaries, so how many of MY keys each rank owns follows from my own
+        # histogram - no second pass over the keys
+        bounds = torch.cat([local_csum[p.split_bins], local_csum[-1:]])
+        self._counts_dev = torch.diff(bounds, prepend=bounds.new_zeros(1)).to(torch.int32).contiguous()
         allc = torch.empty(w * w, dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(allc, self._counts_dev, group=g)
         allc = allc.view(w, w)                                         # [source rank][owner rank]
