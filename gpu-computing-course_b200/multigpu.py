@@ -332,21 +332,42 @@ class PartitionedSelfCollision:
         self.peer_memory = bool(peer_memory) and self.world > 1
         self._mapped = []
         if self.peer_memory:
-            handles, offsets = ctx.ipc_export(self.part.bvh)
+            # every rank must end up in the same mode: if CUDA IPC is unavailable anywhere (e.g. a container
+            # without the needed permissions) all ranks fall back to the NCCL send/recv exchange
+            ok, err = 1, ""
+            try:
+                handles, offsets = ctx.ipc_export(self.part.bvh)
+            except Exception as e:  # noqa: BLE001
+                ok, err, handles, offsets = 0, str(e), b"", []
             everyone = [None] * self.world
-            dist.all_gather_object(everyone, (handles, offsets), group=group)
+            dist.all_gather_object(everyone, (ok, handles, offsets), group=group)
+            ok = int(all(e[0] for e in everyone))
             peers = [0] * (4 * self.world)
-            for r, (h, off) in enumerate(everyone):
-                if r == self.rank:
-                    continue
-                for i in range(4):
-                    base = ctx.ipc_open(h[64 * i:64 * i + 64])
-                    self._mapped.append(base)
-                    peers[4 * r + i] = base + off[i]
-            ctx.bvh_set_peers(self.part.bvh, self.world, self.rank, peers)
-            self._counts_dev = torch.zeros(self.world, dtype=torch.int32, device=self.device)
-            self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
-            dist.barrier(group=group)
+            if ok:
+                try:
+                    for r, (_, h, off) in enumerate(everyone):
+                        if r == self.rank:
+                            continue
+                        for i in range(4):
+                            base = ctx.ipc_open(h[64 * i:64 * i + 64])
+                            self._mapped.append(base)
+                            peers[4 * r + i] = base + off[i]
+                    ctx.bvh_set_peers(self.part.bvh, self.world, self.rank, peers)
+                except Exception as e:  # noqa: BLE001
+                    ok, err = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                if self.rank == 0:
+                    import sys
+                    print(f"[b200cd] CUDA IPC peer memory unavailable ({err or 'on another rank'}): using NCCL send/recv",
+                          file=sys.stderr)
+                self.close()
+                self.peer_memory = False
+            else:
+                self._counts_dev = torch.zeros(self.world, dtype=torch.int32, device=self.device)
+                self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+                dist.barrier(group=group)
 
     def _barrier(self):
         dist.all_reduce(self._token, group=self.group)  # stream-ordered: everybody's preceding kernels have finished
@@ -380,11 +401,12 @@ class PartitionedSelfCollision:
         dist.all_gather_into_tensor(allc, self._counts_dev, group=g)
         allc = allc.view(w, w)                                         # [source rank][owner rank]
         recv_off = allc[:r].sum(0, dtype=torch.int32).contiguous()     # my segment's start in every owner's buffer
-        nlocal_t = allc[:, r].sum()
+        totals_t = allc.sum(0)
         ctx.partition_to_peers_device(p.bvh, p.keys.data_ptr(), p.lo, p.cnt, splitters.data_ptr(), w - 1, recv_off.data_ptr())
-        p.nlocal = int(nlocal_t.item())
-        if p.nlocal > p.cap:
-            raise RuntimeError(f"rank {r}: {p.nlocal} triangles in my Morton range, capacity {p.cap}")
+        totals = totals_t.tolist()                                     # (every rank sees every range's size: all raise together)
+        p.nlocal = int(totals[r])
+        if max(totals) > p.cap:
+            raise RuntimeError(f"a Morton range holds {max(totals)} triangles, capacity {p.cap}: raise slack (very uneven mesh)")
         self._barrier()                                                # all (key, id) stores have landed
         mark("partition+exchange (fused)")
         boxes = p.build()
@@ -432,6 +454,9 @@ class PartitionedSelfCollision:
         counts, pieces = p.partition(hist)
         mark("partition")
         allc = _all_counts(counts, self.device, g) if w > 1 else [counts]
+        biggest = max(sum(allc[src][dst] for src in range(w)) for dst in range(w))
+        if biggest > p.cap:  # same decision on every rank
+            raise RuntimeError(f"a Morton range holds {biggest} triangles, capacity {p.cap}: raise slack (very uneven mesh)")
         views = p.key_recv_views([allc[src][r] for src in range(w)])
         if w > 1:
             _exchange_wait(_exchange_start(r, w, [[k for k, _ in pieces], [i for _, i in pieces]],
