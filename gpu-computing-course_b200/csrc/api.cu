@@ -272,6 +272,9 @@ API int b200cd_destroy(b200cd_ctx* ctx) {
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaFree(ctx->d_scalars);
+    cudaFree(ctx->d_sort_tmp);
+    cudaFree(ctx->d_sort_hist);
+    cudaFree(ctx->d_sort_status);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     delete ctx;
     return B200CD_OK;
@@ -1165,22 +1168,20 @@ API int b200cd_sort_pairs_device(b200cd_ctx* ctx, void* d_pairs, uint64_t count,
     if (count < 2) return B200CD_OK;
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->stream;
-    uint2* tmp = nullptr;
-    uint32_t* hist = nullptr;
-    uint32_t* status = nullptr;
-    uint64_t status_words = 0;
-    CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&tmp), count * sizeof(uint2)));
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&hist), radix_hist_words(8) * sizeof(uint32_t));
-    int rc = B200CD_OK;
-    if (e != cudaSuccess) rc = set_error(ctx, B200CD_E_NOMEM, "cudaMalloc failed");
+    // scratch lives in the context and only grows: this call sits inside every multi-GPU step.
+    // Asynchronous: the sorted list is valid in stream order.
+    if (ctx->sort_tmp_cap < count) {
+        cudaFree(ctx->d_sort_tmp);
+        ctx->d_sort_tmp = nullptr;
+        ctx->sort_tmp_cap = 0;
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_sort_tmp), (count + count / 4) * sizeof(uint2)));
+        ctx->sort_tmp_cap = count + count / 4;
+    }
+    if (!ctx->d_sort_hist) CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_sort_hist), radix_hist_words(8) * sizeof(uint32_t)));
     uint2* p = static_cast<uint2*>(d_pairs);
-    uint2* q = tmp;
-    if (rc == B200CD_OK) rc = sort_pairs_impl(ctx, &p, &q, count, (int)id_bits, &hist, &status, &status_words, s);
+    uint2* q = ctx->d_sort_tmp;
+    int rc = sort_pairs_impl(ctx, &p, &q, count, (int)id_bits, &ctx->d_sort_hist, &ctx->d_sort_status, &ctx->sort_status_words, s);
     if (rc == B200CD_OK && p != d_pairs)  // result landed in the temporary: copy back in place
         if (cudaMemcpyAsync(d_pairs, p, count * sizeof(uint2), cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = B200CD_E_CUDA;
-    cudaStreamSynchronize(s);
-    cudaFree(tmp);
-    cudaFree(hist);
-    cudaFree(status);
     return rc;
 }

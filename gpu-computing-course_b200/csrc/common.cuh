@@ -61,6 +61,10 @@ struct b200cd_ctx {
     // scratch shared by builds/queries on this context
     uint32_t* d_scalars = nullptr;   // small device scratch (counters, flags, bbox)
     uint32_t* h_scalars = nullptr;   // pinned mirror
+    // scratch of b200cd_sort_pairs_device (grow-only)
+    uint2* d_sort_tmp = nullptr;  uint64_t sort_tmp_cap = 0;
+    uint32_t* d_sort_hist = nullptr;
+    uint32_t* d_sort_status = nullptr;  uint64_t sort_status_words = 0;
 };
 
 struct b200cd_mesh {

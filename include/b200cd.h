@@ -232,7 +232,7 @@ int b200cd_self_collide_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t shard,
 
 /* Lexicographic sort of a device-resident pair list (e.g. after gathering the
  * per-rank lists on rank 0). id_bits = number of significant bits in a triangle
- * ID (0 = 32). In place. */
+ * ID (0 = 32). In place; asynchronous on the context's stream. */
 int b200cd_sort_pairs_device(b200cd_ctx* ctx, void* d_pairs, uint64_t count, uint32_t id_bits);
 
 /* Device views for replicating a built BVH to other ranks (NCCL broadcast is
