@@ -70,17 +70,19 @@ def generate(mg, name, out=None):
     return getattr(mg, kind)(**kw, out=out)
 
 
-def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes):
+def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes, recs=True):
     """Compulsory HBM bytes per stage for OUR data layout, each array read or
-    written once per pass. n triangles, nverts vertices."""
+    written once per pass. n triangles, nverts vertices. recs: K1 also writes the face-ordered 64 B leaf
+    records and the tree build moves those (single-GPU full builds) instead of gathering indices + vertices."""
     return {
-        # K1: 12 B indices + one 16 B float4 per vertex (each vertex is read at least once) + 8 B key out
-        "morton": 12 * n + 16 * nverts + 8 * n,
+        # K1: 12 B indices + one 16 B float4 per vertex (each vertex is read at least once) + 8 B key out (+ 64 B record)
+        "morton": 12 * n + 16 * nverts + 8 * n + (64 * n if recs else 0),
         # K2: histogram reads the keys once; every pass reads and writes (8 B key + 4 B id)
         #     (first pass generates the ids: no 4 B read)
-        "sort": 8 * n + sort_passes * 24 * n - 4 * n,
+        #     hybrid sort (< 8 passes): the fix-up reads the keys once more
+        "sort": 8 * n + sort_passes * 24 * n - 4 * n + (8 * n if sort_passes < 8 else 0),
         # K3+K4 (fused): sorted ids + keys + indices + vertices in, 64 B leaf record + 64 B node pair out
-        "tree": 4 * n + 8 * n + 12 * n + 16 * nverts + 64 * n + 64 * n,
+        "tree": 4 * n + 8 * n + (64 * n if recs else 12 * n + 16 * nverts) + 64 * n + 64 * n,
         # K5: every node pair (64 B) and every query record (64 B) once, 8 B per candidate out
         "traverse": 64 * n + 64 * n + 8 * ncand,
         # K6: candidate in, two 64 B leaf records per candidate, 8 B per pair out
@@ -88,7 +90,7 @@ def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes):
     }
 
 
-STAGE_KERNEL = {"morton": "morton_kernel", "sort": "rs_pass (x passes) + rs_histogram", "tree": "build_kernel (+ upper_kernel)",
+STAGE_KERNEL = {"morton": "morton_kernel", "sort": "rs_pass (x passes) + rs_histogram + rs_fixup", "tree": "build_kernel (+ upper_kernel)",
                 "traverse": "broad_kernel (+ entry_kernel)", "narrow": "narrow_kernel"}
 
 
@@ -317,35 +319,67 @@ def run_gpu_arm(args, workload):
     launches = ctx.stats()["kernel_launches"] - launches0
 
     # ---- timed region 2: end to end through the host-buffer calls
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # every step: H2D of that step's mesh from pinned host memory, build, query, D2H of the sorted pair list
     h2d = 12 * nverts + 12 * ntris
     d2h = 0
-    barrier()
-    ev2.record()
-    for _ in range(args.steps):
+
+    def e2e_serial_step():
+        nonlocal merged, d2h
         if world == 1:
             mesh.update_from_ptr(xyz_ptr, idx_ptr)        # b200cd_mesh_update: H2D of vertices + indices
-        else:                                             # 1/world of the mesh per PCIe link + NVLink all-gather
-            mgpu.upload_mesh_sharded(ctx, mesh, xyz_ptr, idx_ptr)
-        if world == 1:
             ctx.bvh_rebuild(bvh, mesh, params)            # b200cd_bvh_rebuild
             cnt = ctx.self_collide_into(bvh, host_pairs.data_ptr(), host_pairs.numel(), sorted=True)  # + D2H
             d2h = 8 * cnt
-        else:
+        else:                                             # 1/world of the mesh per PCIe link + NVLink all-gather
+            mgpu.upload_mesh_sharded(ctx, mesh, xyz_ptr, idx_ptr)
             merged = runner.step(bvh, mesh, params)
             if rank == 0:
                 host_pairs[: merged.numel()].copy_(merged, non_blocking=True)
                 d2h = 8 * int(merged.numel())
             torch.cuda.current_stream().synchronize()
+
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev2.record()
+    for _ in range(args.steps):
+        e2e_serial_step()
     ev3.record()
     barrier()
-    ms_e2e = ev2.elapsed_time(ev3)
+    ms_e2e_serial = ev2.elapsed_time(ev3)
+    ms_e2e = ms_e2e_serial
+    e2e_mode = "serial calls: b200cd_mesh_update, b200cd_bvh_rebuild, b200cd_self_collide (one frame at a time)"
+    if world == 1:
+        # double-buffered frames (b200cd_mesh_update_async / b200cd_mesh_wait): the H2D of frame k+1 runs on the
+        # copy stream while frame k is built and queried from the other mesh object. Still one H2D of the whole
+        # mesh and one D2H of the pair list per step, all inside the timed region.
+        frames = [mesh, ctx.mesh_from_host_ptr(xyz_ptr, nverts, idx_ptr, ntris)]
+        for k in range(2):                                # warm-up: allocates the second staging buffer, events, copy stream
+            frames[k].update_async_from_ptr(xyz_ptr, idx_ptr)
+            frames[k].wait()
+        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev4.record()
+        frames[0].update_async_from_ptr(xyz_ptr, idx_ptr)
+        for k in range(args.steps):
+            cur = frames[k % 2]
+            if k + 1 < args.steps:
+                frames[(k + 1) % 2].update_async_from_ptr(xyz_ptr, idx_ptr)
+            cur.wait()
+            ctx.bvh_rebuild(bvh, cur, params)
+            cnt = ctx.self_collide_into(bvh, host_pairs.data_ptr(), host_pairs.numel(), sorted=True)
+            d2h = 8 * cnt
+        ev5.record()
+        barrier()
+        ms_e2e = ev4.elapsed_time(ev5)
+        e2e_mode = ("double-buffered frames: b200cd_mesh_update_async of frame k+1 overlaps b200cd_bvh_rebuild + "
+                    "b200cd_self_collide of frame k; one full H2D and one D2H per step inside the timed region")
+        frames[1].destroy()
 
     # ---- max over ranks
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_e2e_serial], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    ms_total, ms_e2e, ms_e2e_serial = float(t[0]), float(t[1]), float(t[2])
 
     if partitioned:
         prunner.step(profile=True)  # one extra, untimed step (all ranks) with a synchronise after every phase
@@ -361,10 +395,11 @@ def run_gpu_arm(args, workload):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         ncand, npairs = int(last.get("candidates", 0)), int(last.get("pairs", 0))
-        abytes = algorithmic_bytes(ntris, nverts, ncand, npairs, int(last.get("sort_passes", 8)))
-        if partitioned:  # rank 0's own Morton range
+        recs = os.environ.get("B200CD_RECS", "1") != "0"
+        abytes = algorithmic_bytes(ntris, nverts, ncand, npairs, int(last.get("sort_passes", 8)), recs)
+        if partitioned:  # rank 0's own Morton range (keys arrive from the exchange: no face-ordered records)
             nloc = int(prunner.stats.get("local_triangles", ntris // world))
-            abytes = algorithmic_bytes(nloc, min(nverts, 3 * nloc), ncand, npairs, int(last.get("sort_passes", 8)))
+            abytes = algorithmic_bytes(nloc, min(nverts, 3 * nloc), ncand, npairs, int(last.get("sort_passes", 8)), False)
         elif world > 1:  # per-rank share of the query stages
             abytes["traverse"] = 64 * ntris + 64 * ntris // world + 8 * ncand
         stages = {}
@@ -410,7 +445,10 @@ def run_gpu_arm(args, workload):
                        "l2_policy": "inputs larger than L2 (mesh + BVH >> 126 MB); no explicit flush"},
             "bvh_build_ms": round(acc["ms_build"] / K, 4), "query_ms": round(acc["ms_query"] / K, 4),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(ms_e2e / K, 4)},
+                    "ms_per_step": round(ms_e2e / K, 4), "mode": e2e_mode,
+                    "serial_value": round(ntris / (ms_e2e_serial / K) / 1e3, 2),
+                    "serial_ms_per_step": round(ms_e2e_serial / K, 4),
+                    "h2d_gbs": round(h2d / (ms_e2e / K * 1e-3) / 1e9, 1)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "traversal": traversal,
         }
         if partitioned:

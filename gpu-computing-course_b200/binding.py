@@ -35,7 +35,7 @@ SYMBOLS = [
     "b200cd_ipc_export", "b200cd_ipc_open", "b200cd_ipc_close", "b200cd_bvh_set_peers", "b200cd_partition_counts_device",
     "b200cd_partition_to_peers_device", "b200cd_send_ghosts_to_peers_device", "b200cd_ghost_counter_reset",
     "b200cd_ghost_counter_read", "b200cd_mesh_update_slice", "b200cd_mesh_device_buffers",
-    "b200cd_obj_parse_host", "b200cd_host_array_free",
+    "b200cd_obj_parse_host", "b200cd_host_array_free", "b200cd_mesh_update_async", "b200cd_mesh_wait",
 ]
 
 
@@ -156,6 +156,16 @@ class Mesh:
         self.ctx._chk(lib().b200cd_mesh_update(self.ctx.h, self.h, C.c_void_p(xyz_ptr or None),
                                                C.c_void_p(idx_ptr or None), C.c_int(1 if on_device else 0)),
                       "mesh_update")
+
+    def update_async_from_ptr(self, xyz_ptr, idx_ptr):
+        """enqueue the upload on the context's copy stream and return; the (pinned) host buffers must stay valid
+        until wait(). Double-buffered frames: upload mesh B while mesh A is being built / queried."""
+        self.ctx._chk(lib().b200cd_mesh_update_async(self.ctx.h, self.h, C.c_void_p(xyz_ptr or None),
+                                                     C.c_void_p(idx_ptr or None)), "mesh_update_async")
+
+    def wait(self):
+        """block until a pending asynchronous upload has landed (and raise if its index check failed)"""
+        self.ctx._chk(lib().b200cd_mesh_wait(self.ctx.h, self.h), "mesh_wait")
 
     def update_slice_from_ptr(self, xyz_ptr, first_vert, nverts, idx_ptr, first_tri, ntris):
         """raw host pointers to the slice's first vertex / triangle"""

@@ -81,10 +81,14 @@ void free_bvh_buffers(b200cd_bvh* b) {
     }
     cudaFree(b->d_hist);
     cudaFree(b->d_tile_status);
+    cudaFree(b->d_fix);
+    if (b->h_fix) cudaFreeHost(b->h_fix);
+    if (b->ev_fix) cudaEventDestroy(b->ev_fix);
     cudaFree(b->d_flags);
     cudaFree(b->d_build_scratch);
     cudaFree(b->d_pairs);
     cudaFree(b->d_leaves);
+    cudaFree(b->d_recs);
     cudaFree(b->d_ghost_out);
     cudaFree(b->d_cut_scratch);
     cudaFree(b->d_peers);
@@ -131,6 +135,12 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
     b->tile_status_words = radix_tile_status_words(std::max<uint32_t>(n, 1u), 8);
     A(dev_alloc(ctx, &b->d_hist, radix_hist_words(8)));
     A(dev_alloc(ctx, &b->d_tile_status, b->tile_status_words));
+    if (with_sort) {
+        A(dev_alloc(ctx, &b->d_fix, 4));
+        if (rc == B200CD_OK && (cudaMallocHost(reinterpret_cast<void**>(&b->h_fix), 4 * sizeof(uint32_t)) != cudaSuccess ||
+                                cudaEventCreateWithFlags(&b->ev_fix, cudaEventDisableTiming) != cudaSuccess))
+            rc = set_error(ctx, B200CD_E_NOMEM, "cudaMallocHost failed");
+    }
     A(dev_alloc(ctx, &b->d_pairs, n));
     A(dev_alloc(ctx, &b->d_leaves, (uint64_t)n + ghost_cap));  // ghost records of a partitioned build live after the local leaves
     if (max_peers) {
@@ -153,6 +163,34 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
     return B200CD_OK;
 }
 
+// The last kernel that reads the mesh's device arrays has been enqueued on `s`: an asynchronous
+// upload into the same mesh (b200cd_mesh_update_async, on the copy stream) must not start before it.
+cudaError_t mark_consumed(const b200cd_mesh* cm, cudaStream_t s) {
+    b200cd_mesh* m = const_cast<b200cd_mesh*>(cm);
+    if (!m->ev_consumed) return cudaSuccess;  // never uploaded asynchronously: nothing can race
+    m->consumed_valid = true;
+    return cudaEventRecord(m->ev_consumed, s);
+}
+
+bool leaf_records_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200CD_RECS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// B200CD_SORT=full: always run every radix pass (tuning / A-B knob, read once)
+bool sort_hybrid_disabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200CD_SORT");
+        v = (e && e[0] == 'f') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 int check_params(b200cd_ctx* ctx, const b200cd_params* p) {
     if (!p) return set_error(ctx, B200CD_E_INVALID, "params is NULL");
     if (p->key_bits != 63 && p->key_bits != 30) return set_error(ctx, B200CD_E_INVALID, "key_bits must be 63 or 30");
@@ -167,6 +205,7 @@ int check_params(b200cd_ctx* ctx, const b200cd_params* p) {
 int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd_params* p, bool keys_given = false) {
     cudaStream_t s = ctx->stream;
     const uint32_t n = b->n;
+    if (m->pending) return set_error(ctx, B200CD_E_INVALID, "mesh has an asynchronous upload in flight: call b200cd_mesh_wait first");
     b->params = *p;
     b->built = false;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
@@ -178,7 +217,13 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
             d_bbox = ctx->d_scalars;
             launch_bbox(m->d_verts, m->nverts, d_bbox, ctx->sm_count, s);
         }
-        launch_morton(m->d_verts, m->d_idx, 0, n, *p, d_bbox, b->d_keys[0], s);
+        // face-ordered leaf records for the tree build (64 B per triangle, allocated on first use; B200CD_RECS=0 turns
+        // them off - tuning / A-B knob). Without them the build gathers indices and vertices itself.
+        if (!b->d_recs && leaf_records_enabled() && cudaMalloc(reinterpret_cast<void**>(&b->d_recs), sizeof(LeafRec) * (size_t)n) != cudaSuccess) {
+            cudaGetLastError();
+            b->d_recs = nullptr;  // not enough memory: the gather path needs none
+        }
+        launch_morton(m->d_verts, m->d_idx, 0, n, *p, d_bbox, b->d_keys[0], s, b->d_recs);
     }
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
     if (n) {
@@ -189,14 +234,37 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
         const int total_bits = (p->key_bits == 30) ? 30 : 63;
         const int db = radix_digit_bits();
         for (int sh = 0; sh < total_bits; sh += db) passes[npass++] = {sh, std::min(db, total_bits - sh)};
+        // Hybrid sort for 63-bit keys: radix passes over the top b->sort_high digits only, the low bits are put in
+        // order by a per-run fix-up (radix_sort.cu). The previous build's run statistics steer sort_high.
+        int high = 0;
+        if (npass == 8 && b->d_fix && !sort_hybrid_disabled()) {
+            if (b->fix_pending && cudaEventQuery(b->ev_fix) == cudaSuccess) {
+                b->fix_pending = false;
+                const uint32_t overflow = b->h_fix[0], longest = b->h_fix[1], in_runs = b->h_fix[2];
+                if (overflow || longest > 24) {           // prefix too short for this mesh: sort more digits, for good
+                    b->sort_high = overflow ? 8 : std::min(8, b->sort_high + 1);
+                    b->sort_locked = true;
+                } else if (!b->sort_locked && b->sort_high > 4 && longest <= 3 && (uint64_t)in_runs * 1024 < n) {
+                    --b->sort_high;                       // one digit less multiplies the occupancy of a cell by 256
+                }
+            }
+            high = b->sort_high < 8 ? b->sort_high : 0;
+        }
         b->cur = radix_sort(b->d_keys, b->d_ids, n, passes, npass, /*iota*/ !keys_given, b->d_hist, b->d_tile_status,
-                            b->tile_status_words, ctx->sm_count, s);
+                            b->tile_status_words, ctx->sm_count, s, high, b->d_fix);
+        if (high) {
+            CD_CUDA(ctx, cudaMemcpyAsync(b->h_fix, b->d_fix, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CD_CUDA(ctx, cudaEventRecord(b->ev_fix, s));
+            b->fix_pending = true;
+            npass = high;
+        }
     }
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));  // (K3 is fused into K4: ms_hierarchy stays ~0)
     launch_build_tree(m->d_verts, m->d_idx, b->d_ids[b->cur], b->d_keys[b->cur], n, b->d_flags, b->d_pairs, b->d_leaves,
-                      b->d_root_box, b->d_build_scratch, s);  // K3+K4
+                      b->d_root_box, b->d_build_scratch, s, keys_given ? nullptr : b->d_recs);  // K3+K4
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
+    CD_CUDA(ctx, mark_consumed(m, s));  // nothing after this point reads the mesh
     CD_CUDA(ctx, cudaGetLastError());
     b->id_space = keys_given ? m->ntris : n;
     b->npairs = 0;
@@ -268,6 +336,10 @@ API int b200cd_destroy(b200cd_ctx* ctx) {
     if (ctx->own_stream) {
         cudaStreamSynchronize(ctx->own_stream);
         cudaStreamDestroy(ctx->own_stream);
+    }
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
     }
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -356,6 +428,7 @@ int new_mesh(b200cd_ctx* ctx, uint32_t nverts, uint32_t ntris, b200cd_mesh** out
 // one-shot uploads (mesh_from_arrays / load_obj) give it back.
 int upload(b200cd_ctx* ctx, b200cd_mesh* m, const float* xyz, const uint32_t* idx, bool on_device, bool keep_stage) {
     cudaStream_t s = ctx->stream;
+    if (m->pending) return set_error(ctx, B200CD_E_INVALID, "mesh has an asynchronous upload in flight: call b200cd_mesh_wait first");
     if (xyz && m->nverts && !on_device && !m->d_stage)
         CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&m->d_stage), 12ull * m->nverts));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_U0], s));
@@ -426,6 +499,53 @@ API int b200cd_mesh_update(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz,
     return upload(ctx, mesh, xyz, tri_idx, on_device != 0, true);
 }
 
+// Double-buffered frames: the upload of frame k+1 (H2D, float3 -> float4 expansion, index check) runs on the
+// context's copy stream while the work stream builds and queries frame k from ANOTHER mesh object.
+// Ordering: the copy waits for the last kernel that read this mesh (ev_consumed); users of the mesh call
+// b200cd_mesh_wait, which blocks the host until the upload has landed and reports the index check.
+API int b200cd_mesh_update_async(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, const uint32_t* tri_idx) {
+    if (!ctx || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (mesh->pending) return set_error(ctx, B200CD_E_INVALID, "mesh already has an asynchronous upload in flight");
+    DeviceGuard g(ctx->device);
+    if (!ctx->copy_stream) CD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!mesh->ev_ready) {
+        CD_CUDA(ctx, cudaEventCreateWithFlags(&mesh->ev_ready, cudaEventDisableTiming));
+        CD_CUDA(ctx, cudaEventCreateWithFlags(&mesh->ev_consumed, cudaEventDisableTiming));
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&mesh->d_async_flag), sizeof(uint32_t)));
+        CD_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&mesh->h_async_flag), sizeof(uint32_t)));
+        // work enqueued on the work stream before this call may still be reading the mesh
+        CD_CUDA(ctx, mark_consumed(mesh, ctx->stream));
+    }
+    if (xyz && mesh->nverts && !mesh->d_stage)
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&mesh->d_stage), 12ull * mesh->nverts));
+    cudaStream_t c = ctx->copy_stream;
+    if (mesh->consumed_valid) CD_CUDA(ctx, cudaStreamWaitEvent(c, mesh->ev_consumed, 0));
+    if (xyz && mesh->nverts) {
+        CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_stage, xyz, 12ull * mesh->nverts, cudaMemcpyHostToDevice, c));
+        launch_expand_verts(mesh->d_stage, mesh->d_verts, mesh->nverts, c);
+    }
+    *mesh->h_async_flag = 0;
+    if (tri_idx && mesh->ntris) {
+        CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_idx, tri_idx, 12ull * mesh->ntris, cudaMemcpyHostToDevice, c));
+        launch_check_idx(mesh->d_idx, mesh->ntris, mesh->nverts, mesh->d_async_flag, ctx->sm_count, c);
+        CD_CUDA(ctx, cudaMemcpyAsync(mesh->h_async_flag, mesh->d_async_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c));
+    }
+    CD_CUDA(ctx, cudaEventRecord(mesh->ev_ready, c));
+    CD_CUDA(ctx, cudaGetLastError());
+    mesh->pending = true;
+    return B200CD_OK;
+}
+
+API int b200cd_mesh_wait(b200cd_ctx* ctx, b200cd_mesh* mesh) {
+    if (!ctx || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (!mesh->pending) return B200CD_OK;
+    DeviceGuard g(ctx->device);
+    CD_CUDA(ctx, cudaEventSynchronize(mesh->ev_ready));  // the caller's host buffers are free again from here on
+    mesh->pending = false;
+    if (*mesh->h_async_flag) return set_error(ctx, B200CD_E_INVALID, "triangle references a vertex index >= nverts");
+    return B200CD_OK;
+}
+
 // Partial upload for multi-GPU callers: every rank sends 1/ranks of the mesh over PCIe and the ranks
 // all-gather the device buffers over NVLink (b200cd_mesh_device_buffers), instead of every rank
 // pulling the whole mesh through the host.
@@ -490,6 +610,13 @@ API int b200cd_mesh_destroy(b200cd_mesh* mesh) {
     if (!mesh) return B200CD_OK;
     DeviceGuard g(mesh->ctx->device);
     cudaStreamSynchronize(mesh->ctx->stream);
+    if (mesh->ev_ready) {
+        cudaEventSynchronize(mesh->ev_ready);
+        cudaEventDestroy(mesh->ev_ready);
+        cudaEventDestroy(mesh->ev_consumed);
+        cudaFree(mesh->d_async_flag);
+        cudaFreeHost(mesh->h_async_flag);
+    }
     cudaFree(mesh->d_verts);
     cudaFree(mesh->d_idx);
     cudaFree(mesh->d_stage);
@@ -577,6 +704,7 @@ API int b200cd_bvh_rebuild(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* 
 API int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* mesh) {
     if (!ctx || !bvh || !mesh) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
     if (!bvh->built || bvh->n != mesh->ntris || !bvh->d_keys[0]) return set_error(ctx, B200CD_E_INVALID, "BVH not built for this mesh");
+    if (mesh->pending) return set_error(ctx, B200CD_E_INVALID, "mesh has an asynchronous upload in flight: call b200cd_mesh_wait first");
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->stream;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
@@ -587,6 +715,7 @@ API int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* me
     launch_build_tree(mesh->d_verts, mesh->d_idx, bvh->d_ids[bvh->cur], bvh->d_keys[bvh->cur], bvh->n, bvh->d_flags,
                       bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, bvh->d_build_scratch, s);
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
+    CD_CUDA(ctx, mark_consumed(mesh, s));
     CD_CUDA(ctx, cudaGetLastError());
     ctx->stats.ms_build = -1.f;
     ctx->stats.sort_passes = 0;
@@ -686,7 +815,9 @@ API int b200cd_morton_keys_device(b200cd_ctx* ctx, const b200cd_mesh* mesh, cons
     if (params->auto_box) return set_error(ctx, B200CD_E_INVALID, "auto_box is not available for a partitioned build: pass the box");
     if ((uint64_t)first + count > mesh->ntris) return set_error(ctx, B200CD_E_INVALID, "triangle slice out of range");
     DeviceGuard g(ctx->device);
+    if (mesh->pending) return set_error(ctx, B200CD_E_INVALID, "mesh has an asynchronous upload in flight: call b200cd_mesh_wait first");
     launch_morton(mesh->d_verts, mesh->d_idx, first, count, *params, nullptr, static_cast<uint64_t*>(d_keys_out), ctx->stream);
+    CD_CUDA(ctx, mark_consumed(mesh, ctx->stream));
     CD_CUDA(ctx, cudaGetLastError());
     return B200CD_OK;
 }

@@ -187,7 +187,8 @@ constexpr int BR_REFILL = 16;                          // refill when this many 
 constexpr int BR_KEEP = 32;                            // start subtrees kept per group after the union-box filter
 constexpr int BR_CQ = 128;                             // candidate staging per warp: < 64 carried + <= 64 new per step
 
-__global__ void __launch_bounds__(BR_THREADS)
+template <int MIN_BLOCKS>  // resident CTAs per SM the register allocation is bounded for (6 -> 40 registers, 48 warps)
+__global__ void __launch_bounds__(BR_THREADS, MIN_BLOCKS)
 broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, uint32_t n, uint32_t shard,
              uint32_t nshards, uint32_t chunk, uint32_t nquery, uint32_t ngroups, int refill, const Node32* __restrict__ entries,
              const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand, uint64_t cand_cap,
@@ -232,7 +233,7 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
 
     int stack[B200CD_MAX_STACK];
     int sp = 0;
-    bool overflow = false;
+    uint32_t overflow = 0;  // a word, not a bool: nvcc packs bools into byte lanes and re-packs them (PRMT) on every path
 
     auto flush = [&]() {
         unsigned long long base = 0;
@@ -304,11 +305,14 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
                 if (!spilled) c = s_entry[g][e];
                 else ld256_nc(entries + (size_t)eb * BR_ENTRIES + e, c.a, c.b);
                 const bool hit = take && c.ext() > q && overlap(qlo, qhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y);
-                const int link = c.link();
-                if (hit && link >= 0) {
-                    if (sp < B200CD_MAX_STACK) stack[sp++] = link; else overflow = true;
+                const int link = c.link();  // the same entry for every lane: the branch below is warp-uniform
+                if (link >= 0) {
+                    if (hit) {
+                        if (sp < B200CD_MAX_STACK) stack[sp++] = link; else overflow = 1;
+                    }
+                } else {
+                    stage2((uint32_t)q, hit, ~link, false, 0);  // a start subtree that is a single leaf (rare)
                 }
-                stage2((uint32_t)q, hit && link < 0, ~link, false, 0);
             }
             if (take) node = sp > 0 ? stack[--sp] : -1;
             continue;
@@ -331,7 +335,7 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
             if (goL) {
                 node = linkL;
                 if (goR) {
-                    if (sp < B200CD_MAX_STACK) stack[sp++] = linkR; else overflow = true;
+                    if (sp < B200CD_MAX_STACK) stack[sp++] = linkR; else overflow = 1;
                 }
             } else if (goR) {
                 node = linkR;
@@ -716,8 +720,17 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
             refill = e ? atoi(e) : BR_REFILL;
             if (refill < 1 || refill > 32) refill = BR_REFILL;
         }
-        broad_kernel<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill, d_entries,
-                                                   d_entry_count, d_cand, cand_cap, d_counters);
+        static int occ = 0;  // B200CD_BROAD_OCC=5: the 48-register build (5 CTAs per SM); default 6 CTAs per SM
+        if (!occ) {
+            const char* e = getenv("B200CD_BROAD_OCC");
+            occ = (e && e[0] == '5') ? 5 : 6;
+        }
+        if (occ == 5)
+            broad_kernel<5><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
+                                                          d_entries, d_entry_count, d_cand, cand_cap, d_counters);
+        else
+            broad_kernel<6><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
+                                                          d_entries, d_entry_count, d_cand, cand_cap, d_counters);
     } else {
         broad_kernel_simple<<<groups, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery,
                                                           foreign, ghost_base, d_entries, d_entry_count, d_cand, cand_cap,

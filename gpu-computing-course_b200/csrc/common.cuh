@@ -54,6 +54,7 @@ struct b200cd_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // b200cd_mesh_update_async: uploads that overlap the build / query of another mesh
     int sm_count = 148;
     b200cd_stats stats{};
     std::string last_error;
@@ -73,6 +74,13 @@ struct b200cd_mesh {
     float4* d_verts = nullptr;   // nverts float4 (xyz, w = 0)
     uint32_t* d_idx = nullptr;   // ntris * 3
     float* d_stage = nullptr;    // nverts * 3: H2D landing area of b200cd_mesh_update (kept between frames)
+    // asynchronous upload (b200cd_mesh_update_async / b200cd_mesh_wait)
+    cudaEvent_t ev_ready = nullptr;     // recorded on the copy stream after the upload's last operation
+    cudaEvent_t ev_consumed = nullptr;  // recorded on the work stream after the last kernel that read this mesh
+    uint32_t* d_async_flag = nullptr;   // index check of the pending upload (device word + pinned mirror)
+    uint32_t* h_async_flag = nullptr;
+    bool pending = false;               // an asynchronous upload has been enqueued and not yet waited for
+    bool consumed_valid = false;
 };
 
 namespace b200cd {
@@ -99,11 +107,19 @@ struct b200cd_bvh {
     uint32_t* d_hist = nullptr;        // radix histograms / digit bases
     uint32_t* d_tile_status = nullptr; // decoupled look-back words
     uint64_t tile_status_words = 0;
+    // hybrid sort (radix_sort.cu): radix passes over the key bits >= 64 - 8 * sort_high only, per-run fix-up below
+    uint32_t* d_fix = nullptr;         // [0] fallback ran, [1] longest run of equal high bits, [2] items in runs >= 2
+    uint32_t* h_fix = nullptr;         // pinned copy, read by the NEXT build to adapt sort_high
+    cudaEvent_t ev_fix = nullptr;      // the copy above has landed
+    bool fix_pending = false;
+    int sort_high = 5;                 // digits sorted by radix passes (8 = plain full sort)
+    bool sort_locked = false;          // a longer prefix was needed once: never try a shorter one again
     // hierarchy
     uint32_t* d_flags = nullptr;       // n-1 arrival counters of the splits merged through global memory
     void* d_build_scratch = nullptr;   // pending-subtree list of the tree build (lbvh.cu)
     b200cd::NodePair* d_pairs = nullptr;  // n-1
     b200cd::LeafRec* d_leaves = nullptr;  // n
+    b200cd::LeafRec* d_recs = nullptr;    // n, face order: written by K1, moved into sorted order by the tree build (full builds only)
     float* d_root_box = nullptr;       // 6 floats + [6] = index of the root node (int)
     // query
     b200cd::Node32* d_entries = nullptr;  // [blocks][B200CD_MAX_ENTRIES] traversal start subtrees
@@ -174,15 +190,19 @@ int obj_parse(const char* path, std::vector<float>& xyz, std::vector<uint32_t>& 
 void launch_expand_verts(const float* d_xyz, float4* d_verts, uint32_t nverts, cudaStream_t s);
 void launch_check_idx(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, uint32_t* d_flag, int sms, cudaStream_t s);
 void launch_bbox(const float4* d_verts, uint32_t nverts, uint32_t* d_bbox6 /*ordered-uint min3,max3*/, int sms, cudaStream_t s);
+// d_recs (optional): also write every triangle's LeafRec, in face order (slice-relative like d_keys)
 void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t first, uint32_t n, const b200cd_params& p,
-                   const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s);
+                   const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s, LeafRec* d_recs = nullptr);
 // radix_sort.cu
 struct RadixPass { int shift; int bits; };
 // sorts n (key,value) items; values may be null (keys only); if iota_values the
 // first pass generates value = index. Result lands in buffer index returned.
+// high_passes > 0 (with d_fix, 4 device words): hybrid sort - only the top `high_passes` digits are sorted with
+// radix passes, the low bits by a per-run fix-up (radix_sort.cu, rs_fixup); needs an EVEN npass.
+// d_fix afterwards: [0] the fallback (all passes) ran, [1] longest run of equal high bits, [2] items in runs >= 2.
 int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
                bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words,
-               int sms, cudaStream_t s);
+               int sms, cudaStream_t s, int high_passes = 0, uint32_t* d_fix = nullptr);
 // stable range partition (multi-GPU): bucket = number of device-resident splitters <= key; needs
 // d_hist >= 2*256+1 words and d_tile_status >= radix_tile_status_words(n, 1); counts land in d_hist[256..]
 void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t iota_base, uint64_t* keys_out,
@@ -211,9 +231,11 @@ uint32_t radix_hist_words(int npass);
 // lbvh.cu
 uint32_t build_tree_pending_capacity(uint32_t n);
 uint64_t build_tree_scratch_bytes(uint32_t n);
+// d_recs (optional): face-ordered leaf records from launch_morton - the leaves are then copied from there
+// (one 64-byte gather per leaf) instead of being assembled from d_idx / d_verts
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
-                       void* d_scratch, cudaStream_t s);
+                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs = nullptr);
 // d_scratch: 2 * (2n-1) words
 void launch_export_nodes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t* d_scratch,
                          b200cd_node32* d_nodes_out, cudaStream_t s);

@@ -160,11 +160,12 @@ upper_kernel(const Pending* __restrict__ list, const uint32_t* __restrict__ list
     climb_global(c, p.side >= 0, p.slot, p.side, keys, n, flags, pairs, root_box);
 }
 
+template <bool RECS>  // leaf records come from the face-ordered copies K1 wrote (recs) instead of idx / verts
 __global__ void __launch_bounds__(BL)
 build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ sorted_ids,
              const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
              LeafRec* __restrict__ leaves, float* __restrict__ root_box, Pending* __restrict__ list,
-             uint32_t* __restrict__ list_count, uint32_t capacity) {
+             uint32_t* __restrict__ list_count, uint32_t capacity, const LeafRec* __restrict__ recs) {
     __shared__ int s_sim[BL + 1];          // s_sim[i] = similarity of sorted positions (B0-1+i, B0+i); -1 outside
     __shared__ uint32_t s_flag[BL];        // per split B0+i: bit 0 = left child arrived, bit 1 = right child arrived
     __shared__ float4 s_dep[BL][2][2];     // per split, per side: the child's Node32 (ext as in pairs[])
@@ -182,13 +183,23 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     uint64_t kj = 0;
     if (j < n) {
         const uint32_t id = __ldg(sorted_ids + j);
-        const uint32_t* f = idx + 3ull * id;
-        const uint32_t i0 = __ldg(f), i1 = __ldg(f + 1), i2 = __ldg(f + 2);
-        const float4 a = __ldg(verts + i0), b = __ldg(verts + i1), d = __ldg(verts + i2);
+        float4 a, b, d;
         float4* rec = reinterpret_cast<float4*>(leaves + j);
-        st256(rec, make_float4(a.x, a.y, a.z, b.x), make_float4(b.y, b.z, d.x, d.y));
-        st256(rec + 2, make_float4(d.z, __uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2)),
-              make_float4(__uint_as_float(id), 0.f, 0.f, 0.f));
+        if (RECS) {
+            float4 r0, r1, r2, r3;
+            ld256_nc(recs + id, r0, r1);
+            ld256_nc(reinterpret_cast<const float4*>(recs + id) + 2, r2, r3);
+            st256(rec, r0, r1);
+            st256(rec + 2, r2, r3);
+            a = make_float4(r0.x, r0.y, r0.z, 0.f); b = make_float4(r0.w, r1.x, r1.y, 0.f); d = make_float4(r1.z, r1.w, r2.x, 0.f);
+        } else {
+            const uint32_t* f = idx + 3ull * id;
+            const uint32_t i0 = __ldg(f), i1 = __ldg(f + 1), i2 = __ldg(f + 2);
+            a = __ldg(verts + i0); b = __ldg(verts + i1); d = __ldg(verts + i2);
+            st256(rec, make_float4(a.x, a.y, a.z, b.x), make_float4(b.y, b.z, d.x, d.y));
+            st256(rec + 2, make_float4(d.z, __uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2)),
+                  make_float4(__uint_as_float(id), 0.f, 0.f, 0.f));
+        }
         // box.cuh:13-22
         c.lo[0] = min3_ref(a.x, b.x, d.x); c.lo[1] = min3_ref(a.y, b.y, d.y); c.lo[2] = min3_ref(a.z, b.z, d.z);
         c.hi[0] = max3_ref(a.x, b.x, d.x); c.hi[1] = max3_ref(a.y, b.y, d.y); c.hi[2] = max3_ref(a.z, b.z, d.z);
@@ -429,15 +440,19 @@ uint32_t build_tree_pending_capacity(uint32_t n) { return n / 8 + 4096; }
 
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
-                       void* d_scratch, cudaStream_t s) {
+                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs) {
     if (!n) return;
     uint32_t* list_count = static_cast<uint32_t*>(d_scratch);
     Pending* list = reinterpret_cast<Pending*>(static_cast<char*>(d_scratch) + 16);
     const uint32_t capacity = build_tree_pending_capacity(n);
     if (n > 1) cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (size_t)(n - 1), s);
     cudaMemsetAsync(list_count, 0, sizeof(uint32_t), s);
-    build_kernel<<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs, d_leaves,
-                                                  d_root_box, list, list_count, capacity);
+    if (d_recs)
+        build_kernel<true><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs, d_leaves,
+                                                            d_root_box, list, list_count, capacity, d_recs);
+    else
+        build_kernel<false><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs,
+                                                             d_leaves, d_root_box, list, list_count, capacity, nullptr);
     count_launch();
     {
         upper_kernel<<<(capacity + 127) / 128, 128, 0, s>>>(list, list_count, capacity, d_keys, (int)n, d_flags, d_pairs,

@@ -113,9 +113,17 @@ __global__ void __launch_bounds__(RH_THREADS) rs_histogram_split(const uint64_t*
     if (threadIdx.x <= RS_MAX_SPLIT && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
+// cond (optional): device word; the kernel does nothing when it is 0 (fallback path of the hybrid sort, below).
+// clear / clear_words: status words to zero first (grid-stride) - only the conditional launch uses it.
 __global__ void __launch_bounds__(RH_THREADS) rs_histogram(const uint64_t* __restrict__ keys, uint32_t n,
-                                                           PassList pl, uint32_t* __restrict__ hist) {
+                                                           PassList pl, uint32_t* __restrict__ hist,
+                                                           const uint32_t* __restrict__ cond, uint4* __restrict__ clear,
+                                                           uint64_t clear_vec) {
     __shared__ uint32_t sh[RS_MAX_PASS * RS_RADIX];
+    if (cond && *cond == 0) return;
+    if (clear)
+        for (uint64_t i = (uint64_t)blockIdx.x * RH_THREADS + threadIdx.x; i < clear_vec; i += (uint64_t)gridDim.x * RH_THREADS)
+            clear[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < pl.npass * RS_RADIX; i += RH_THREADS) sh[i] = 0;
     __syncthreads();
     // grid-stride over 2-key vectors (16-B loads)
@@ -143,8 +151,9 @@ __global__ void __launch_bounds__(RH_THREADS) rs_histogram(const uint64_t* __res
 }
 
 // ---- 2. exclusive scan of 256 bins, one block per pass
-__global__ void __launch_bounds__(RS_RADIX) rs_scan(uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(RS_RADIX) rs_scan(uint32_t* __restrict__ hist, const uint32_t* __restrict__ cond) {
     __shared__ uint32_t wsum[RS_RADIX / 32];
+    if (cond && *cond == 0) return;
     uint32_t* h = hist + blockIdx.x * RS_RADIX;
     uint32_t v = h[threadIdx.x];
     uint32_t incl = v;
@@ -172,7 +181,9 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
 
 // 512 threads x 8 items, two CTAs per SM (<= 64 registers): 32 resident warps hide the
 // load -> rank -> look-back -> scatter latency chain of each tile behind the other tile's.
-template <bool HAS_VALUES, bool SPLIT>
+// COND: persistent variant for the hybrid sort's fallback - a fixed grid that does nothing when *cond == 0 and
+// otherwise works through all the tiles (ticket loop). The plain variant runs one tile per CTA.
+template <bool HAS_VALUES, bool SPLIT, bool COND = false>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
         uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values, uint32_t iota_base,
@@ -180,7 +191,8 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         const PeerTable* __restrict__ peers,        // non-null: bucket d is written into peer d's buffers (NVLink stores)
         const uint32_t* __restrict__ digit_base_g,  // [256] exclusive global digit offsets of this pass
         uint32_t* __restrict__ status,              // [ntiles][256] look-back words of this pass
-        uint32_t* __restrict__ ticket) {
+        uint32_t* __restrict__ ticket, const uint32_t* __restrict__ cond = nullptr, uint32_t ntiles = 0) {
+    if (COND && *cond == 0) return;
     // dynamic shared memory (> 48 KiB): [stage_k 32 KiB][stage_v 16 KiB if values][warp_hist][digit_base][warp_tot][tile][tile_hist]
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t* stage_k = reinterpret_cast<uint64_t*>(rs_smem);
@@ -196,11 +208,13 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
     long long t_prev = clock64();
 #endif
     const Digit<SPLIT> digit_of = make_digit<SPLIT>(shift, mask, splitters, nsplit);
+  for (;;) {  // one tile per CTA, or (COND) a ticket loop over all tiles
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < RS_WARPS * (RS_RADIX + 1); i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
     if (tid < RS_RADIX) (warp_tot + RS_RADIX / 32 + 1)[tid] = 0;  // tile_hist
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (COND && tile >= ntiles) break;
     const uint32_t tile_base = tile * RS_TILE;
     const uint32_t tile_items = min((uint32_t)RS_TILE, n - tile_base);
     const uint32_t my_base = tile_base + warp * (32 * RS_IPT) + lane;  // warp-striped: item k at my_base + 32k
@@ -366,6 +380,68 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         }
     }
     RS_MARK(7);  // write-out issue
+    if (!COND) break;
+    __syncthreads();
+  }
+}
+
+// ---- 4. hybrid sort: fix-up of the low bits after sorting only the high digits
+// After stable passes over the digits at and above `lowbit`, the items are ordered by their high bits and every
+// run of equal high bits still has to be ordered by its low bits (ties keep their order). With lowbit chosen so
+// that the high bits alone separate nearly all keys (Morton keys of N triangles: ~log2 N + a few bits), the runs
+// are 1-3 items long and ONE coalesced read of the keys replaces lowbit/8 full passes. One thread per run head:
+// stable insertion sort of the run in place. A run longer than RS_MAXRUN raises fix[0]; the conditional passes
+// launched behind this kernel then redo the sort over every digit (correct for any input, e.g. all keys equal).
+// fix[1] = longest run seen, fix[2] = items in runs of 2 or more (the host adapts lowbit for the next build).
+constexpr int RS_MAXRUN = 48;
+constexpr int RF_THREADS = 256;
+constexpr int RF_IPT = 8;  // items per thread: one pair of (same-address) statistics atomics per 2048 items
+__global__ void __launch_bounds__(RF_THREADS)
+rs_fixup(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, int lowbit, uint32_t* __restrict__ fix) {
+    __shared__ uint32_t s_max, s_sum;
+    if (threadIdx.x == 0) { s_max = 0; s_sum = 0; }
+    __syncthreads();
+    uint32_t tmax = 0, tsum = 0;
+#pragma unroll 1
+    for (int r = 0; r < RF_IPT; ++r) {
+        const uint32_t i = (blockIdx.x * RF_IPT + r) * RF_THREADS + threadIdx.x;
+        if (i >= n) break;
+        const uint64_t k = keys[i];
+        const uint64_t hi = k >> lowbit;
+        const bool head = i == 0 || (keys[i - 1] >> lowbit) != hi;
+        if (!head) continue;
+        uint32_t j = i + 1;
+        while (j < n && j - i <= (uint32_t)RS_MAXRUN && (keys[j] >> lowbit) == hi) ++j;
+        const uint32_t len = j - i;
+        if (len > (uint32_t)RS_MAXRUN) {
+            atomicExch(fix + 0, 1u);
+        } else if (len > 1) {
+            for (uint32_t a = i + 1; a < j; ++a) {  // stable: an item only moves past strictly larger keys
+                const uint64_t ka = keys[a];
+                const uint32_t va = vals ? vals[a] : 0u;
+                uint32_t b = a;
+                while (b > i) {
+                    const uint64_t kb = keys[b - 1];
+                    if (kb <= ka) break;
+                    keys[b] = kb;
+                    if (vals) vals[b] = vals[b - 1];
+                    --b;
+                }
+                if (b != a) {
+                    keys[b] = ka;
+                    if (vals) vals[b] = va;
+                }
+            }
+        }
+        if (len > 1) { tmax = max(tmax, len); tsum += len; }
+    }
+    // statistics: shared-memory reduction, then one pair of global atomics per block that saw a run of 2 or more
+    if (tmax) { atomicMax(&s_max, tmax); atomicAdd(&s_sum, tsum); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max) {
+        atomicMax(fix + 1, s_max);
+        atomicAdd(fix + 2, s_sum);
+    }
 }
 
 constexpr size_t rs_smem_bytes(bool has_values) {
@@ -385,14 +461,21 @@ uint64_t radix_tile_status_words(uint32_t n, int npass) {
 
 int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
                bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words, int sms,
-               cudaStream_t s) {
+               cudaStream_t s, int high_passes, uint32_t* d_fix) {
     (void)tile_status_words;
     if (n == 0 || npass == 0) return 0;
-    PassList pl{};
-    pl.npass = npass;
+    const bool hybrid = high_passes > 0 && high_passes < npass && d_fix && vals && npass % 2 == 0;
+    const int first = hybrid ? npass - high_passes : 0;  // passes [first, npass) run unconditionally
+    PassList pl{}, all{};
+    all.npass = npass;
     for (int p = 0; p < npass; ++p) {
-        pl.shift[p] = passes[p].shift;
-        pl.mask[p] = (1u << passes[p].bits) - 1u;
+        all.shift[p] = passes[p].shift;
+        all.mask[p] = (1u << passes[p].bits) - 1u;
+    }
+    pl.npass = npass - first;
+    for (int p = first; p < npass; ++p) {
+        pl.shift[p - first] = all.shift[p];
+        pl.mask[p - first] = all.mask[p];
     }
     const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
     static bool attr_set[64] = {};  // > 48 KiB of dynamic shared memory must be opted into, once per function and device
@@ -401,26 +484,47 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaFuncSetAttribute(rs_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
         cudaFuncSetAttribute(rs_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false));
+        cudaFuncSetAttribute(rs_pass<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
+    const uint32_t hblocks = min((n / 2 + RH_THREADS - 1) / RH_THREADS + 1, (uint32_t)sms * 8u);
     uint32_t* d_ticket = d_hist + npass * RS_RADIX;
     cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);
-    cudaMemsetAsync(d_tile_status, 0, sizeof(uint32_t) * (size_t)tiles * RS_RADIX * npass, s);
-    uint32_t hblocks = min((n / 2 + RH_THREADS - 1) / RH_THREADS + 1, (uint32_t)sms * 8u);
-    rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[0], n, pl, d_hist);
+    cudaMemsetAsync(d_tile_status, 0, sizeof(uint32_t) * (size_t)tiles * RS_RADIX * pl.npass, s);
+    if (hybrid) cudaMemsetAsync(d_fix, 0, sizeof(uint32_t) * 4, s);
+    rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[0], n, pl, d_hist, nullptr, nullptr, 0);
     count_launch();
-    rs_scan<<<npass, RS_RADIX, 0, s>>>(d_hist);
+    rs_scan<<<pl.npass, RS_RADIX, 0, s>>>(d_hist, nullptr);
     count_launch();
     int cur = 0;
-    for (int p = 0; p < npass; ++p) {
+    for (int p = 0; p < pl.npass; ++p) {
         uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
+        const int iota = (iota_values && p == 0) ? 1 : 0;
         if (vals)
             rs_pass<true, false><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n,
-                                                       pl.shift[p], pl.mask[p], (iota_values && p == 0) ? 1 : 0, 0u, nullptr, 0, nullptr,
+                                                       pl.shift[p], pl.mask[p], iota, 0u, nullptr, 0, nullptr,
                                                        d_hist + p * RS_RADIX, status, d_ticket + p);
         else
             rs_pass<false, false><<<tiles, RS_THREADS, rs_smem_bytes(false), s>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, pl.shift[p],
                                                         pl.mask[p], 0, 0u, nullptr, 0, nullptr, d_hist + p * RS_RADIX, status, d_ticket + p);
+        count_launch();
+        cur ^= 1;
+    }
+    if (!hybrid) return cur;
+    // low bits: per-run fix-up; if a run was too long, the conditional kernels below sort the (already permuted,
+    // ties still in their original order) items again over every digit. They exit at once when fix[0] == 0.
+    rs_fixup<<<(n + RF_THREADS * RF_IPT - 1) / (RF_THREADS * RF_IPT), RF_THREADS, 0, s>>>(keys[cur], vals[cur], n, all.shift[first], d_fix);
+    count_launch();
+    cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);  // small; the status words are cleared conditionally
+    rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[cur], n, all, d_hist, d_fix, reinterpret_cast<uint4*>(d_tile_status),
+                                                 (uint64_t)tiles * RS_RADIX * npass / 4);
+    rs_scan<<<npass, RS_RADIX, 0, s>>>(d_hist, d_fix);
+    count_launch(2);
+    for (int p = 0; p < npass; ++p) {  // an even number of passes: the result lands in the buffer the fix-up worked on
+        uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
+        rs_pass<true, false, true><<<2 * sms, RS_THREADS, rs_smem_bytes(true), s>>>(
+            keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, all.shift[p], all.mask[p], 0, 0u, nullptr, 0, nullptr,
+            d_hist + p * RS_RADIX, status, d_ticket + p, d_fix, tiles);
         count_launch();
         cur ^= 1;
     }
@@ -449,7 +553,7 @@ void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t 
     rs_histogram_split<<<hblocks, RH_THREADS, 0, s>>>(keys_in, n, d_splitters, nsplit, d_hist);
     count_launch();
     cudaMemcpyAsync(d_hist + RS_RADIX, d_hist, sizeof(uint32_t) * RS_RADIX, cudaMemcpyDeviceToDevice, s);  // keep the counts
-    rs_scan<<<1, RS_RADIX, 0, s>>>(d_hist);
+    rs_scan<<<1, RS_RADIX, 0, s>>>(d_hist, nullptr);
     count_launch();
     rs_pass<true, true><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys_in, keys_out, vals_in, vals_out, n, 0, 0u,
                                                                 vals_in ? 0 : 1, iota_base, d_splitters, nsplit, nullptr,

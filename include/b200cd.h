@@ -168,6 +168,15 @@ int b200cd_mesh_from_device(b200cd_ctx* ctx, const void* d_xyz, uint32_t nverts,
  * the steady-state upload path (no allocation). */
 int b200cd_mesh_update(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, const uint32_t* tri_idx,
                        int on_device);
+/* Double-buffered frames (a simulation that streams meshes through the library): same as
+ * b200cd_mesh_update from HOST pointers, but enqueued on the context's copy stream and returning at
+ * once, so the PCIe transfer of frame k+1 overlaps the build + query of frame k running from
+ * another mesh object. The host arrays must stay valid until b200cd_mesh_wait(mesh) returns; every
+ * other call that takes this mesh fails with B200CD_E_INVALID until then. The copy is ordered
+ * after the last build / refit that read this mesh. b200cd_mesh_wait blocks the host until the
+ * upload has landed and returns the index check's verdict (B200CD_E_INVALID for an index >= nverts). */
+int b200cd_mesh_update_async(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, const uint32_t* tri_idx);
+int b200cd_mesh_wait(b200cd_ctx* ctx, b200cd_mesh* mesh);
 /* Multi-GPU upload: overwrite only vertices [first_vert, +nverts) and triangles [first_tri, +ntris)
  * from host memory; the ranks then all-gather b200cd_mesh_device_buffers over NVLink (the buffers
  * carry 16 elements of padding so equal chunks of ceil(n / ranks) fit). */

@@ -106,6 +106,39 @@ def test_30bit_keys_with_duplicates(cd, co, ctx, mg):
     assert len(np.unique(ref["keys"])) < len(idx), "test needs duplicate keys"
 
 
+@pytest.mark.parametrize("scale", [1.0, 1 / 128, 1 / 180, 1 / 4096])
+def test_hybrid_sort_runs_fixup_and_fallback(cd, co, ctx, mg, scale):
+    """63-bit keys are sorted by radix passes over their top digits only; runs of equal high bits are put in order
+    by the fix-up kernel, too long runs by the conditional full passes, and the number of digits adapts from one
+    build to the next (api.cu run_build). Shrinking the mesh inside the Morton box makes the runs longer:
+    1.0 -> runs of 1-2, 1/128 and 1/180 -> runs of 5-30 (insertion sort; one more digit next time),
+    1/4096 -> every key in a handful of runs (fallback, then plain full sorts). Every build must give exactly the
+    host sort's order (load_obj.h:107: ascending keys, ties in face order)."""
+    xyz, idx = mg.soup(150_000, seed=5)
+    xyz = (xyz * np.float32(scale) + np.float32(0.25)).astype(np.float32)
+    op, gp = co.make_params(**UNIT), cd.make_params(**UNIT)
+    rk, ri = co.sort_keys(co.morton_keys(xyz, idx, op))
+    want, _ = co.run(xyz, idx, op)
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, gp)
+    seen = []
+    for it in range(5):
+        if it:
+            ctx.bvh_rebuild(bvh, mesh, gp)
+        _, sk, si = bvh.download()
+        seen.append(ctx.stats()["sort_passes"])
+        assert np.array_equal(sk, rk), f"build {it}: sorted keys differ (passes {seen})"
+        assert np.array_equal(si, ri), f"build {it}: tie order differs (passes {seen})"
+    assert np.array_equal(ctx.self_collide(bvh), want)
+    assert seen[0] == 5 and all(4 <= p <= 8 for p in seen), seen
+    if scale == 1.0:
+        assert seen[-1] == 4, seen      # the prefix got shorter
+    if scale <= 1 / 4096:
+        assert seen[-1] == 8, seen      # fell back to plain full sorts
+    bvh.destroy()
+    mesh.destroy()
+
+
 def test_all_keys_identical(cd, co, ctx, mg):
     # every centroid in one Morton cell: the tree is decided by the index tie-break alone
     xyz, idx = mg.soup(3000, h=0.08, seed=4)
@@ -185,6 +218,45 @@ def test_rebuild_and_refit_after_vertex_update(cd, co, ctx, mg):
     assert not np.array_equal(first, ref2)
     bvh.destroy()
     mesh.destroy()
+
+
+def test_double_buffered_frames_async_upload(cd, co, ctx, mg):
+    """b200cd_mesh_update_async / b200cd_mesh_wait: frame k+1 is uploaded on the copy stream while frame k is
+    built and queried from the other mesh object; every frame's pair list equals the oracle's"""
+    xyz0, idx = mg.cloth_fold(120, 120)
+    rng = np.random.default_rng(11)
+    frames_xyz = [xyz0] + [(xyz0 + rng.normal(0, 3e-4, xyz0.shape)).astype(np.float32) for _ in range(3)]
+    op, p = co.default_params(), cd.default_params()
+    want = [co.run(x, idx, op)[0] for x in frames_xyz]
+    assert not np.array_equal(want[0], want[1])
+    nv, nt = len(xyz0), len(idx)
+    hx, hx_ptr = zip(*[cd.pinned_array((nv, 3), np.float32) for _ in range(2)])
+    hi, hi_ptr = cd.pinned_array((nt, 3), np.uint32)
+    hi[:] = idx
+    meshes = [ctx.mesh_from_arrays(xyz0, idx) for _ in range(2)]
+    bvh = ctx.bvh_build(meshes[0], p)
+    hx[0][:] = frames_xyz[0]
+    meshes[0].update_async_from_ptr(hx_ptr[0], hi_ptr)
+    with pytest.raises(cd.B200cdError) as e:      # a mesh with an upload in flight cannot be used before wait()
+        ctx.bvh_rebuild(bvh, meshes[0], p)
+    assert e.value.status == cd.E_INVALID
+    for k in range(len(frames_xyz)):
+        cur = meshes[k % 2]
+        if k + 1 < len(frames_xyz):
+            hx[(k + 1) % 2][:] = frames_xyz[k + 1]
+            meshes[(k + 1) % 2].update_async_from_ptr(hx_ptr[(k + 1) % 2], hi_ptr)
+        cur.wait()
+        ctx.bvh_rebuild(bvh, cur, p)
+        assert np.array_equal(ctx.self_collide(bvh), want[k]), f"frame {k}"
+    # the index check of an asynchronous upload is reported by wait()
+    hi[0, 0] = nv
+    meshes[0].update_async_from_ptr(0, hi_ptr)
+    with pytest.raises(cd.B200cdError) as e:
+        meshes[0].wait()
+    assert e.value.status == cd.E_INVALID
+    bvh.destroy()
+    for m in meshes:
+        m.destroy()
 
 
 def test_capacity_error_reports_true_count(cd, ctx, mg):
