@@ -42,6 +42,7 @@ PKG = "gpu-computing-course_b200"
 METRIC = "Mtri/s end-to-end self-collision (build+query)"
 UNIT = "Mtri/s"
 UNIT_CUBE = ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+SCALING_WORKLOAD = "sheets64m"  # default workload at N > 1
 
 WORKLOADS = {
     # name: (kind, args, morton box or None = reference constants)
@@ -85,8 +86,9 @@ def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes, recs=True):
         "tree": 4 * n + 8 * n + (64 * n if recs else 12 * n + 16 * nverts) + 64 * n + 64 * n,
         # K5: every node pair (64 B) and every query record (64 B) once, 8 B per candidate out
         "traverse": 64 * n + 64 * n + 8 * ncand,
-        # K6: candidate in, two 64 B leaf records per candidate, 8 B per pair out
-        "narrow": 8 * ncand + 128 * ncand + 8 * npairs,
+        # K6: candidate list in, every leaf record it names at most once from HBM (compulsory traffic; repeats are
+        #     cache hits), 8 B per pair out
+        "narrow": 8 * ncand + 64 * min(2 * ncand, n) + 8 * npairs,
     }
 
 
@@ -234,6 +236,40 @@ def run_reference_arm(args, workload):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+
+def device_value(cd, mg, mgpu, ctx, name, steps, warmup=3):
+    """triangles / CUDA-event time of `steps` build + query steps of workload `name` on ONE GPU, mesh resident in HBM"""
+    import numpy as np
+    import torch
+    _, _, box = WORKLOADS[name]
+    nverts, ntris = workload_sizes(mg, name)
+    xyz, xyz_ptr = cd.pinned_array((nverts, 3), np.float32)
+    idx, idx_ptr = cd.pinned_array((ntris, 3), np.uint32)
+    generate(mg, name, out=(xyz, idx))
+    params = cd.make_params(*box) if box else cd.default_params()
+    mesh = ctx.mesh_from_host_ptr(xyz_ptr, nverts, idx_ptr, ntris)
+    runner = mgpu.ShardedSelfCollision(cd, ctx)
+    bvh = ctx.bvh_build(mesh, params)
+    for _ in range(warmup):
+        pairs = runner.step(bvh, mesh, params)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        pairs = runner.step(bvh, mesh, params)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    st = ctx.stats()
+    out = {"workload": name, "triangles": ntris, "vertices": nverts, "n_gpus": 1, "steps": steps,
+           "value": round(ntris / ms / 1e3, 2), "unit": UNIT, "ms_per_step": round(ms, 4), "pairs": int(pairs.numel()),
+           "bvh_build_ms": round(st["ms_build"], 4), "query_ms": round(st["ms_query"], 4)}
+    bvh.destroy()
+    mesh.destroy()
+    cd.host_free(xyz_ptr)
+    cd.host_free(idx_ptr)
+    return out
+
 
 def run_gpu_arm(args, workload):
     import numpy as np
@@ -396,6 +432,7 @@ def run_gpu_arm(args, workload):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         ncand, npairs = int(last.get("candidates", 0)), int(last.get("pairs", 0))
         recs = os.environ.get("B200CD_RECS", "1") != "0"
+        recs = recs and 2 * nverts >= 3 * ntris  # api.cu run_build: only for (mostly) unshared vertices
         abytes = algorithmic_bytes(ntris, nverts, ncand, npairs, int(last.get("sort_passes", 8)), recs)
         if partitioned:  # rank 0's own Morton range (keys arrive from the exchange: no face-ordered records)
             nloc = int(prunner.stats.get("local_triangles", ntris // world))
@@ -453,6 +490,10 @@ def run_gpu_arm(args, workload):
         }
         if partitioned:
             line["partition"] = dict(prunner.stats, rank=0, build_ms=ctx.stats()["ms_build"], query_ms=ctx.stats()["ms_query"])
+        if world == 1 and workload != SCALING_WORKLOAD and not args.no_scaling_base:
+            # the N > 1 runs use sheets64m (strong scaling of a fixed 2^26-triangle mesh): its single-GPU time, measured
+            # here in the same run, is the denominator of that scaling curve (this line's `value` is soup16m)
+            line["scaling_base"] = device_value(cd, mg, mgpu, ctx, SCALING_WORKLOAD, steps=max(3, min(args.steps, 5)))
         if world == 1 and not args.no_cpu_baseline:
             vals, info = cpu_reference_run(workload, args.cpu_sample, 1)
             line["cpu_baseline"] = {"value": round(vals[0], 4), "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
@@ -485,8 +526,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 14, help="sorted leaves per block-cyclic query chunk (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 21, help="triangles in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaling-base", action="store_true", help="N = 1: skip the single-GPU run of the N > 1 workload")
     args = ap.parse_args()
-    workload = args.workload or ("soup16m" if args.gpus == 1 else "sheets64m")
+    workload = args.workload or ("soup16m" if args.gpus == 1 else SCALING_WORKLOAD)
 
     if args.impl == "reference":
         run_reference_arm(args, workload)

@@ -219,7 +219,11 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
         }
         // face-ordered leaf records for the tree build (64 B per triangle, allocated on first use; B200CD_RECS=0 turns
         // them off - tuning / A-B knob). Without them the build gathers indices and vertices itself.
-        if (!b->d_recs && leaf_records_enabled() && cudaMalloc(reinterpret_cast<void**>(&b->d_recs), sizeof(LeafRec) * (size_t)n) != cudaSuccess) {
+        // Worth it when vertices are (mostly) unshared - a triangle soup, V = 3N: -0.21 ms in the tree build for
+        // +0.11 ms in K1 at 16 M. On a mesh (V ~ N/2) the vertex gathers hit L2 anyway and the records only add traffic.
+        const bool want_recs = leaf_records_enabled() && 2ull * m->nverts >= 3ull * n;
+        if (!want_recs && b->d_recs) { cudaFree(b->d_recs); b->d_recs = nullptr; }
+        if (!b->d_recs && want_recs && cudaMalloc(reinterpret_cast<void**>(&b->d_recs), sizeof(LeafRec) * (size_t)n) != cudaSuccess) {
             cudaGetLastError();
             b->d_recs = nullptr;  // not enough memory: the gather path needs none
         }
@@ -903,7 +907,7 @@ API int b200cd_select_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void
     cudaStream_t s = ctx->stream;
     unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(ctx->d_scalars);  // 32 x u64 = 64 words
     launch_ghosts(bvh->d_leaves, bvh->n, static_cast<const float*>(d_peer_boxes), npeers, K, peer_mask, bvh->d_ghost_out,
-                  bvh->ghost_out_cap, d_counts, s);
+                  bvh->ghost_out_cap, d_counts, reinterpret_cast<float*>(bvh->d_cut_scratch), s);  // (cut scratch: free by now)
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, d_counts, sizeof(unsigned long long) * npeers, cudaMemcpyDeviceToHost, s));
     CD_CUDA(ctx, cudaStreamSynchronize(s));
     CD_CUDA(ctx, cudaGetLastError());
@@ -1037,8 +1041,9 @@ API int b200cd_send_ghosts_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, con
         return set_error(ctx, B200CD_E_INVALID, "bad argument");
     if (!bvh->built || !bvh->d_peers) return set_error(ctx, B200CD_E_INVALID, "BVH not built / peers not set");
     DeviceGuard g(ctx->device);
+    if (!bvh->d_cut_scratch) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
     launch_ghosts_to_peers(bvh->d_leaves, bvh->n, static_cast<const float*>(d_peer_boxes), npeers, K, peer_mask, bvh->d_peers,
-                           ctx->stream);
+                           reinterpret_cast<float*>(bvh->d_cut_scratch), ctx->stream);
     CD_CUDA(ctx, cudaGetLastError());
     return B200CD_OK;
 }

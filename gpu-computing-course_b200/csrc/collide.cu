@@ -332,16 +332,18 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
             candL = hitL && linkL < 0; leafL = ~linkL;
             candR = hitR && linkR < 0; leafR = ~linkR;
             const bool goL = hitL && linkL >= 0, goR = hitR && linkR >= 0;
-            if (goL) {
-                node = linkL;
-                if (goR) {
-                    if (sp < B200CD_MAX_STACK) stack[sp++] = linkR; else overflow = 1;
-                }
-            } else if (goR) {
-                node = linkR;
-            } else {
-                node = sp > 0 ? stack[--sp] : -1;
+            // straight-line (predicated) successor selection: descend left first, park the right child, pop when neither
+            if (goL && goR) {
+                stack[sp] = linkR;  // sp <= B200CD_MAX_STACK - 1: on overflow the top entry is overwritten and the query reports E_DEPTH
+                if (sp < B200CD_MAX_STACK - 1) ++sp; else overflow = 1;
             }
+            int nxt = goL ? linkL : linkR;
+            if (!(goL || goR)) {
+                const bool have = sp > 0;
+                sp -= have ? 1 : 0;
+                nxt = have ? stack[sp] : -1;
+            }
+            node = nxt;
         }
         stage2((uint32_t)q, candL, leafL, candR, leafR);
     }

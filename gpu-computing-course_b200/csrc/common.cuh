@@ -249,10 +249,10 @@ void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32
 int ghost_max_k();
 void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                    uint32_t peer_mask, LeafRec* d_ghosts, uint64_t cap_per_peer, unsigned long long* d_counts,
-                   cudaStream_t s);
+                   float* d_overall /* scratch: 6 * npeers floats */, cudaStream_t s);
 // same selection, but the records are appended straight into the peers' ghost buffers (remote atomics + stores)
 void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
-                            uint32_t peer_mask, const PeerTable* d_peers, cudaStream_t s);
+                            uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, cudaStream_t s);
 // collide.cu
 // foreign != 0: the queries are the nquery ghost records stored at leaves[ghost_base ...]; they start at the
 // root and are tested against every local leaf (no "only later positions" rule)

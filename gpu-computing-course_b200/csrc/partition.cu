@@ -93,7 +93,8 @@ template <bool REMOTE>
 __global__ void __launch_bounds__(256)
 ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __restrict__ peer_boxes, uint32_t npeers,
              uint32_t K, uint32_t peer_mask, LeafRec* __restrict__ ghosts, uint64_t cap_per_peer,
-             unsigned long long* __restrict__ counts, const PeerTable* __restrict__ peers) {
+             unsigned long long* __restrict__ counts, const PeerTable* __restrict__ peers,
+             const float* __restrict__ peer_overall) {
     __shared__ float s_box[GH_MAXK][6];
     __shared__ float s_sup[GH_MAXK / GH_GROUP + 1][6];  // super boxes; the last used slot + 1 .. : [nsup] = overall box
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,8 +114,40 @@ ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __rest
     auto hits = [&](const float* b) {
         return lo[0] < b[3] && b[0] < hi[0] && lo[1] < b[4] && b[1] < hi[1] && lo[2] < b[5] && b[2] < hi[2];
     };
+    // union box of the block's 256 consecutive sorted leaves (a compact cell of the Morton curve): a peer whose
+    // overall box it does not overlap cannot receive any of them, and the block skips that peer's K boxes
+    // altogether - all but the blocks next to a range boundary skip every peer
+    __shared__ float s_red[8][6];
+    __shared__ float s_union[6];
+    {
+        float v[6] = {valid ? lo[0] : inf, valid ? lo[1] : inf, valid ? lo[2] : inf,
+                      valid ? hi[0] : -inf, valid ? hi[1] : -inf, valid ? hi[2] : -inf};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float t = __shfl_xor_sync(0xffffffffu, v[c], o);
+                v[c] = c < 3 ? fminf(v[c], t) : fmaxf(v[c], t);
+            }
+            if (lane == 0) s_red[threadIdx.x >> 5][c] = v[c];
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            const uint32_t c = threadIdx.x;
+            float u = s_red[0][c];
+            for (int w = 1; w < 8; ++w) u = c < 3 ? fminf(u, s_red[w][c]) : fmaxf(u, s_red[w][c]);
+            s_union[c] = u;
+        }
+        __syncthreads();
+    }
     for (uint32_t p = 0; p < npeers; ++p) {
         if (!((peer_mask >> p) & 1u)) continue;  // uniform
+        {   // block-uniform: the peer's overall box (peer_overall, 6 floats per peer) against the block's union box
+            const float* ob = peer_overall + 6 * (size_t)p;
+            const float o0 = __ldg(ob), o1 = __ldg(ob + 1), o2 = __ldg(ob + 2), o3 = __ldg(ob + 3), o4 = __ldg(ob + 4), o5 = __ldg(ob + 5);
+            if (!(s_union[0] < o3 && o0 < s_union[3] && s_union[1] < o4 && o1 < s_union[4] && s_union[2] < o5 && o2 < s_union[5]))
+                continue;
+        }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < K * 6; i += blockDim.x) (&s_box[0][0])[i] = __ldg(peer_boxes + (size_t)p * K * 6 + i);
         __syncthreads();
@@ -158,6 +191,28 @@ ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __rest
     }
 }
 
+// overall[p] = union of peer p's K coarse boxes (one warp per peer)
+__global__ void __launch_bounds__(32)
+peer_overall_kernel(const float* __restrict__ peer_boxes, uint32_t K, float* __restrict__ overall) {
+    const uint32_t p = blockIdx.x, lane = threadIdx.x;
+    const float inf = __int_as_float(0x7f800000);
+    float v[6] = {inf, inf, inf, -inf, -inf, -inf};
+    for (uint32_t k = lane; k < K; k += 32) {
+        const float* b = peer_boxes + ((size_t)p * K + k) * 6;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v[c] = c < 3 ? fminf(v[c], __ldg(b + c)) : fmaxf(v[c], __ldg(b + c));
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float t = __shfl_xor_sync(0xffffffffu, v[c], o);
+            v[c] = c < 3 ? fminf(v[c], t) : fmaxf(v[c], t);
+        }
+        if (lane == 0) overall[6 * (size_t)p + c] = v[c];
+    }
+}
+
 }  // namespace
 
 void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist, int sms, cudaStream_t s) {
@@ -185,22 +240,25 @@ void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32
 
 int ghost_max_k() { return GH_MAXK; }
 
+// d_overall: scratch of 6 * npeers floats (the peers' overall boxes)
 void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                    uint32_t peer_mask, LeafRec* d_ghosts, uint64_t cap_per_peer, unsigned long long* d_counts,
-                   cudaStream_t s) {
+                   float* d_overall, cudaStream_t s) {
     cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * npeers, s);
     if (!n || !npeers || !peer_mask) return;
+    peer_overall_kernel<<<npeers, 32, 0, s>>>(d_peer_boxes, K, d_overall);
     ghost_kernel<false><<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, d_ghosts,
-                                                       cap_per_peer, d_counts, nullptr);
-    count_launch();
+                                                       cap_per_peer, d_counts, nullptr, d_overall);
+    count_launch(2);
 }
 
 void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
-                            uint32_t peer_mask, const PeerTable* d_peers, cudaStream_t s) {
+                            uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, cudaStream_t s) {
     if (!n || !npeers || !peer_mask) return;
+    peer_overall_kernel<<<npeers, 32, 0, s>>>(d_peer_boxes, K, d_overall);
     ghost_kernel<true><<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, nullptr, 0, nullptr,
-                                                      d_peers);
-    count_launch();
+                                                      d_peers, d_overall);
+    count_launch(2);
 }
 
 }  // namespace b200cd

@@ -402,13 +402,23 @@ rs_fixup(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, i
     if (threadIdx.x == 0) { s_max = 0; s_sum = 0; }
     __syncthreads();
     uint32_t tmax = 0, tsum = 0;
-#pragma unroll 1
+    // all the block's loads first (two coalesced reads per item), then the rare per-run work
+    const uint32_t base = blockIdx.x * (RF_IPT * RF_THREADS) + threadIdx.x;
+    uint64_t kk[RF_IPT], kp[RF_IPT];
+#pragma unroll
     for (int r = 0; r < RF_IPT; ++r) {
-        const uint32_t i = (blockIdx.x * RF_IPT + r) * RF_THREADS + threadIdx.x;
-        if (i >= n) break;
-        const uint64_t k = keys[i];
-        const uint64_t hi = k >> lowbit;
-        const bool head = i == 0 || (keys[i - 1] >> lowbit) != hi;
+        const uint32_t i = base + r * RF_THREADS;
+        kk[r] = i < n ? keys[i] : 0ull;
+        kp[r] = (i < n && i > 0) ? keys[i - 1] : 0ull;
+    }
+    // (a run's head may already be reordering it while others take their snapshot: harmless, the HIGH bits - all that
+    // the head test looks at - are the same for every item of a run, and 8-byte accesses do not tear)
+#pragma unroll
+    for (int r = 0; r < RF_IPT; ++r) {
+        const uint32_t i = base + r * RF_THREADS;
+        if (i >= n) continue;
+        const uint64_t hi = kk[r] >> lowbit;
+        const bool head = i == 0 || (kp[r] >> lowbit) != hi;
         if (!head) continue;
         uint32_t j = i + 1;
         while (j < n && j - i <= (uint32_t)RS_MAXRUN && (keys[j] >> lowbit) == hi) ++j;
@@ -432,8 +442,9 @@ rs_fixup(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, i
                     if (vals) vals[b] = va;
                 }
             }
+            tmax = max(tmax, len);
+            tsum += len;
         }
-        if (len > 1) { tmax = max(tmax, len); tsum += len; }
     }
     // statistics: shared-memory reduction, then one pair of global atomics per block that saw a run of 2 or more
     if (tmax) { atomicMax(&s_max, tmax); atomicAdd(&s_sum, tsum); }
