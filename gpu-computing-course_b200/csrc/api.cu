@@ -89,6 +89,7 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_pairs);
     cudaFree(b->d_leaves);
     cudaFree(b->d_recs);
+    cudaFree(b->d_block_boxes);
     cudaFree(b->d_ghost_out);
     cudaFree(b->d_cut_scratch);
     cudaFree(b->d_peers);
@@ -147,6 +148,7 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
         b->ghost_out_cap = ghost_cap;
         A(dev_alloc(ctx, &b->d_ghost_out, (uint64_t)max_peers * ghost_cap));
         A(dev_alloc(ctx, &b->d_cut_scratch, (uint64_t)ghost_max_k() * 6 + 1));
+        A(dev_alloc(ctx, &b->d_block_boxes, ((uint64_t)n / 256 + 1) * 8));
         A(dev_alloc(ctx, &b->d_peers, 1));
         A(dev_alloc(ctx, &b->d_ghost_in_count, 2));
     }
@@ -266,7 +268,7 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));  // (K3 is fused into K4: ms_hierarchy stays ~0)
     launch_build_tree(m->d_verts, m->d_idx, b->d_ids[b->cur], b->d_keys[b->cur], n, b->d_flags, b->d_pairs, b->d_leaves,
-                      b->d_root_box, b->d_build_scratch, s, keys_given ? nullptr : b->d_recs);  // K3+K4
+                      b->d_root_box, b->d_build_scratch, s, keys_given ? nullptr : b->d_recs, b->d_block_boxes);  // K3+K4
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, mark_consumed(m, s));  // nothing after this point reads the mesh
     CD_CUDA(ctx, cudaGetLastError());
@@ -717,7 +719,7 @@ API int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* me
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));
     // the sorted keys are kept, so the same climb reproduces the same topology around the new boxes
     launch_build_tree(mesh->d_verts, mesh->d_idx, bvh->d_ids[bvh->cur], bvh->d_keys[bvh->cur], bvh->n, bvh->d_flags,
-                      bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, bvh->d_build_scratch, s);
+                      bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, bvh->d_build_scratch, s, nullptr, bvh->d_block_boxes);
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, mark_consumed(mesh, s));
     CD_CUDA(ctx, cudaGetLastError());
@@ -907,7 +909,7 @@ API int b200cd_select_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void
     cudaStream_t s = ctx->stream;
     unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(ctx->d_scalars);  // 32 x u64 = 64 words
     launch_ghosts(bvh->d_leaves, bvh->n, static_cast<const float*>(d_peer_boxes), npeers, K, peer_mask, bvh->d_ghost_out,
-                  bvh->ghost_out_cap, d_counts, reinterpret_cast<float*>(bvh->d_cut_scratch), s);  // (cut scratch: free by now)
+                  bvh->ghost_out_cap, d_counts, reinterpret_cast<float*>(bvh->d_cut_scratch), bvh->d_block_boxes, s);  // (cut scratch: free by now)
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, d_counts, sizeof(unsigned long long) * npeers, cudaMemcpyDeviceToHost, s));
     CD_CUDA(ctx, cudaStreamSynchronize(s));
     CD_CUDA(ctx, cudaGetLastError());
@@ -1043,7 +1045,7 @@ API int b200cd_send_ghosts_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, con
     DeviceGuard g(ctx->device);
     if (!bvh->d_cut_scratch) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
     launch_ghosts_to_peers(bvh->d_leaves, bvh->n, static_cast<const float*>(d_peer_boxes), npeers, K, peer_mask, bvh->d_peers,
-                           reinterpret_cast<float*>(bvh->d_cut_scratch), ctx->stream);
+                           reinterpret_cast<float*>(bvh->d_cut_scratch), bvh->d_block_boxes, ctx->stream);
     CD_CUDA(ctx, cudaGetLastError());
     return B200CD_OK;
 }

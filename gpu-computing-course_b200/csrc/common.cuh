@@ -92,6 +92,7 @@ struct b200cd_bvh {
     uint32_t n = 0;         // triangles (leaves) currently in the tree
     uint32_t cap = 0;       // leaves the buffers were sized for (== n except for partitioned builds)
     uint64_t ghost_cap = 0; // ghost leaf records that fit after the local leaves in d_leaves
+    float* d_block_boxes = nullptr;           // [cap / 256 + 1][8] union box of every 256-leaf block (partitioned builds)
     b200cd::LeafRec* d_ghost_out = nullptr;   // [peers][ghost_out_cap] outgoing ghost lists
     uint32_t* d_cut_scratch = nullptr;        // coarse-box reduction scratch (256*6+1 words)
     b200cd::PeerTable* d_peers = nullptr;     // peer-memory destinations (b200cd_bvh_set_peers)
@@ -235,7 +236,7 @@ uint64_t build_tree_scratch_bytes(uint32_t n);
 // (one 64-byte gather per leaf) instead of being assembled from d_idx / d_verts
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
-                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs = nullptr);
+                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs = nullptr, float* d_block_boxes = nullptr);
 // d_scratch: 2 * (2n-1) words
 void launch_export_nodes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t* d_scratch,
                          b200cd_node32* d_nodes_out, cudaStream_t s);
@@ -249,10 +250,11 @@ void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32
 int ghost_max_k();
 void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                    uint32_t peer_mask, LeafRec* d_ghosts, uint64_t cap_per_peer, unsigned long long* d_counts,
-                   float* d_overall /* scratch: 6 * npeers floats */, cudaStream_t s);
+                   float* d_overall /* scratch: 6 * npeers floats */, const float* d_block_boxes, cudaStream_t s);
 // same selection, but the records are appended straight into the peers' ghost buffers (remote atomics + stores)
 void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
-                            uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, cudaStream_t s);
+                            uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, const float* d_block_boxes,
+                            cudaStream_t s);
 // collide.cu
 // foreign != 0: the queries are the nquery ghost records stored at leaves[ghost_base ...]; they start at the
 // root and are tested against every local leaf (no "only later positions" rule)

@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(BL)
 build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ sorted_ids,
              const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
              LeafRec* __restrict__ leaves, float* __restrict__ root_box, Pending* __restrict__ list,
-             uint32_t* __restrict__ list_count, uint32_t capacity, const LeafRec* __restrict__ recs) {
+             uint32_t* __restrict__ list_count, uint32_t capacity, const LeafRec* __restrict__ recs,
+             float* __restrict__ block_boxes /* optional: [blocks][8], union box of each block's 256 leaves */) {
+    __shared__ float s_bb[BL / 32][6];
     __shared__ int s_sim[BL + 1];          // s_sim[i] = similarity of sorted positions (B0-1+i, B0+i); -1 outside
     __shared__ uint32_t s_flag[BL];        // per split B0+i: bit 0 = left child arrived, bit 1 = right child arrived
     __shared__ float4 s_dep[BL][2][2];     // per split, per side: the child's Node32 (ext as in pairs[])
@@ -214,9 +216,29 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     }
     s_flag[tid] = 0;
     if (tid == 0) s_npend = 0;
+    if (block_boxes) {  // (partitioned builds) the ghost selection tests whole blocks against the peers' boxes first
+        const float inf = __int_as_float(0x7f800000);
+        float v[6] = {j < n ? c.lo[0] : inf, j < n ? c.lo[1] : inf, j < n ? c.lo[2] : inf,
+                      j < n ? c.hi[0] : -inf, j < n ? c.hi[1] : -inf, j < n ? c.hi[2] : -inf};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float t = __shfl_xor_sync(0xffffffffu, v[k], o);
+                v[k] = k < 3 ? fminf(v[k], t) : fmaxf(v[k], t);
+            }
+            if ((tid & 31) == 0) s_bb[tid >> 5][k] = v[k];
+        }
+    }
     BT_MARK(0);  // gathers + leaf record + similarities (thread 0)
     __syncthreads();
     BT_MARK(1);  // wait for the block
+    if (block_boxes && tid < 6) {
+        float u = s_bb[0][tid];
+#pragma unroll
+        for (int w = 1; w < BL / 32; ++w) u = tid < 3 ? fminf(u, s_bb[w][tid]) : fmaxf(u, s_bb[w][tid]);
+        block_boxes[8 * (size_t)blockIdx.x + tid] = u;
+    }
 
     // ---- climb inside the block: splits s with both neighbours in the block, B0 <= s < Bend
     bool pending = false;  // holding a subtree whose parent split lies outside the block's shared-memory range
@@ -440,7 +462,7 @@ uint32_t build_tree_pending_capacity(uint32_t n) { return n / 8 + 4096; }
 
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
-                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs) {
+                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs, float* d_block_boxes) {
     if (!n) return;
     uint32_t* list_count = static_cast<uint32_t*>(d_scratch);
     Pending* list = reinterpret_cast<Pending*>(static_cast<char*>(d_scratch) + 16);
@@ -449,10 +471,10 @@ void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint3
     cudaMemsetAsync(list_count, 0, sizeof(uint32_t), s);
     if (d_recs)
         build_kernel<true><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs, d_leaves,
-                                                            d_root_box, list, list_count, capacity, d_recs);
+                                                            d_root_box, list, list_count, capacity, d_recs, d_block_boxes);
     else
         build_kernel<false><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs,
-                                                             d_leaves, d_root_box, list, list_count, capacity, nullptr);
+                                                             d_leaves, d_root_box, list, list_count, capacity, nullptr, d_block_boxes);
     count_launch();
     {
         upper_kernel<<<(capacity + 127) / 128, 128, 0, s>>>(list, list_count, capacity, d_keys, (int)n, d_flags, d_pairs,

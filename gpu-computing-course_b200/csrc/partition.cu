@@ -94,7 +94,24 @@ __global__ void __launch_bounds__(256)
 ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __restrict__ peer_boxes, uint32_t npeers,
              uint32_t K, uint32_t peer_mask, LeafRec* __restrict__ ghosts, uint64_t cap_per_peer,
              unsigned long long* __restrict__ counts, const PeerTable* __restrict__ peers,
-             const float* __restrict__ peer_overall) {
+             const float* __restrict__ peer_overall, const float* __restrict__ block_boxes) {
+    __shared__ float s_red[8][6];
+    __shared__ float s_union[6];
+    // The tree build left the union box of every 256-leaf block (build_kernel, block_boxes): a block that
+    // overlaps no selected peer's overall box retires here, without reading a single leaf record - on a
+    // Morton-range partition that is every block except those next to a range boundary.
+    if (block_boxes) {
+        if (threadIdx.x < 6) s_union[threadIdx.x] = __ldg(block_boxes + 8 * (size_t)blockIdx.x + threadIdx.x);
+        __syncthreads();
+        bool any = false;
+        for (uint32_t p = 0; p < npeers; ++p) {
+            if (!((peer_mask >> p) & 1u)) continue;
+            const float* ob = peer_overall + 6 * (size_t)p;
+            any = any || (s_union[0] < __ldg(ob + 3) && __ldg(ob) < s_union[3] && s_union[1] < __ldg(ob + 4) &&
+                          __ldg(ob + 1) < s_union[4] && s_union[2] < __ldg(ob + 5) && __ldg(ob + 2) < s_union[5]);
+        }
+        if (!any) return;  // block-uniform
+    }
     __shared__ float s_box[GH_MAXK][6];
     __shared__ float s_sup[GH_MAXK / GH_GROUP + 1][6];  // super boxes; the last used slot + 1 .. : [nsup] = overall box
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,9 +134,7 @@ ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __rest
     // union box of the block's 256 consecutive sorted leaves (a compact cell of the Morton curve): a peer whose
     // overall box it does not overlap cannot receive any of them, and the block skips that peer's K boxes
     // altogether - all but the blocks next to a range boundary skip every peer
-    __shared__ float s_red[8][6];
-    __shared__ float s_union[6];
-    {
+    if (!block_boxes) {
         float v[6] = {valid ? lo[0] : inf, valid ? lo[1] : inf, valid ? lo[2] : inf,
                       valid ? hi[0] : -inf, valid ? hi[1] : -inf, valid ? hi[2] : -inf};
 #pragma unroll
@@ -243,21 +258,22 @@ int ghost_max_k() { return GH_MAXK; }
 // d_overall: scratch of 6 * npeers floats (the peers' overall boxes)
 void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                    uint32_t peer_mask, LeafRec* d_ghosts, uint64_t cap_per_peer, unsigned long long* d_counts,
-                   float* d_overall, cudaStream_t s) {
+                   float* d_overall, const float* d_block_boxes, cudaStream_t s) {
     cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * npeers, s);
     if (!n || !npeers || !peer_mask) return;
     peer_overall_kernel<<<npeers, 32, 0, s>>>(d_peer_boxes, K, d_overall);
     ghost_kernel<false><<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, d_ghosts,
-                                                       cap_per_peer, d_counts, nullptr, d_overall);
+                                                       cap_per_peer, d_counts, nullptr, d_overall, d_block_boxes);
     count_launch(2);
 }
 
 void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
-                            uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, cudaStream_t s) {
+                            uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, const float* d_block_boxes,
+                            cudaStream_t s) {
     if (!n || !npeers || !peer_mask) return;
     peer_overall_kernel<<<npeers, 32, 0, s>>>(d_peer_boxes, K, d_overall);
     ghost_kernel<true><<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, nullptr, 0, nullptr,
-                                                      d_peers, d_overall);
+                                                      d_peers, d_overall, d_block_boxes);
     count_launch(2);
 }
 

@@ -112,6 +112,28 @@ def gather_pairs(local, dst=0, group=None):
     return merged, counts
 
 
+def gather_pairs_padded(local, id_bits, group=None):
+    """The same exchange as ONE fixed-size collective: all-gather of the counts (one host read), then a single
+    all-gather of every rank's list padded to the longest one. The padding is a sentinel word that sorts behind
+    every real pair (both halves = 2^id_bits - 1; a real pair has lo < hi), so the caller sorts the whole
+    buffer and keeps the first sum(counts) words - no per-rank offsets, no grouped send/recv launches.
+    Returns (buffer of world * max(counts) words - identical on every rank -, counts list)."""
+    world = dist.get_world_size(group)
+    cnt = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    counts_t = torch.empty(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(counts_t, cnt, group=group)
+    counts = counts_t.cpu().tolist()
+    cap = max(counts)
+    if cap == 0:
+        return torch.empty(0, dtype=torch.int64, device=local.device), counts
+    top = (1 << id_bits) - 1
+    mine = torch.full((cap,), (top << 32) | top, dtype=torch.int64, device=local.device)
+    mine[:local.numel()] = local
+    buf = torch.empty(world * cap, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(buf, mine, group=group)
+    return buf, counts
+
+
 def unpack_pairs(words):
     """int64 packed words -> (count, 2) uint32 numpy array, lower ID first"""
     a = words.detach().cpu().numpy().astype(np.int64, copy=False)
@@ -425,9 +447,13 @@ class PartitionedSelfCollision:
         local = p.collide_ghosts()
         mark("ghost query")
         self.stats = {"local_triangles": p.nlocal, "ghosts": p.nghost, "local_pairs": int(local.numel()), "peer_memory": True}
-        merged, self.counts = gather_pairs(local, 0, g)
-        if r == 0 and merged.numel() > 1:
-            ctx.sort_pairs_device(merged.data_ptr(), merged.numel(), id_bits=max(1, int(p.n - 1).bit_length()))
+        id_bits = max(1, int(p.n - 1).bit_length())
+        buf, self.counts = gather_pairs_padded(local, id_bits, g)
+        merged = None
+        if r == 0:
+            if buf.numel() > 1:
+                ctx.sort_pairs_device(buf.data_ptr(), buf.numel(), id_bits=id_bits)  # sentinels end up behind the pairs
+            merged = buf[:sum(self.counts)]
         mark("gather+sort")
         if profile:
             self.stats["phase_ms"] = {b[0]: round(1e3 * (b[1] - a[1]), 3) for a, b in zip(marks, marks[1:])}

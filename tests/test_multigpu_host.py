@@ -51,6 +51,15 @@ def _worker(rank, world, port, chunk, tmpdir):
             np.save(os.path.join(tmpdir, "ok.npy"), np.array(counts))
         else:
             assert merged is None
+        # the single-collective variant: padded all-gather, sentinels sort behind every real pair
+        id_bits = max(1, int(len(idx) - 1).bit_length())
+        words = torch.from_numpy(mine.view(np.int64).reshape(-1).copy())
+        buf, counts2 = mgpu.gather_pairs_padded(words, id_bits)
+        assert counts2 == counts and buf.numel() == world * max(counts)
+        u = buf.numpy().view(np.uint32).reshape(-1, 2)
+        order = np.lexsort((u[:, 1], u[:, 0]))  # what b200cd_sort_pairs_device does on the GPU: by lo id, then hi id
+        assert np.array_equal(u[order][: len(full)], full)
+        assert (u[order][len(full):] == (1 << id_bits) - 1).all()
         # empty contribution from one rank
         words = torch.zeros(0 if rank == 1 else 5, dtype=torch.int64)
         merged, counts = mgpu.gather_pairs(words, 0)
