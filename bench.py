@@ -410,6 +410,42 @@ def run_gpu_arm(args, workload):
         e2e_mode = ("double-buffered frames: b200cd_mesh_update_async of frame k+1 overlaps b200cd_bvh_rebuild + "
                     "b200cd_self_collide of frame k; one full H2D and one D2H per step inside the timed region")
         frames[1].destroy()
+    elif partitioned and prunner.peer_memory:
+        # several GPUs, double-buffered frames: every rank pushes its 1/world slice of frame k+1 over its own PCIe
+        # link and on into the peers' mesh buffers with the copy engines over NVLink (copy stream, no NCCL, no SMs)
+        # while frame k is built and queried. Still one whole mesh H2D (summed over the ranks) and one D2H per step.
+        frames = [mesh, ctx.mesh_from_host_ptr(xyz_ptr, nverts, idx_ptr, ntris)]
+        pm = mgpu.PeerMeshFrames(cd, ctx, frames)
+        if pm.ok:
+            for k in range(2):                            # warm-up: staging buffers, events, copy stream, peer mappings
+                pm.upload_async(k, xyz_ptr, idx_ptr)
+                pm.wait(k)
+            torch.cuda.synchronize()
+            ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            ev4.record()
+            pm.upload_async(0, xyz_ptr, idx_ptr)
+            for k in range(args.steps):
+                if k + 1 < args.steps:
+                    pm.upload_async((k + 1) % 2, xyz_ptr, idx_ptr)
+                prunner.part.mesh = pm.wait(k % 2)
+                merged = prunner.step()
+                if rank == 0:
+                    host_pairs[: merged.numel()].copy_(merged, non_blocking=True)
+                    d2h = 8 * int(merged.numel())
+                torch.cuda.current_stream().synchronize()
+            ev5.record()
+            barrier()
+            ms_e2e = ev4.elapsed_time(ev5)
+            e2e_mode = ("double-buffered frames on every rank: 1/N of frame k+1 per PCIe link, then copy-engine pushes into the "
+                        "peers' mesh buffers over NVLink (b200cd_mesh_update_slice_async), overlapping build + query of frame k; "
+                        "one whole-mesh H2D (summed over ranks) and one D2H per step inside the timed region")
+            prunner.part.mesh = mesh
+            torch.cuda.synchronize()
+            dist.barrier()
+            pm.close()
+            dist.barrier()                                # nobody frees a frame another rank still has mapped
+        frames[1].destroy()
 
     # ---- max over ranks
     t = torch.tensor([ms_total, ms_e2e, ms_e2e_serial], dtype=torch.float64, device=dev)
@@ -478,8 +514,9 @@ def run_gpu_arm(args, workload):
                        "morton_box": "unit cube" if box else "reference constants (morton.h:45,51,57)",
                        "key_bits": 63, "pairs": npairs_total,
                        "parallelism": "single GPU" if world == 1 else (
-                           f"partitioned x{world}: one Morton range per rank (NCCL all-to-all of (key,id)), local tree + query, "
-                           f"ghost exchange, NCCL gather + sort on rank 0" if partitioned else
+                           f"partitioned x{world}: one Morton range per rank; (key, id) exchange and ghost records "
+                           f"{'stored straight into the owners buffers over NVLink peer memory (CUDA IPC)' if prunner.peer_memory else 'over grouped NCCL send/recv'}; "
+                           f"local tree + query; one padded NCCL all-gather of the pair lists + sort on rank 0" if partitioned else
                            f"query-sharded x{world}, replicated BVH, block-cyclic chunks of {args.chunk} sorted leaves, "
                            f"NCCL gather + sort on rank 0"),
                        "l2_policy": "inputs larger than L2 (mesh + BVH >> 126 MB); no explicit flush"},

@@ -36,6 +36,7 @@ SYMBOLS = [
     "b200cd_partition_to_peers_device", "b200cd_send_ghosts_to_peers_device", "b200cd_ghost_counter_reset",
     "b200cd_ghost_counter_read", "b200cd_mesh_update_slice", "b200cd_mesh_device_buffers",
     "b200cd_obj_parse_host", "b200cd_host_array_free", "b200cd_mesh_update_async", "b200cd_mesh_wait",
+    "b200cd_mesh_ipc_export", "b200cd_mesh_set_peers", "b200cd_mesh_update_slice_async",
 ]
 
 
@@ -162,6 +163,25 @@ class Mesh:
         until wait(). Double-buffered frames: upload mesh B while mesh A is being built / queried."""
         self.ctx._chk(lib().b200cd_mesh_update_async(self.ctx.h, self.h, C.c_void_p(xyz_ptr or None),
                                                      C.c_void_p(idx_ptr or None)), "mesh_update_async")
+
+    def update_slice_async_from_ptr(self, xyz_ptr, first_vert, nverts, idx_ptr, first_tri, ntris):
+        """multi-GPU twin of update_async_from_ptr: my slice goes host -> my mesh -> every peer's mesh (set_peers),
+        all on the copy stream; wait() returns when it has landed everywhere"""
+        self.ctx._chk(lib().b200cd_mesh_update_slice_async(self.ctx.h, self.h, C.c_void_p(xyz_ptr or None), C.c_uint32(first_vert),
+                                                           C.c_uint32(nverts), C.c_void_p(idx_ptr or None), C.c_uint32(first_tri),
+                                                           C.c_uint32(ntris)), "mesh_update_slice_async")
+
+    def ipc_export(self):
+        """(128 handle bytes, [2 offsets]) of the vertex and index buffers, for the other ranks' ipc_open"""
+        handles = (C.c_uint8 * 128)()
+        offsets = (C.c_uint64 * 2)()
+        self.ctx._chk(lib().b200cd_mesh_ipc_export(self.ctx.h, self.h, handles, offsets), "mesh_ipc_export")
+        return bytes(handles), [int(o) for o in offsets]
+
+    def set_peers(self, nranks, my_rank, peers):
+        """peers[2 * r + {0, 1}] = rank r's vertex / index buffer as mapped on this GPU (0 for my own rank)"""
+        arr = (C.c_void_p * (2 * nranks))(*[C.c_void_p(p or None) for p in peers])
+        self.ctx._chk(lib().b200cd_mesh_set_peers(self.ctx.h, self.h, C.c_uint32(nranks), C.c_uint32(my_rank), arr), "mesh_set_peers")
 
     def wait(self):
         """block until a pending asynchronous upload has landed (and raise if its index check failed)"""

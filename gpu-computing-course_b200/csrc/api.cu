@@ -210,6 +210,7 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     if (m->pending) return set_error(ctx, B200CD_E_INVALID, "mesh has an asynchronous upload in flight: call b200cd_mesh_wait first");
     b->params = *p;
     b->built = false;
+    b->unshared_verts = 2ull * m->nverts >= 3ull * m->ntris;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
     int npass = 0;
     if (n && !keys_given) {
@@ -223,7 +224,7 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
         // them off - tuning / A-B knob). Without them the build gathers indices and vertices itself.
         // Worth it when vertices are (mostly) unshared - a triangle soup, V = 3N: -0.21 ms in the tree build for
         // +0.11 ms in K1 at 16 M. On a mesh (V ~ N/2) the vertex gathers hit L2 anyway and the records only add traffic.
-        const bool want_recs = leaf_records_enabled() && 2ull * m->nverts >= 3ull * n;
+        const bool want_recs = leaf_records_enabled() && b->unshared_verts;
         if (!want_recs && b->d_recs) { cudaFree(b->d_recs); b->d_recs = nullptr; }
         if (!b->d_recs && want_recs && cudaMalloc(reinterpret_cast<void**>(&b->d_recs), sizeof(LeafRec) * (size_t)n) != cudaSuccess) {
             cudaGetLastError();
@@ -966,6 +967,89 @@ API int b200cd_ipc_close(b200cd_ctx* ctx, void* d_ptr) {
     if (!ctx) return B200CD_E_INVALID;
     DeviceGuard g(ctx->device);
     CD_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return B200CD_OK;
+}
+
+// ---- the mesh itself over peer memory: every rank uploads 1/ranks of a frame over its own PCIe link and copies
+// that slice into the other ranks' mesh buffers with the copy engines (NVLink), all on the copy stream, so the
+// next frame travels while the current one is being built and queried (b200cd_mesh_update_slice_async).
+
+API int b200cd_mesh_ipc_export(b200cd_ctx* ctx, b200cd_mesh* mesh, uint8_t* handles_out /* 2 x 64 bytes */, uint64_t* offsets_out /* 2 */) {
+    if (!ctx || !mesh || !handles_out || !offsets_out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    DeviceGuard g(ctx->device);
+    void* ptrs[2] = {mesh->d_verts, mesh->d_idx};
+    for (int i = 0; i < 2; ++i) {
+        cudaIpcMemHandle_t h;
+        CD_CUDA(ctx, cudaIpcGetMemHandle(&h, ptrs[i]));
+        memcpy(handles_out + 64 * i, &h, 64);
+        void* base = nullptr;
+        size_t size = 0;
+        if (cuMemGetAddressRange_shim(&base, &size, ptrs[i]) != 0) return set_error(ctx, B200CD_E_CUDA, "address range query failed");
+        offsets_out[i] = (uint64_t)((char*)ptrs[i] - (char*)base);
+    }
+    return B200CD_OK;
+}
+
+/* peers[2 * r + {0,1}] = rank r's vertex (float4) and index buffers as mapped on THIS GPU (b200cd_ipc_open + offset);
+ * the entries of my_rank are ignored. */
+API int b200cd_mesh_set_peers(b200cd_ctx* ctx, b200cd_mesh* mesh, uint32_t nranks, uint32_t my_rank, void* const* peers) {
+    if (!ctx || !mesh || !peers || nranks == 0 || nranks > 16 || my_rank >= nranks) return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    mesh->npeers = nranks;
+    mesh->my_rank = my_rank;
+    for (uint32_t r = 0; r < nranks; ++r) {
+        mesh->peer_verts[r] = r == my_rank ? mesh->d_verts : static_cast<float4*>(peers[2 * r]);
+        mesh->peer_idx[r] = r == my_rank ? mesh->d_idx : static_cast<uint32_t*>(peers[2 * r + 1]);
+        if (!mesh->peer_verts[r] || !mesh->peer_idx[r]) return set_error(ctx, B200CD_E_INVALID, "NULL peer buffer");
+    }
+    return B200CD_OK;
+}
+
+/* Asynchronous twin of b200cd_mesh_update_slice for double-buffered frames on several GPUs: the slice goes
+ * host -> my mesh (H2D, expansion, index check) and from there into every peer's copy of the mesh (D2D over
+ * NVLink, copy engines), all on the copy stream. b200cd_mesh_wait(mesh) returns when MY slice has landed
+ * everywhere; a barrier across the ranks after it (any collective) then guarantees the whole frame is in place.
+ * The caller must not start this before every rank has finished the last build that read this mesh object
+ * (true at the start of step k for the mesh of step k-1 when the steps end with a collective). */
+API int b200cd_mesh_update_slice_async(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, uint32_t first_vert, uint32_t nverts,
+                                       const uint32_t* tri_idx, uint32_t first_tri, uint32_t ntris) {
+    if (!ctx || !mesh || (nverts && !xyz) || (ntris && !tri_idx)) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if ((uint64_t)first_vert + nverts > mesh->nverts || (uint64_t)first_tri + ntris > mesh->ntris)
+        return set_error(ctx, B200CD_E_INVALID, "slice out of range");
+    if (mesh->pending) return set_error(ctx, B200CD_E_INVALID, "mesh already has an asynchronous upload in flight");
+    DeviceGuard g(ctx->device);
+    if (!ctx->copy_stream) CD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!mesh->ev_ready) {
+        CD_CUDA(ctx, cudaEventCreateWithFlags(&mesh->ev_ready, cudaEventDisableTiming));
+        CD_CUDA(ctx, cudaEventCreateWithFlags(&mesh->ev_consumed, cudaEventDisableTiming));
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&mesh->d_async_flag), sizeof(uint32_t)));
+        CD_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&mesh->h_async_flag), sizeof(uint32_t)));
+        CD_CUDA(ctx, mark_consumed(mesh, ctx->stream));
+    }
+    if (nverts && !mesh->d_stage) CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&mesh->d_stage), 12ull * mesh->nverts));
+    cudaStream_t c = ctx->copy_stream;
+    if (mesh->consumed_valid) CD_CUDA(ctx, cudaStreamWaitEvent(c, mesh->ev_consumed, 0));
+    *mesh->h_async_flag = 0;
+    if (nverts) {
+        CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_stage, xyz, 12ull * nverts, cudaMemcpyHostToDevice, c));
+        launch_expand_verts(mesh->d_stage, mesh->d_verts + first_vert, nverts, c);
+    }
+    if (ntris) {
+        CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_idx + 3ull * first_tri, tri_idx, 12ull * ntris, cudaMemcpyHostToDevice, c));
+        launch_check_idx(mesh->d_idx + 3ull * first_tri, ntris, mesh->nverts, mesh->d_async_flag, ctx->sm_count, c);
+        CD_CUDA(ctx, cudaMemcpyAsync(mesh->h_async_flag, mesh->d_async_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c));
+    }
+    for (uint32_t d = 1; d < mesh->npeers; ++d) {  // staggered: rank r starts with r+1, so no two ranks hit the same GPU at once
+        const uint32_t r = (mesh->my_rank + d) % mesh->npeers;
+        if (nverts)
+            CD_CUDA(ctx, cudaMemcpyAsync(mesh->peer_verts[r] + first_vert, mesh->d_verts + first_vert, sizeof(float4) * (size_t)nverts,
+                                         cudaMemcpyDefault, c));
+        if (ntris)
+            CD_CUDA(ctx, cudaMemcpyAsync(mesh->peer_idx[r] + 3ull * first_tri, mesh->d_idx + 3ull * first_tri, 12ull * ntris,
+                                         cudaMemcpyDefault, c));
+    }
+    CD_CUDA(ctx, cudaEventRecord(mesh->ev_ready, c));
+    CD_CUDA(ctx, cudaGetLastError());
+    mesh->pending = true;
     return B200CD_OK;
 }
 

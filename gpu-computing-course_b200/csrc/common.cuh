@@ -81,6 +81,10 @@ struct b200cd_mesh {
     uint32_t* h_async_flag = nullptr;
     bool pending = false;               // an asynchronous upload has been enqueued and not yet waited for
     bool consumed_valid = false;
+    // multi-GPU: the same mesh object on the other ranks' GPUs (CUDA-IPC mappings), b200cd_mesh_set_peers
+    uint32_t npeers = 0, my_rank = 0;
+    float4* peer_verts[16] = {};
+    uint32_t* peer_idx[16] = {};
 };
 
 namespace b200cd {
@@ -100,6 +104,7 @@ struct b200cd_bvh {
     uint64_t ghost_out_cap = 0;
     uint32_t nverts = 0;
     bool built = false;
+    bool unshared_verts = false;  // mesh with (mostly) unshared vertices, V >= 1.5 N: a triangle soup (set by the build)
     b200cd_params params{};
     // sort buffers (ping-pong); sorted result is in d_keys[cur] / d_ids[cur]
     uint64_t* d_keys[2] = {nullptr, nullptr};

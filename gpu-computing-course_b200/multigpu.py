@@ -575,3 +575,75 @@ def upload_mesh_sharded(ctx, mesh, xyz_host_ptr, idx_host_ptr, group=None):
     dist.all_gather_into_tensor(verts, verts[4 * cv * rank:4 * cv * (rank + 1)], group=group)
     dist.all_gather_into_tensor(idx, idx[3 * ct * rank:3 * ct * (rank + 1)], group=group)
     return 12 * nv + 12 * nt
+
+
+class PeerMeshFrames:
+    """Double-buffered mesh frames on several GPUs (one process per GPU).
+
+    Every rank holds the same list of mesh objects (normally two). upload_async(k, ...) sends THIS rank's
+    1/world slice of a frame host -> own GPU over its own PCIe link and from there into the peers' copies of
+    mesh k with the copy engines over NVLink (CUDA-IPC peer memory), on the context's copy stream - no NCCL, no SMs -
+    so frame k+1 travels while frame k is built and queried. wait(k) blocks until my slice has landed
+    everywhere and then passes a barrier, after which the whole frame is in place on every rank.
+    `ok` is False when CUDA IPC is unavailable on any rank (use upload_mesh_sharded then)."""
+
+    def __init__(self, cd, ctx, meshes, group=None):
+        self.cd, self.ctx, self.meshes, self.group = cd, ctx, list(meshes), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device("cuda", ctx.device)
+        self._mapped = []
+        self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ok, err, mine = 1, "", []
+        try:
+            mine = [m.ipc_export() for m in self.meshes]
+        except Exception as e:  # noqa: BLE001
+            ok, err = 0, str(e)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (ok, mine), group=group)
+        ok = int(all(e[0] for e in everyone))
+        if ok:
+            try:
+                for k, m in enumerate(self.meshes):
+                    peers = [0] * (2 * self.world)
+                    for r, (_, exported) in enumerate(everyone):
+                        if r == self.rank:
+                            continue
+                        handles, offsets = exported[k]
+                        for i in range(2):
+                            base = ctx.ipc_open(handles[64 * i:64 * i + 64])
+                            self._mapped.append(base)
+                            peers[2 * r + i] = base + offsets[i]
+                    m.set_peers(self.world, self.rank, peers)
+            except Exception as e:  # noqa: BLE001
+                ok, err = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(int(flag.item()))
+        self.error = err
+        if not self.ok:
+            self.close()
+
+    def slice_of(self, mesh):
+        V, N = mesh.nverts, mesh.ntris
+        cv, ct = (V + self.world - 1) // self.world, (N + self.world - 1) // self.world
+        v0, t0 = min(cv * self.rank, V), min(ct * self.rank, N)
+        return v0, min(cv, V - v0), t0, min(ct, N - t0)
+
+    def upload_async(self, k, xyz_host_ptr, idx_host_ptr):
+        """my slice of frame k: host -> my GPU -> every peer (returns at once). xyz_host_ptr / idx_host_ptr: the WHOLE
+        frame in pinned host memory of this rank. Returns the bytes this rank pushes over PCIe."""
+        m = self.meshes[k]
+        v0, nv, t0, nt = self.slice_of(m)
+        m.update_slice_async_from_ptr(xyz_host_ptr + 12 * v0, v0, nv, idx_host_ptr + 12 * t0, t0, nt)
+        return 12 * nv + 12 * nt
+
+    def wait(self, k):
+        """frame k is complete on every rank when this returns (host-blocking on my own copies, then a barrier)"""
+        self.meshes[k].wait()
+        dist.all_reduce(self._token, group=self.group)
+        return self.meshes[k]
+
+    def close(self):
+        for base in self._mapped:
+            self.ctx.ipc_close(base)
+        self._mapped = []

@@ -182,6 +182,18 @@ int b200cd_mesh_wait(b200cd_ctx* ctx, b200cd_mesh* mesh);
  * carry 16 elements of padding so equal chunks of ceil(n / ranks) fit). */
 int b200cd_mesh_update_slice(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, uint32_t first_vert, uint32_t nverts,
                              const uint32_t* tri_idx, uint32_t first_tri, uint32_t ntris);
+/* Several GPUs, double-buffered frames: b200cd_mesh_ipc_export gives the CUDA-IPC handles (2 x 64 bytes) and
+ * offsets (2) of the mesh's vertex and index buffers; every other rank maps them (b200cd_ipc_open) and hands the
+ * mapped addresses to b200cd_mesh_set_peers (peers[2 * r + {0, 1}] = rank r's vertex / index buffer as seen from
+ * this GPU). b200cd_mesh_update_slice_async then uploads this rank's slice over its own PCIe link AND copies it into
+ * every peer's mesh with the copy engines over NVLink, all on the copy stream, returning at once;
+ * b200cd_mesh_wait(mesh) blocks until this rank's slice has landed everywhere (index check as for
+ * b200cd_mesh_update_async), and a collective across the ranks after it means the whole frame is in place.
+ * Not before every rank has finished its last build from this mesh object. */
+int b200cd_mesh_ipc_export(b200cd_ctx* ctx, b200cd_mesh* mesh, uint8_t* handles_out, uint64_t* offsets_out);
+int b200cd_mesh_set_peers(b200cd_ctx* ctx, b200cd_mesh* mesh, uint32_t nranks, uint32_t my_rank, void* const* peers);
+int b200cd_mesh_update_slice_async(b200cd_ctx* ctx, b200cd_mesh* mesh, const float* xyz, uint32_t first_vert, uint32_t nverts,
+                                   const uint32_t* tri_idx, uint32_t first_tri, uint32_t ntris);
 /* float4[nverts + 16] (xyz, w = 0) and uint32[3 * (ntris + 16)] on the context's GPU */
 int b200cd_mesh_device_buffers(b200cd_ctx* ctx, b200cd_mesh* mesh, void** d_verts4, void** d_idx);
 int b200cd_mesh_info(const b200cd_mesh* mesh, uint32_t* nverts, uint32_t* ntris);

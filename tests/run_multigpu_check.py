@@ -25,6 +25,26 @@ for name, (xyz, idx), box in (("soup4m", mg.soup(1 << 22, seed=5), ((0,0,0),(1,1
     x2, i2 = mesh.download()
     assert np.array_equal(x2, xyz) and np.array_equal(i2, idx), "sharded upload mismatch"
     if rank == 0: print(name, "sharded upload OK", flush=True)
+    # double-buffered frames over peer memory: every rank pushes its slice of each frame into all the others
+    fr = [ctx.mesh_from_arrays(np.zeros_like(xyz), np.zeros_like(idx)) for _ in range(2)]
+    pm = mgpu.PeerMeshFrames(cd, ctx, fr)
+    if pm.ok:
+        hx, hx_ptr = cd.pinned_array(xyz.shape, np.float32); hi, hi_ptr = cd.pinned_array(idx.shape, np.uint32)
+        hx2, hx2_ptr = cd.pinned_array(xyz.shape, np.float32)
+        hx[:] = xyz; hi[:] = idx; hx2[:] = xyz[::-1]
+        pm.upload_async(0, hx_ptr, hi_ptr); pm.upload_async(1, hx2_ptr, hi_ptr)
+        for k, want in ((0, xyz), (1, xyz[::-1])):
+            x2, i2 = pm.wait(k).download()
+            assert np.array_equal(x2, want) and np.array_equal(i2, idx), f"peer-memory frame {k} mismatch"
+        pm.upload_async(0, hx2_ptr, hi_ptr)              # reuse of a frame object
+        x2, _ = pm.wait(0).download()
+        assert np.array_equal(x2, xyz[::-1])
+        if rank == 0: print(name, "peer-memory frames OK", flush=True)
+        torch.cuda.synchronize(); dist.barrier(); pm.close(); dist.barrier()
+    elif rank == 0:
+        print(name, "peer-memory frames SKIPPED:", pm.error, flush=True)
+    for m in fr:
+        m.destroy()
     bvh = ctx.bvh_build(mesh, p)
     sh = mgpu.ShardedSelfCollision(cd, ctx)
     ref = sh.step(bvh, mesh, p)
