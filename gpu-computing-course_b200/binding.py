@@ -36,7 +36,7 @@ SYMBOLS = [
     "b200cd_partition_to_peers_device", "b200cd_send_ghosts_to_peers_device", "b200cd_ghost_counter_reset",
     "b200cd_ghost_counter_read", "b200cd_mesh_update_slice", "b200cd_mesh_device_buffers",
     "b200cd_obj_parse_host", "b200cd_host_array_free", "b200cd_mesh_update_async", "b200cd_mesh_wait",
-    "b200cd_mesh_ipc_export", "b200cd_mesh_set_peers", "b200cd_mesh_update_slice_async",
+    "b200cd_mesh_ipc_export", "b200cd_mesh_set_peers", "b200cd_mesh_update_slice_async", "b200cd_partition_plan_device",
 ]
 
 
@@ -376,6 +376,11 @@ class Context:
     def key_histogram_device(self, d_keys, count, shift, d_hist):
         self._chk(lib().b200cd_key_histogram_device(self.h, C.c_void_p(d_keys), C.c_uint32(count), C.c_int32(shift),
                                                     C.c_void_p(d_hist)), "key_histogram_device")
+
+    def partition_plan_device(self, d_global_hist, d_local_hist, shift, world, d_splitters, d_counts):
+        self._chk(lib().b200cd_partition_plan_device(self.h, C.c_void_p(d_global_hist), C.c_void_p(d_local_hist), C.c_int32(shift),
+                                                     C.c_uint32(world), C.c_void_p(d_splitters or None), C.c_void_p(d_counts)),
+                  "partition_plan_device")
 
     def bvh_alloc_partial(self, capacity, ghost_capacity, max_peers):
         b = C.c_void_p()

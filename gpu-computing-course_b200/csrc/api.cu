@@ -348,6 +348,13 @@ API int b200cd_destroy(b200cd_ctx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
+    for (int i = 0; i < 4; ++i) {
+        if (ctx->push_stream[i]) {
+            cudaStreamSynchronize(ctx->push_stream[i]);
+            cudaStreamDestroy(ctx->push_stream[i]);
+            cudaEventDestroy(ctx->push_ev[i]);
+        }
+    }
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaFree(ctx->d_scalars);
@@ -838,6 +845,18 @@ API int b200cd_key_histogram_device(b200cd_ctx* ctx, const void* d_keys, uint32_
     return B200CD_OK;
 }
 
+API int b200cd_partition_plan_device(b200cd_ctx* ctx, const void* d_global_hist65536, const void* d_local_hist65536, int32_t shift,
+                                     uint32_t world, void* d_splitters_out, void* d_counts_out) {
+    if (!ctx || !d_global_hist65536 || !d_local_hist65536 || !d_counts_out || (world > 1 && !d_splitters_out) || world == 0 ||
+        world > RS_MAX_SPLIT_P1 || shift < 0 || shift > 47)
+        return set_error(ctx, B200CD_E_INVALID, "bad argument");
+    DeviceGuard g(ctx->device);
+    launch_partition_plan(static_cast<const uint32_t*>(d_global_hist65536), static_cast<const uint32_t*>(d_local_hist65536), shift,
+                          (int)world, static_cast<uint64_t*>(d_splitters_out), static_cast<int32_t*>(d_counts_out), ctx->stream);
+    CD_CUDA(ctx, cudaGetLastError());
+    return B200CD_OK;
+}
+
 API int b200cd_bvh_alloc_partial(b200cd_ctx* ctx, uint32_t capacity, uint64_t ghost_capacity, uint32_t max_peers,
                                  b200cd_bvh** out) {
     if (!ctx || !out || max_peers > 32) return set_error(ctx, B200CD_E_INVALID, "bad argument");
@@ -1027,25 +1046,47 @@ API int b200cd_mesh_update_slice_async(b200cd_ctx* ctx, b200cd_mesh* mesh, const
     }
     if (nverts && !mesh->d_stage) CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&mesh->d_stage), 12ull * mesh->nverts));
     cudaStream_t c = ctx->copy_stream;
+    constexpr int NPUSH = 4;
+    for (int i = 0; i < NPUSH; ++i) {
+        if (!ctx->push_stream[i]) {
+            CD_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->push_stream[i], cudaStreamNonBlocking));
+            CD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->push_ev[i], cudaEventDisableTiming));
+        }
+    }
     if (mesh->consumed_valid) CD_CUDA(ctx, cudaStreamWaitEvent(c, mesh->ev_consumed, 0));
     *mesh->h_async_flag = 0;
-    if (nverts) {
-        CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_stage, xyz, 12ull * nverts, cudaMemcpyHostToDevice, c));
-        launch_expand_verts(mesh->d_stage, mesh->d_verts + first_vert, nverts, c);
+    // The slice moves in NPUSH chunks: chunk i's H2D (+ expansion) runs on the copy stream while push stream i
+    // copies the chunks that have landed into the peers' meshes - the PCIe transfer and the NVLink pushes overlap,
+    // and the pushes of different chunks use different copy engines.
+    if (ntris) CD_CUDA(ctx, cudaMemsetAsync(mesh->d_async_flag, 0, sizeof(uint32_t), c));
+    for (int i = 0; i < NPUSH; ++i) {
+        const uint32_t v0 = (uint32_t)((uint64_t)nverts * i / NPUSH), v1 = (uint32_t)((uint64_t)nverts * (i + 1) / NPUSH);
+        const uint32_t t0 = (uint32_t)((uint64_t)ntris * i / NPUSH), t1 = (uint32_t)((uint64_t)ntris * (i + 1) / NPUSH);
+        if (v1 > v0) {
+            CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_stage + 3ull * v0, xyz + 3ull * v0, 12ull * (v1 - v0), cudaMemcpyHostToDevice, c));
+            launch_expand_verts(mesh->d_stage + 3ull * v0, mesh->d_verts + first_vert + v0, v1 - v0, c);
+        }
+        if (t1 > t0) {
+            CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_idx + 3ull * (first_tri + t0), tri_idx + 3ull * t0, 12ull * (t1 - t0), cudaMemcpyHostToDevice, c));
+            launch_check_idx_accumulate(mesh->d_idx + 3ull * (first_tri + t0), t1 - t0, mesh->nverts, mesh->d_async_flag, ctx->sm_count, c);
+        }
+        CD_CUDA(ctx, cudaEventRecord(ctx->push_ev[i], c));
+        cudaStream_t ps = ctx->push_stream[i];
+        CD_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->push_ev[i], 0));
+        for (uint32_t d = 1; d < mesh->npeers; ++d) {  // staggered: rank r starts with r+1, so no two ranks hit the same GPU at once
+            const uint32_t r = (mesh->my_rank + d) % mesh->npeers;
+            if (v1 > v0)
+                CD_CUDA(ctx, cudaMemcpyAsync(mesh->peer_verts[r] + first_vert + v0, mesh->d_verts + first_vert + v0,
+                                             sizeof(float4) * (size_t)(v1 - v0), cudaMemcpyDefault, ps));
+            if (t1 > t0)
+                CD_CUDA(ctx, cudaMemcpyAsync(mesh->peer_idx[r] + 3ull * (first_tri + t0), mesh->d_idx + 3ull * (first_tri + t0),
+                                             12ull * (t1 - t0), cudaMemcpyDefault, ps));
+        }
     }
-    if (ntris) {
-        CD_CUDA(ctx, cudaMemcpyAsync(mesh->d_idx + 3ull * first_tri, tri_idx, 12ull * ntris, cudaMemcpyHostToDevice, c));
-        launch_check_idx(mesh->d_idx + 3ull * first_tri, ntris, mesh->nverts, mesh->d_async_flag, ctx->sm_count, c);
-        CD_CUDA(ctx, cudaMemcpyAsync(mesh->h_async_flag, mesh->d_async_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c));
-    }
-    for (uint32_t d = 1; d < mesh->npeers; ++d) {  // staggered: rank r starts with r+1, so no two ranks hit the same GPU at once
-        const uint32_t r = (mesh->my_rank + d) % mesh->npeers;
-        if (nverts)
-            CD_CUDA(ctx, cudaMemcpyAsync(mesh->peer_verts[r] + first_vert, mesh->d_verts + first_vert, sizeof(float4) * (size_t)nverts,
-                                         cudaMemcpyDefault, c));
-        if (ntris)
-            CD_CUDA(ctx, cudaMemcpyAsync(mesh->peer_idx[r] + 3ull * first_tri, mesh->d_idx + 3ull * first_tri, 12ull * ntris,
-                                         cudaMemcpyDefault, c));
+    if (ntris) CD_CUDA(ctx, cudaMemcpyAsync(mesh->h_async_flag, mesh->d_async_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c));
+    for (int i = 0; i < NPUSH; ++i) {  // the copy stream (and ev_ready on it) waits for every push stream
+        CD_CUDA(ctx, cudaEventRecord(ctx->push_ev[i], ctx->push_stream[i]));
+        CD_CUDA(ctx, cudaStreamWaitEvent(c, ctx->push_ev[i], 0));
     }
     CD_CUDA(ctx, cudaEventRecord(mesh->ev_ready, c));
     CD_CUDA(ctx, cudaGetLastError());

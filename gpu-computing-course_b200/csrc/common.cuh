@@ -55,6 +55,8 @@ struct b200cd_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // b200cd_mesh_update_async: uploads that overlap the build / query of another mesh
+    cudaStream_t push_stream[4] = {};    // b200cd_mesh_update_slice_async: peer pushes (several copy engines at once)
+    cudaEvent_t push_ev[4] = {};         // chunk c's H2D has landed / push stream p has drained
     int sm_count = 148;
     b200cd_stats stats{};
     std::string last_error;
@@ -195,6 +197,7 @@ int obj_parse(const char* path, std::vector<float>& xyz, std::vector<uint32_t>& 
 // morton.cu
 void launch_expand_verts(const float* d_xyz, float4* d_verts, uint32_t nverts, cudaStream_t s);
 void launch_check_idx(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, uint32_t* d_flag, int sms, cudaStream_t s);
+void launch_check_idx_accumulate(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, uint32_t* d_flag, int sms, cudaStream_t s);
 void launch_bbox(const float4* d_verts, uint32_t nverts, uint32_t* d_bbox6 /*ordered-uint min3,max3*/, int sms, cudaStream_t s);
 // d_recs (optional): also write every triangle's LeafRec, in face order (slice-relative like d_keys)
 void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t first, uint32_t n, const b200cd_params& p,
@@ -248,6 +251,8 @@ void launch_export_nodes(const NodePair* d_pairs, const float* d_root_box, uint3
 void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, const uint64_t* d_keys,
                      uint32_t n, uint32_t nverts, uint32_t* d_scratch, uint32_t* d_checks9, cudaStream_t s);
 // partition.cu (partitioned multi-GPU build)
+void launch_partition_plan(const uint32_t* d_ghist, const uint32_t* d_lhist, int shift, int world, uint64_t* d_splitters,
+                           int32_t* d_counts, cudaStream_t s);
 void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist65536, int sms, cudaStream_t s);
 // d_scratch: K*6 + 1 words
 void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t K, uint32_t* d_scratch,

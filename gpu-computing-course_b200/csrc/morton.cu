@@ -48,6 +48,15 @@ void launch_check_idx(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, ui
     count_launch();
 }
 
+// same check without clearing the flag first: several slices OR their verdicts into one word
+void launch_check_idx_accumulate(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, uint32_t* d_flag, int sms, cudaStream_t s) {
+    if (!ntris) return;
+    uint64_t count = 3ull * ntris;
+    uint32_t blocks = (uint32_t)std::min<uint64_t>((count + 255) / 256, (uint64_t)sms * 16);
+    check_idx_kernel<<<blocks, 256, 0, s>>>(d_idx, count, nverts, d_flag);
+    count_launch();
+}
+
 // ---- bounding box of all vertices (auto Morton box). Order-preserving uint encoding
 // of floats lets plain integer atomicMin/atomicMax do the reduction.
 __device__ __forceinline__ uint32_t f2ord(float f) {

@@ -206,6 +206,76 @@ ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __rest
     }
 }
 
+// Range plan of the partitioned build in ONE launch (one block): from the all-reduced 65536-bin histogram of the
+// keys' top bits, the world-1 splitters that cut the keys into equal shares - splitter r-1 is the first bin
+// boundary at which the cumulative count reaches r * total / world - and, from this rank's own histogram, how
+// many of ITS keys each rank will own (the splitters sit on bin boundaries, so no second pass over the keys).
+constexpr int PP_THREADS = 1024, PP_BINS = 65536, PP_PER = PP_BINS / PP_THREADS;
+__device__ __forceinline__ uint64_t pp_block_exclusive(uint64_t v, uint64_t* s_w, uint64_t& total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    __syncthreads();  // s_w may still be read from a previous call
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint64_t base = 0, tot = 0;
+    for (int w = 0; w < PP_THREADS / 32; ++w) {
+        const uint64_t x = s_w[w];
+        if (w < (int)warp) base += x;
+        tot += x;
+    }
+    total = tot;
+    return base + incl - v;
+}
+__global__ void __launch_bounds__(PP_THREADS)
+partition_plan_kernel(const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ lhist, int shift, int world,
+                      uint64_t* __restrict__ splitters, int32_t* __restrict__ counts) {
+    __shared__ uint64_t s_w[PP_THREADS / 32];
+    __shared__ uint32_t s_bin[RS_MAX_SPLIT_P1];
+    __shared__ uint64_t s_lc[RS_MAX_SPLIT_P1];
+    const uint32_t tid = threadIdx.x, b0 = tid * PP_PER;
+    uint64_t sum = 0;
+    for (int k = 0; k < PP_PER; ++k) sum += ghist[b0 + k];
+    uint64_t total;
+    const uint64_t excl = pp_block_exclusive(sum, s_w, total);
+    for (int r = 1; r < world; ++r) {
+        const uint64_t target = (uint64_t)r * total / (uint64_t)world;
+        // first bin whose cumulative count reaches the target (bin 0 for an empty histogram)
+        if (target == 0 ? tid == 0 : (excl < target && target <= excl + sum)) {
+            uint32_t bin = b0;
+            uint64_t run = excl;
+            for (int k = 0; k < PP_PER; ++k) {
+                run += ghist[b0 + k];
+                if (run >= target) { bin = b0 + k; break; }
+            }
+            s_bin[r - 1] = min(bin, (uint32_t)PP_BINS - 2u);  // keys beyond the histogram's range share the last bin
+        }
+    }
+    __syncthreads();
+    uint64_t lsum = 0;
+    for (int k = 0; k < PP_PER; ++k) lsum += lhist[b0 + k];
+    uint64_t ltotal;
+    const uint64_t lexcl = pp_block_exclusive(lsum, s_w, ltotal);
+    for (int r = 1; r < world; ++r) {
+        const uint32_t bin = s_bin[r - 1];
+        if (bin / PP_PER == tid) {  // my own keys in the bins [0, bin]
+            uint64_t run = lexcl;
+            for (uint32_t k = 0; k <= bin % PP_PER; ++k) run += lhist[b0 + k];
+            s_lc[r - 1] = run;
+        }
+    }
+    __syncthreads();
+    if (tid < (uint32_t)world) {
+        const uint64_t hi = tid + 1 < (uint32_t)world ? s_lc[tid] : ltotal, lo = tid ? s_lc[tid - 1] : 0;
+        counts[tid] = (int32_t)(hi - lo);
+        if (tid + 1 < (uint32_t)world) splitters[tid] = (uint64_t)(s_bin[tid] + 1u) << shift;  // keys >= splitter r-1 belong to rank >= r
+    }
+}
+
 // overall[p] = union of peer p's K coarse boxes (one warp per peer)
 __global__ void __launch_bounds__(32)
 peer_overall_kernel(const float* __restrict__ peer_boxes, uint32_t K, float* __restrict__ overall) {
@@ -229,6 +299,12 @@ peer_overall_kernel(const float* __restrict__ peer_boxes, uint32_t K, float* __r
 }
 
 }  // namespace
+
+void launch_partition_plan(const uint32_t* d_ghist, const uint32_t* d_lhist, int shift, int world, uint64_t* d_splitters,
+                           int32_t* d_counts, cudaStream_t s) {
+    partition_plan_kernel<<<1, PP_THREADS, 0, s>>>(d_ghist, d_lhist, shift, world, d_splitters, d_counts);
+    count_launch();
+}
 
 void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist, int sms, cudaStream_t s) {
     if (!n) return;

@@ -388,6 +388,8 @@ class PartitionedSelfCollision:
                 self.peer_memory = False
             else:
                 self._counts_dev = torch.zeros(self.world, dtype=torch.int32, device=self.device)
+                self._ghist = torch.zeros(65536, dtype=torch.int32, device=self.device)
+                self._splitters = torch.zeros(max(self.world - 1, 1), dtype=torch.int64, device=self.device)
                 self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
                 dist.barrier(group=group)
 
@@ -410,25 +412,26 @@ class PartitionedSelfCollision:
                 marks.append((name, time.perf_counter()))
         mark("start")
         ctx.ghost_counter_reset(p.bvh)
-        hist = p.keys_and_histogram()
-        local_csum = torch.cumsum(hist, 0, dtype=torch.int64)  # my own keys per top-bits bin, before the all-reduce
-        dist.all_reduce(hist, group=g)  # also orders every rank's counter reset before any ghost append of this step
+        hist = p.keys_and_histogram()                                  # my own keys per top-bits bin
+        ghist = self._ghist
+        ghist.copy_(hist)
+        dist.all_reduce(ghist, group=g)  # also orders every rank's counter reset before any ghost append of this step
         mark("keys+hist+allreduce")
-        splitters = p.splitters_from(hist)
-        # the splitters sit on bin boundaries, so how many of MY keys each rank owns follows from my own
-        # histogram - no second pass over the keys
-        bounds = torch.cat([local_csum[p.split_bins], local_csum[-1:]])
-        self._counts_dev = torch.diff(bounds, prepend=bounds.new_zeros(1)).to(torch.int32).contiguous()
+        # splitters from the global histogram and - they sit on bin boundaries - how many of MY keys each rank owns from
+        # my own histogram, in one launch (b200cd_partition_plan_device; PartitionedRank.splitters_from is the torch twin)
+        splitters = self._splitters
+        ctx.partition_plan_device(ghist.data_ptr(), hist.data_ptr(), p.shift, w, splitters.data_ptr(), self._counts_dev.data_ptr())
         allc = torch.empty(w * w, dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(allc, self._counts_dev, group=g)
         allc = allc.view(w, w)                                         # [source rank][owner rank]
         recv_off = allc[:r].sum(0, dtype=torch.int32).contiguous()     # my segment's start in every owner's buffer
-        totals_t = allc.sum(0)
-        ctx.partition_to_peers_device(p.bvh, p.keys.data_ptr(), p.lo, p.cnt, splitters.data_ptr(), w - 1, recv_off.data_ptr())
-        totals = totals_t.tolist()                                     # (every rank sees every range's size: all raise together)
+        totals = allc.sum(0).tolist()                                  # (every rank sees every range's size: all raise together)
+        # read BEFORE the partition kernel is launched: the host then waits for the count all-gather only and the
+        # partition kernel, the barrier and the build's kernels are enqueued back to back behind it
         p.nlocal = int(totals[r])
         if max(totals) > p.cap:
             raise RuntimeError(f"a Morton range holds {max(totals)} triangles, capacity {p.cap}: raise slack (very uneven mesh)")
+        ctx.partition_to_peers_device(p.bvh, p.keys.data_ptr(), p.lo, p.cnt, splitters.data_ptr(), w - 1, recv_off.data_ptr())
         self._barrier()                                                # all (key, id) stores have landed
         mark("partition+exchange (fused)")
         boxes = p.build()

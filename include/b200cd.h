@@ -293,6 +293,11 @@ int b200cd_key_histogram_device(b200cd_ctx* ctx, const void* d_keys, uint32_t co
                                 void* d_hist65536 /* 65536 x u32, accumulated into */);
 /* BVH with room for `capacity` local triangles, `ghost_capacity` received ghost records and
  * `max_peers` outgoing ghost lists of `ghost_capacity` records each. */
+/* The range plan in one launch: from the all-reduced histogram (b200cd_key_histogram_device, summed over the ranks) the
+ * world-1 splitters (uint64, ascending; keys >= splitter r-1 belong to rank >= r) that give every rank an equal share,
+ * and from this rank's own histogram how many of ITS keys each rank will own (int32[world]). */
+int b200cd_partition_plan_device(b200cd_ctx* ctx, const void* d_global_hist65536, const void* d_local_hist65536, int32_t shift,
+                                 uint32_t world, void* d_splitters_out, void* d_counts_out);
 int b200cd_bvh_alloc_partial(b200cd_ctx* ctx, uint32_t capacity, uint64_t ghost_capacity, uint32_t max_peers,
                              b200cd_bvh** out);
 int b200cd_bvh_key_buffers(b200cd_ctx* ctx, b200cd_bvh* bvh, void** d_keys, void** d_ids, uint32_t* capacity);

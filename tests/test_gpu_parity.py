@@ -303,3 +303,40 @@ def test_partitioned_build_emulated_ranks_equal_single_gpu(cd, co, ctx, mg, worl
             assert sum(s["ghosts"] for s in stats) > 0
         mesh.destroy()
     ctx.set_stream(None)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8, 16])
+def test_partition_plan_kernel_equals_torch_twin(cd, ctx, world):
+    """b200cd_partition_plan_device (splitters + per-owner counts in one launch) against the torch statement of the
+    same rule (multigpu.PartitionedRank.splitters_from + the cumulative-sum differences)"""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    shift = 44
+    g = torch.Generator(device="cpu").manual_seed(world)
+    cases = []
+    dense = torch.randint(0, 50, (65536,), generator=g, dtype=torch.int32)
+    cases.append((dense * world, dense))                                        # every rank holds the same share
+    sparse = torch.zeros(65536, dtype=torch.int32); sparse[torch.randint(0, 65536, (300,), generator=g)] = 7
+    loc = torch.zeros(65536, dtype=torch.int32); loc[::2] = sparse[::2]
+    cases.append((sparse, loc))                                                 # long runs of empty bins
+    one = torch.zeros(65536, dtype=torch.int32); one[12345] = 1000
+    cases.append((one, one // 2))                                               # everything in one bin
+    last = torch.zeros(65536, dtype=torch.int32); last[65535] = 10; last[0] = 10
+    cases.append((last, last))                                                  # the clamped last bin
+    cases.append((torch.zeros(65536, dtype=torch.int32), torch.zeros(65536, dtype=torch.int32)))  # empty
+    for gh, lh in cases:
+        gh, lh = gh.to(dev), lh.to(dev)
+        spl = torch.zeros(world - 1, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(world, dtype=torch.int32, device=dev)
+        ctx.partition_plan_device(gh.data_ptr(), lh.data_ptr(), shift, world, spl.data_ptr(), cnt.data_ptr())
+        csum = torch.cumsum(gh.to(torch.int64), 0)
+        targets = (torch.arange(1, world, device=dev, dtype=torch.int64) * csum[-1]) // world
+        bins = torch.clamp(torch.searchsorted(csum, targets), max=65534)
+        lcs = torch.cumsum(lh.to(torch.int64), 0)
+        bounds = torch.cat([lcs[bins], lcs[-1:]])
+        want_cnt = torch.diff(bounds, prepend=bounds.new_zeros(1)).to(torch.int32)
+        torch.cuda.synchronize()
+        assert torch.equal(spl, (bins + 1) << shift), (world, spl.tolist()[:4], bins.tolist()[:4])
+        assert torch.equal(cnt, want_cnt), (world, cnt.tolist(), want_cnt.tolist())
+    ctx.set_stream(None)
