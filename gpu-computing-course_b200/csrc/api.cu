@@ -1270,7 +1270,7 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
         } else {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), s));
         }
-        launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s);
+        launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s, b->unshared_verts);
         CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q2], s));
         CD_CUDA(ctx, cudaMemcpyAsync(b->h_counters, b->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CD_CUDA(ctx, cudaStreamSynchronize(s));
@@ -1356,7 +1356,7 @@ int run_ghost_query(b200cd_ctx* ctx, b200cd_bvh* b, uint64_t nghost, int keep, u
         if (need_broad)
             launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, 0, 1, B200CD_QUERY_BLOCK, nquery, /*foreign*/ 1, b->cap, b->d_entries,
                          b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s);
-        launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s);
+        launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s, b->unshared_verts);
         CD_CUDA(ctx, cudaMemcpyAsync(b->h_counters, b->d_counters, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CD_CUDA(ctx, cudaStreamSynchronize(s));
         CD_CUDA(ctx, cudaGetLastError());

@@ -183,7 +183,7 @@ entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_
 constexpr int BR_PER_WARP = 128;                       // queries per warp = one group (one entry list)
 constexpr int BR_GROUPS = BR_WARPS;                    // groups per block
 constexpr int BR_QB = BR_GROUPS * BR_PER_WARP;         // 1024 queries per block
-constexpr int BR_REFILL = 16;                          // refill when this many lanes are idle
+constexpr int BR_REFILL = 24;                          // refill when this many lanes are idle (16: 2.47 ms, 20: 2.44, 24: 2.42 at 6 CTAs/SM)
 constexpr int BR_KEEP = 32;                            // start subtrees kept per group after the union-box filter
 constexpr int BR_CQ = 128;                             // candidate staging per warp: < 64 carried + <= 64 new per step
 
@@ -634,7 +634,8 @@ __device__ __forceinline__ void narrow_stage_b(const LeafRec* __restrict__ leave
 // So: stage A (filters + 2 axes) runs dense over the candidate list, its survivors are
 // compacted into a per-warp shared-memory queue by ballot, and stage B (15 axes) runs whenever
 // 32 survivors are waiting - both stages execute with (nearly) full warps.
-__global__ void __launch_bounds__(NR_THREADS, 3)
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(NR_THREADS, MIN_BLOCKS)
 narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand, uint64_t cand_cap,
               uint2* __restrict__ out, uint64_t out_cap, unsigned long long* __restrict__ counters) {
     __shared__ uint2 queue[NR_WARPS][NR_QUEUE];
@@ -742,8 +743,20 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
 }
 
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
-                   unsigned long long* d_counters, int sms, cudaStream_t s) {
-    narrow_kernel<<<sms * 3 * 4, NR_THREADS, 0, s>>>(d_leaves, d_cand, cand_cap, d_out, out_cap, d_counters);
+                   unsigned long long* d_counters, int sms, cudaStream_t s, bool unshared_vertices) {
+    // On a mesh most candidates are vertex-sharing neighbours that leave after one 32-byte read: latency-bound, the
+    // 64-register build with 4 CTAs per SM wins (0.77 vs 0.88 ms on the 16 M sheets). On a soup every candidate runs
+    // the fp64 face-normal axes and the 64-register build spills (0.85 vs 0.83 ms). B200CD_NARROW_OCC=3/4 overrides.
+    static int force = -1;
+    if (force < 0) {
+        const char* e = getenv("B200CD_NARROW_OCC");
+        force = e ? (e[0] == '4' ? 4 : 3) : 0;
+    }
+    const int occ = force ? force : (unshared_vertices ? 3 : 4);
+    if (occ == 4)
+        narrow_kernel<4><<<sms * 4 * 4, NR_THREADS, 0, s>>>(d_leaves, d_cand, cand_cap, d_out, out_cap, d_counters);
+    else
+        narrow_kernel<3><<<sms * 3 * 4, NR_THREADS, 0, s>>>(d_leaves, d_cand, cand_cap, d_out, out_cap, d_counters);
     count_launch();
 }
 

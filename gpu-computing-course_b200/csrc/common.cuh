@@ -272,6 +272,6 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
                   uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
                   uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s);
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
-                   unsigned long long* d_counters, int sms, cudaStream_t s);
+                   unsigned long long* d_counters, int sms, cudaStream_t s, bool unshared_vertices = false);
 
 }  // namespace b200cd

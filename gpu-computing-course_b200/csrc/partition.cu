@@ -231,20 +231,34 @@ __device__ __forceinline__ uint64_t pp_block_exclusive(uint64_t v, uint64_t* s_w
     total = tot;
     return base + incl - v;
 }
+// sums of the 1024 segments of 64 consecutive bins, read with coalesced loads (a warp's 32 consecutive bins lie in
+// one segment: warp reduction, then one shared-memory atomic per warp and load)
+__device__ __forceinline__ void pp_segment_sums(const uint32_t* __restrict__ hist, uint32_t* s_seg) {
+    s_seg[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (uint32_t)PP_BINS; i += PP_THREADS) {
+        uint32_t v = __ldg(hist + i);
+        v = __reduce_add_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_seg[i / PP_PER], v);
+    }
+    __syncthreads();
+}
 __global__ void __launch_bounds__(PP_THREADS)
 partition_plan_kernel(const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ lhist, int shift, int world,
                       uint64_t* __restrict__ splitters, int32_t* __restrict__ counts) {
     __shared__ uint64_t s_w[PP_THREADS / 32];
+    __shared__ uint32_t s_seg[PP_THREADS];
     __shared__ uint32_t s_bin[RS_MAX_SPLIT_P1];
     __shared__ uint64_t s_lc[RS_MAX_SPLIT_P1];
-    const uint32_t tid = threadIdx.x, b0 = tid * PP_PER;
-    uint64_t sum = 0;
-    for (int k = 0; k < PP_PER; ++k) sum += ghist[b0 + k];
+    const uint32_t tid = threadIdx.x, b0 = tid * PP_PER;  // thread tid owns segment tid = bins [b0, b0 + 64)
+    pp_segment_sums(ghist, s_seg);
+    const uint64_t sum = s_seg[tid];
     uint64_t total;
     const uint64_t excl = pp_block_exclusive(sum, s_w, total);
     for (int r = 1; r < world; ++r) {
         const uint64_t target = (uint64_t)r * total / (uint64_t)world;
-        // first bin whose cumulative count reaches the target (bin 0 for an empty histogram)
+        // first bin whose cumulative count reaches the target (bin 0 for an empty histogram): only the owner of the
+        // segment the target falls into walks its 64 bins
         if (target == 0 ? tid == 0 : (excl < target && target <= excl + sum)) {
             uint32_t bin = b0;
             uint64_t run = excl;
@@ -256,8 +270,8 @@ partition_plan_kernel(const uint32_t* __restrict__ ghist, const uint32_t* __rest
         }
     }
     __syncthreads();
-    uint64_t lsum = 0;
-    for (int k = 0; k < PP_PER; ++k) lsum += lhist[b0 + k];
+    pp_segment_sums(lhist, s_seg);
+    const uint64_t lsum = s_seg[tid];
     uint64_t ltotal;
     const uint64_t lexcl = pp_block_exclusive(lsum, s_w, ltotal);
     for (int r = 1; r < world; ++r) {

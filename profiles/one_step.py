@@ -1,0 +1,12 @@
+import importlib, sys
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+cd = importlib.import_module("gpu-computing-course_b200.binding")
+mg = importlib.import_module("gpu-computing-course_b200.meshgen")
+lg = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+ctx = cd.Context(0)
+xyz, idx = mg.soup(1 << lg, seed=1234)
+p = cd.make_params((0,0,0),(1,1,1))
+mesh = ctx.mesh_from_arrays(xyz, idx)
+bvh = ctx.bvh_build(mesh, p)
+ptr, cnt = ctx.self_collide_device(bvh, sorted=True)
+print(cnt, ctx.stats())
