@@ -92,3 +92,64 @@ def write_obj(path, xyz, idx):
                             C.c_uint32(idx.shape[0]))
     if rc != 0:
         raise OSError(f"mg_write_obj({path}) failed: {rc}")
+
+
+def edge_cases(copies=10, seed=3, origin=REF_ORIGIN, extent=REF_EXTENT):
+    """Pairs of private triangles in the configurations where the narrow phase (reference tri_contact.cuh:19-78) and
+    the strict box test (box.cuh:40-43) are at their limits: piercing, coplanar overlap, exactly shared edges and
+    vertices, a vertex lying exactly in the other triangle's plane, crossing edges, near misses tens of fp32 ulps apart,
+    and degenerate triangles (points, segments, collinear). Every pattern is instantiated `copies` times, each copy at
+    its own lattice cell of the box with its own random rotation (so boxes have volume; one copy per pattern stays
+    axis-aligned, where flat boxes fail the STRICT overlap test and the reference reports nothing).
+    Plain numpy, deterministic; fp32 coordinates; centroids all distinct (the reference needs unique Morton codes)."""
+    rng = np.random.default_rng(seed)
+
+    def rot(k):
+        if k == 0:
+            return np.eye(3)
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+    A = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+    patterns = [
+        ("pierce", [[0.25, 0.25, -0.5], [0.25, 0.25, 0.5], [0.6, 0.1, 0.4]]),
+        ("coplanar_overlap", [[0.2, 0.2, 0.0], [1.2, 0.3, 0.0], [0.3, 1.1, 0.0]]),
+        ("coplanar_disjoint", [[1.5, 1.5, 0.0], [2.5, 1.5, 0.0], [1.5, 2.5, 0.0]]),
+        ("shared_edge_coords", [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [1.0, 1.0, 0.5]]),
+        ("shared_vertex_coords", [[1.0, 0.0, 0.0], [2.0, 0.5, 0.5], [1.5, -0.5, 0.7]]),
+        ("vertex_in_plane", [[0.25, 0.25, 0.0], [0.5, 0.5, 1.0], [0.1, 0.6, 0.8]]),
+        ("vertex_on_edge", [[0.5, 0.0, 0.0], [0.5, -1.0, 0.6], [0.9, -0.8, -0.4]]),
+        ("edges_cross", [[0.5, -0.5, 0.0], [0.5, 0.5, 0.0], [0.5, 0.0, 1.0]]),
+        ("near_miss_above", [[0.15, 0.1, 2 ** -12], [0.7, 0.15, 2 ** -12], [0.2, 0.6, 2 ** -12]]),
+        ("near_miss_side", [[1.0 + 2 ** -12, 0.0, -0.5], [1.0 + 2 ** -12, 1.0, 0.5], [1.6, 0.5, 0.0]]),
+        ("graze_below", [[0.15, 0.1, -(2 ** -12)], [0.7, 0.15, 2 ** -12], [0.2, 0.6, -(2 ** -12)]]),
+        ("point_inside", [[0.3, 0.3, 0.0]] * 3),
+        ("point_outside", [[0.3, 0.3, 0.25]] * 3),
+        ("segment_through", [[0.3, 0.3, -0.5], [0.3, 0.3, 0.5], [0.3, 0.3, -0.5]]),
+        ("collinear_in_plane", [[-0.5, 0.4, 0.0], [0.5, 0.4, 0.0], [1.5, 0.4, 0.0]]),
+        ("parallel_close", [[0.0, 0.0, 0.01], [1.0, 0.0, 0.01], [0.0, 1.0, 0.01]]),
+        ("contained_coplanar", [[0.1, 0.1, 0.0], [0.4, 0.1, 0.0], [0.1, 0.4, 0.0]]),
+    ]
+    ncell = len(patterns) * copies
+    side = int(np.ceil(ncell ** (1.0 / 3.0)))
+    o, e = np.asarray(origin, np.float64), np.asarray(extent, np.float64)
+    cell = 0.9 * e / side
+    s = 0.18 * cell.min()  # pattern coordinates span about [-1, 2.5]: everything stays inside its cell
+    verts = []
+    k = 0
+    for name, B in patterns:
+        for c in range(copies):
+            ijk = np.array([k % side, (k // side) % side, k // (side * side)], np.float64)
+            centre = o + 0.05 * e + (ijk + 0.5) * cell + rng.uniform(-0.01, 0.01, 3) * cell
+            R = rot(c)
+            for tri in (A, np.asarray(B, np.float64)):
+                verts.append((centre + s * (tri - 0.5) @ R.T))
+            k += 1
+    xyz = np.concatenate(verts).astype(np.float32)
+    idx = np.arange(len(xyz), dtype=np.uint32).reshape(-1, 3)
+    names = [n for n, _ in patterns for _ in range(copies)]
+    return xyz, idx, names

@@ -97,3 +97,5 @@ if __name__ == "__main__":
     pipeline_fixture("cloth_20x20", *mg.cloth_fold(20, 20), via_obj=True)
     pipeline_fixture("soup_1500_refbox", *mg.soup(1500, seed=42, origin=(0.1, -0.4, -0.3), extent=(2.8, 0.6, 2.2)),
                      via_obj=False)
+    # narrow-phase / strict-box limit cases: exact touching, coplanar, near misses, degenerate triangles
+    pipeline_fixture("edge_cases", *mg.edge_cases()[:2], via_obj=False)

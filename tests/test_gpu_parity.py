@@ -139,6 +139,15 @@ def test_hybrid_sort_runs_fixup_and_fallback(cd, co, ctx, mg, scale):
     mesh.destroy()
 
 
+def test_narrow_phase_edge_cases(cd, co, ctx, mg):
+    """exact touching, coplanar, near-miss and degenerate triangle pairs: bit-exact pair set (and every build stage)"""
+    xyz, idx, _ = mg.edge_cases(copies=24, seed=11)
+    ref, _ = check_all_stages(cd, co, ctx, xyz, idx)
+    assert 50 < len(ref["pairs"]) < len(idx)
+    xyz, idx, _ = mg.edge_cases(copies=6, seed=5, origin=(0.0, 0.0, 0.0), extent=(1.0, 1.0, 1.0))
+    check_all_stages(cd, co, ctx, xyz, idx, **UNIT)
+
+
 def test_all_keys_identical(cd, co, ctx, mg):
     # every centroid in one Morton cell: the tree is decided by the index tie-break alone
     xyz, idx = mg.soup(3000, h=0.08, seed=4)

@@ -53,6 +53,23 @@ def test_cloth_dense_contacts(co, mg):
     m.close()
 
 
+def test_edge_cases_touching_coplanar_degenerate(co, mg):
+    """exact touching, coplanar, near-miss and degenerate triangle pairs (meshgen.edge_cases): the restatement follows
+    the reference through every borderline compare of project3 / project6 and the strict box test"""
+    xyz, idx, names = mg.edge_cases()
+    m = refcd.RefMesh.from_arrays(xyz, idx)
+    rp, _ = compare_all_stages(co, m, xyz, idx)
+    hit = set(map(tuple, rp.tolist()))
+    per = {}
+    for c, n in enumerate(names):
+        per.setdefault(n, []).append((2 * c, 2 * c + 1) in hit)
+    assert all(per["pierce"]) and all(per["segment_through"]) and all(per["graze_below"])
+    assert not any(per["coplanar_disjoint"]) and not any(per["parallel_close"]) and not any(per["point_outside"])
+    assert not per["coplanar_overlap"][0]  # the axis-aligned copy: flat boxes fail the STRICT overlap test (box.cuh:40-43)
+    assert any(per["coplanar_overlap"][1:])
+    m.close()
+
+
 def test_flag_standin_through_obj_parser(co, mg, tmp_path, capfd):
     xyz, idx = mg.flag(100, 100)
     path = os.path.join(tmp_path, "flag.obj")
