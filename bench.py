@@ -284,12 +284,6 @@ def run_gpu_arm(args, workload):
                          "(use --impl reference for the CPU arm).")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    try:  # run (and first-touch the pinned host buffers) on the CPUs / NUMA node next to this rank's GPU
-        import pynvml
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index(local_rank)))
-    except Exception:
-        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
