@@ -36,9 +36,19 @@ extern "C" __attribute__((visibility("default"))) void b200cd_debug_rs_prof(unsi
 
 namespace {
 
-constexpr int RS_THREADS = 512;
+// tile shape (overridable for tuning builds: -DRS_THREADS_V=256 -DRS_IPT_V=8 -DRS_MINB_V=4)
+#ifndef RS_THREADS_V
+#define RS_THREADS_V 512
+#endif
+#ifndef RS_IPT_V
+#define RS_IPT_V 8
+#endif
+#ifndef RS_MINB_V
+#define RS_MINB_V 2
+#endif
+constexpr int RS_THREADS = RS_THREADS_V;      // >= 256: one thread per digit publishes / looks back
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_IPT = 8;                     // items per thread
+constexpr int RS_IPT = RS_IPT_V;              // items per thread
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 items per tile
 constexpr int RS_BITS = 8;                    // digit width (9 bits = 7 passes was measured slower: 1.51 vs 1.29 ms at 16 M)
 constexpr int RS_RADIX = 1 << RS_BITS;
@@ -184,7 +194,7 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
 // COND: persistent variant for the hybrid sort's fallback - a fixed grid that does nothing when *cond == 0 and
 // otherwise works through all the tiles (ticket loop). The plain variant runs one tile per CTA.
 template <bool HAS_VALUES, bool SPLIT, bool COND = false>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB_V)
 rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
         uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values, uint32_t iota_base,
         const uint64_t* __restrict__ splitters, int nsplit,
