@@ -127,9 +127,11 @@ __device__ void climb_global(Carry c, bool have_slot, int s, int side, const uin
         float4 a, b;
         pack(c, side ? c.L : c.F, a, b);
         st256_cg(&pairs[s].c[side], a, b);
-        __threadfence();  // publish my half before announcing arrival
-        if (atomicAdd(flags + s, 1u) == 0u) return;
-        __threadfence();
+        // arrival counter with release (my half is visible before the count) and acquire (the sibling's half is
+        // read after it) semantics in ONE instruction instead of two device-wide fences around a relaxed atomic
+        unsigned int old;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(flags + s) : "memory");
+        if (old == 0u) return;
         float4 sa, sb;
         ld256_cg(&pairs[s].c[side ^ 1], sa, sb);  // published before the sibling's atomic; read through L2
         merge_with(c, side, sa, sb, s);
