@@ -48,7 +48,10 @@ extern "C" __attribute__((visibility("default"))) void b200cd_debug_bt_prof(unsi
 
 namespace {
 
-constexpr int BL = 256;  // sorted leaves per block
+#ifndef BL_V
+#define BL_V 256
+#endif
+constexpr int BL = BL_V;  // sorted leaves per block (tuning builds: -DBL_V=512)
 
 __device__ __forceinline__ float min3_ref(float a, float b, float c) {  // mathop.cuh:38-44
     float t = a;
