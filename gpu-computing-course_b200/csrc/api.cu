@@ -245,7 +245,9 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
         // order by a per-run fix-up (radix_sort.cu). The previous build's run statistics steer sort_high.
         int high = 0;
         if (npass == 8 && b->d_fix && !sort_hybrid_disabled()) {
-            if (b->fix_pending && cudaEventQuery(b->ev_fix) == cudaSuccess) {
+            const cudaError_t landed = b->fix_pending ? cudaEventQuery(b->ev_fix) : cudaErrorNotReady;
+            if (landed != cudaSuccess) cudaGetLastError();  // "not ready" is an answer, not a failure: do not leave it behind
+            if (b->fix_pending && landed == cudaSuccess) {
                 b->fix_pending = false;
                 const uint32_t overflow = b->h_fix[0], longest = b->h_fix[1], in_runs = b->h_fix[2];
                 if (overflow || longest > 24) {           // prefix too short for this mesh: sort more digits, for good

@@ -130,6 +130,10 @@ def test_hybrid_sort_runs_fixup_and_fallback(cd, co, ctx, mg, scale):
         assert np.array_equal(sk, rk), f"build {it}: sorted keys differ (passes {seen})"
         assert np.array_equal(si, ri), f"build {it}: tie order differs (passes {seen})"
     assert np.array_equal(ctx.self_collide(bvh), want)
+    for _ in range(3):  # back-to-back rebuilds with no synchronisation in between (the run statistics are not ready yet)
+        ctx.bvh_rebuild(bvh, mesh, gp)
+    _, sk, si = bvh.download()
+    assert np.array_equal(sk, rk) and np.array_equal(si, ri)
     assert seen[0] == 5 and all(4 <= p <= 8 for p in seen), seen
     if scale == 1.0:
         assert seen[-1] == 4, seen      # the prefix got shorter
@@ -266,6 +270,35 @@ def test_double_buffered_frames_async_upload(cd, co, ctx, mg):
     bvh.destroy()
     for m in meshes:
         m.destroy()
+
+
+def test_async_slice_upload_without_peers(cd, co, ctx, mg):
+    """b200cd_mesh_update_slice_async on one GPU (no peers set): the slice arithmetic of the chunked upload (four chunks,
+    sizes that do not divide) and the index check; the multi-GPU pushes are covered by tests/run_multigpu_check.py"""
+    xyz, idx = mg.soup(10_007, seed=17)
+    nv, nt = len(xyz), len(idx)
+    hx, hx_ptr = cd.pinned_array((nv, 3), np.float32)
+    hi, hi_ptr = cd.pinned_array((nt, 3), np.uint32)
+    hx[:] = xyz
+    hi[:] = idx
+    mesh = ctx.mesh_from_arrays(np.zeros_like(xyz), np.zeros_like(idx))
+    cuts_v, cuts_t = [0, 1, 4099, nv], [0, 3333, 3334, nt]
+    for a in range(3):
+        v0, v1, t0, t1 = cuts_v[a], cuts_v[a + 1], cuts_t[a], cuts_t[a + 1]
+        mesh.update_slice_async_from_ptr(hx_ptr + 12 * v0, v0, v1 - v0, hi_ptr + 12 * t0, t0, t1 - t0)
+        mesh.wait()
+    x2, i2 = mesh.download()
+    assert np.array_equal(x2, xyz) and np.array_equal(i2, idx)
+    bvh = ctx.bvh_build(mesh, cd.make_params(**UNIT))
+    want, _ = co.run(xyz, idx, co.make_params(**UNIT))
+    assert np.array_equal(ctx.self_collide(bvh), want)
+    hi[5, 1] = nv + 3                                     # a bad index inside the second triangle slice
+    mesh.update_slice_async_from_ptr(0, 0, 0, hi_ptr, 0, 100)
+    with pytest.raises(cd.B200cdError) as e:
+        mesh.wait()
+    assert e.value.status == cd.E_INVALID
+    bvh.destroy()
+    mesh.destroy()
 
 
 def test_capacity_error_reports_true_count(cd, ctx, mg):
