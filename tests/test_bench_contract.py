@@ -1,0 +1,38 @@
+"""CPU: bench.py's reference arm prints exactly ONE JSON line with the keys the driver reads.
+
+`bench.py --impl reference` times the reference's own host functions (oracle/_ref when it was built here, else the
+plain-C oracle port) on a bounded sample of the workload; it needs no GPU. The GPU arm prints the same keys plus
+`roofline`, `clocks`, `gpu_launches` (checked on the GPU box by the driver's own run)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "Mtri/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["metric"].startswith("Mtri/s end-to-end self-collision") and d["data"] == "synthetic" and d["dtype"] == "f64"
+    assert d["config"]["workload"] == "soup16m" and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb and cb["unit"] == "Mtri/s"
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["unit"] == "Mtri/s" and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_non_zero_ranks_of_the_reference_arm_print_nothing():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
