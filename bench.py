@@ -237,6 +237,15 @@ def run_reference_arm(args, workload):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 
+def pairs_checksum(words):
+    """two wrap-around sums over the sorted packed pair list (int64 words = hi_id << 32 | lo_id): equal lists give equal
+    sums, so the records of different GPU counts can be compared without shipping the lists"""
+    if words is None or words.numel() == 0:
+        return [0, 0]
+    w = words.to("cuda") if not words.is_cuda else words
+    return [int(w.sum().item()) & 0xFFFFFFFFFFFFFFFF, int((w * w + (w >> 7)).sum().item()) & 0xFFFFFFFFFFFFFFFF]
+
+
 def device_value(cd, mg, mgpu, ctx, name, steps, warmup=3):
     """triangles / CUDA-event time of `steps` build + query steps of workload `name` on ONE GPU, mesh resident in HBM"""
     import numpy as np
@@ -263,6 +272,7 @@ def device_value(cd, mg, mgpu, ctx, name, steps, warmup=3):
     st = ctx.stats()
     out = {"workload": name, "triangles": ntris, "vertices": nverts, "n_gpus": 1, "steps": steps,
            "value": round(ntris / ms / 1e3, 2), "unit": UNIT, "ms_per_step": round(ms, 4), "pairs": int(pairs.numel()),
+           "pairs_checksum": pairs_checksum(pairs),
            "bvh_build_ms": round(st["ms_build"], 4), "query_ms": round(st["ms_query"], 4)}
     bvh.destroy()
     mesh.destroy()
@@ -327,6 +337,7 @@ def run_gpu_arm(args, workload):
     for _ in range(max(args.warmup, 3)):
         merged = runner.step(bvh, mesh, params)
     npairs_total = int(merged.numel()) if rank == 0 else 0
+    checksum = pairs_checksum(merged) if rank == 0 else None
     host_pairs = torch.empty(max(npairs_total, 1) + 1024, dtype=torch.int64).pin_memory() if rank == 0 else None
     # count_launch() is process-wide; sample before/after the timed region
     launches0 = ctx.stats()["kernel_launches"]
@@ -512,7 +523,7 @@ def run_gpu_arm(args, workload):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "triangles": ntris, "vertices": nverts,
                        "morton_box": "unit cube" if box else "reference constants (morton.h:45,51,57)",
-                       "key_bits": 63, "pairs": npairs_total,
+                       "key_bits": 63, "pairs": npairs_total, "pairs_checksum": checksum,
                        "parallelism": "single GPU" if world == 1 else (
                            f"partitioned x{world}: one Morton range per rank; (key, id) exchange and ghost records "
                            f"{'stored straight into the owners buffers over NVLink peer memory (CUDA IPC)' if prunner.peer_memory else 'over grouped NCCL send/recv'}; "
