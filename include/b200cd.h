@@ -29,7 +29,9 @@
 extern "C" {
 #endif
 
-#define B200CD_ABI_VERSION 1
+/* 2: + b200cd_mesh_update_async / _wait / _update_slice_async / _ipc_export / _set_peers, b200cd_partition_plan_device
+ * (additions only: every version-1 entry point keeps its signature and meaning) */
+#define B200CD_ABI_VERSION 2
 
 typedef struct b200cd_ctx b200cd_ctx;
 typedef struct b200cd_mesh b200cd_mesh;
