@@ -60,6 +60,13 @@ def _worker(rank, world, port, chunk, tmpdir):
         order = np.lexsort((u[:, 1], u[:, 0]))  # what b200cd_sort_pairs_device does on the GPU: by lo id, then hi id
         assert np.array_equal(u[order][: len(full)], full)
         assert (u[order][len(full):] == (1 << id_bits) - 1).all()
+        # nothing to gather anywhere
+        buf, counts3 = mgpu.gather_pairs_padded(torch.zeros(0, dtype=torch.int64), id_bits)
+        assert buf.numel() == 0 and counts3 == [0] * world
+        # one rank empty: its slot is all sentinel
+        buf, counts3 = mgpu.gather_pairs_padded(torch.arange(3 if rank == 0 else 0, dtype=torch.int64), id_bits)
+        assert counts3 == [3, 0][:world] or world != 2
+        assert buf.numel() == 3 * world and buf[:3].tolist() == [0, 1, 2] and (buf[3:] == (((1 << id_bits) - 1) << 32 | ((1 << id_bits) - 1))).all()
         # empty contribution from one rank
         words = torch.zeros(0 if rank == 1 else 5, dtype=torch.int64)
         merged, counts = mgpu.gather_pairs(words, 0)
