@@ -249,7 +249,10 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
             if (landed != cudaSuccess) cudaGetLastError();  // "not ready" is an answer, not a failure: do not leave it behind
             if (b->fix_pending && landed == cudaSuccess) {
                 b->fix_pending = false;
-                const uint32_t overflow = b->h_fix[0], longest = b->h_fix[1], in_runs = b->h_fix[2];
+                const uint32_t overflow = b->h_fix[0] & 1u, longest = b->h_fix[1], in_runs = b->h_fix[2];
+                // (bit 1 of h_fix[0]: a key reached above the digit window - the fallback sorted that build; the window
+                // only ever moves up, so a mesh whose keys hover around a power of two does not fall back every frame)
+                if ((int)b->h_fix[3] > b->sort_top) b->sort_top = (int)b->h_fix[3];
                 if (overflow || longest > 24) {           // prefix too short for this mesh: sort more digits, for good
                     b->sort_high = overflow ? 8 : std::min(8, b->sort_high + 1);
                     b->sort_locked = true;
@@ -260,7 +263,7 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
             high = b->sort_high < 8 ? b->sort_high : 0;
         }
         b->cur = radix_sort(b->d_keys, b->d_ids, n, passes, npass, /*iota*/ !keys_given, b->d_hist, b->d_tile_status,
-                            b->tile_status_words, ctx->sm_count, s, high, b->d_fix);
+                            b->tile_status_words, ctx->sm_count, s, high, b->d_fix, b->sort_top);
         if (high) {
             CD_CUDA(ctx, cudaMemcpyAsync(b->h_fix, b->d_fix, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CD_CUDA(ctx, cudaEventRecord(b->ev_fix, s));

@@ -121,6 +121,7 @@ struct b200cd_bvh {
     cudaEvent_t ev_fix = nullptr;      // the copy above has landed
     bool fix_pending = false;
     int sort_high = 5;                 // digits sorted by radix passes (8 = plain full sort)
+    int sort_top = 0;                  // significant key bits seen by the previous build (0 = unknown: all 63)
     bool sort_locked = false;          // a longer prefix was needed once: never try a shorter one again
     // hierarchy
     uint32_t* d_flags = nullptr;       // n-1 arrival counters of the splits merged through global memory
@@ -208,10 +209,11 @@ struct RadixPass { int shift; int bits; };
 // first pass generates value = index. Result lands in buffer index returned.
 // high_passes > 0 (with d_fix, 4 device words): hybrid sort - only the top `high_passes` digits are sorted with
 // radix passes, the low bits by a per-run fix-up (radix_sort.cu, rs_fixup); needs an EVEN npass.
-// d_fix afterwards: [0] the fallback (all passes) ran, [1] longest run of equal high bits, [2] items in runs >= 2.
+// d_fix afterwards: [0] the fallback (all passes) ran, [1] longest run of equal high bits, [2] items in runs >= 2,
+// [3] significant key bits (highest set bit + 1). top_bits (0 = all): where the window of sorted digits ends.
 int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
                bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words,
-               int sms, cudaStream_t s, int high_passes = 0, uint32_t* d_fix = nullptr);
+               int sms, cudaStream_t s, int high_passes = 0, uint32_t* d_fix = nullptr, int top_bits = 0);
 // stable range partition (multi-GPU): bucket = number of device-resident splitters <= key; needs
 // d_hist >= 2*256+1 words and d_tile_status >= radix_tile_status_words(n, 1); counts land in d_hist[256..]
 void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t iota_base, uint64_t* keys_out,

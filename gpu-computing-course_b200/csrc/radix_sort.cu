@@ -19,6 +19,8 @@
 //
 // HBM traffic per pass: 12 B read + 12 B written per item (8+8 keys-only); the
 // histogram adds one 8 B read. Look-back words: 1 KiB per tile per pass.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200cd {
@@ -407,11 +409,12 @@ constexpr int RS_MAXRUN = 48;
 constexpr int RF_THREADS = 256;
 constexpr int RF_IPT = 8;  // items per thread: one pair of (same-address) statistics atomics per 2048 items
 __global__ void __launch_bounds__(RF_THREADS)
-rs_fixup(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, int lowbit, uint32_t* __restrict__ fix) {
-    __shared__ uint32_t s_max, s_sum;
-    if (threadIdx.x == 0) { s_max = 0; s_sum = 0; }
+rs_fixup(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, int lowbit, int top, uint32_t* __restrict__ fix) {
+    __shared__ uint32_t s_max, s_sum, s_bits;
+    if (threadIdx.x == 0) { s_max = 0; s_sum = 0; s_bits = 0; }
     __syncthreads();
     uint32_t tmax = 0, tsum = 0;
+    uint64_t seen = 0;  // OR of this thread's keys: fix[3] = significant key bits (where the next build puts its digit window)
     // all the block's loads first (two coalesced reads per item), then the rare per-run work
     const uint32_t base = blockIdx.x * (RF_IPT * RF_THREADS) + threadIdx.x;
     uint64_t kk[RF_IPT], kp[RF_IPT];
@@ -420,7 +423,10 @@ rs_fixup(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, i
         const uint32_t i = base + r * RF_THREADS;
         kk[r] = i < n ? keys[i] : 0ull;
         kp[r] = (i < n && i > 0) ? keys[i - 1] : 0ull;
+        seen |= kk[r];
     }
+    // a key with bits at or above `top` was not ordered by the passes (their window ends there): redo everything
+    if (top < 64 && (seen >> top)) atomicOr(fix + 0, 2u);
     // (a run's head may already be reordering it while others take their snapshot: harmless, the HIGH bits - all that
     // the head test looks at - are the same for every item of a run, and 8-byte accesses do not tear)
 #pragma unroll
@@ -434,7 +440,7 @@ rs_fixup(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, i
         while (j < n && j - i <= (uint32_t)RS_MAXRUN && (keys[j] >> lowbit) == hi) ++j;
         const uint32_t len = j - i;
         if (len > (uint32_t)RS_MAXRUN) {
-            atomicExch(fix + 0, 1u);
+            atomicOr(fix + 0, 1u);  // bit 0: a run was too long; bit 1: a key reached above the digit window
         } else if (len > 1) {
             for (uint32_t a = i + 1; a < j; ++a) {  // stable: an item only moves past strictly larger keys
                 const uint64_t ka = keys[a];
@@ -458,10 +464,15 @@ rs_fixup(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, i
     }
     // statistics: shared-memory reduction, then one pair of global atomics per block that saw a run of 2 or more
     if (tmax) { atomicMax(&s_max, tmax); atomicAdd(&s_sum, tsum); }
+    const uint32_t wbits = __reduce_max_sync(0xffffffffu, seen ? 64u - (uint32_t)__clzll((long long)seen) : 0u);
+    if ((threadIdx.x & 31) == 0 && wbits) atomicMax(&s_bits, wbits);
     __syncthreads();
-    if (threadIdx.x == 0 && s_max) {
-        atomicMax(fix + 1, s_max);
-        atomicAdd(fix + 2, s_sum);
+    if (threadIdx.x == 0) {
+        if (s_max) {
+            atomicMax(fix + 1, s_max);
+            atomicAdd(fix + 2, s_sum);
+        }
+        if (s_bits) atomicMax(fix + 3, s_bits);
     }
 }
 
@@ -482,7 +493,7 @@ uint64_t radix_tile_status_words(uint32_t n, int npass) {
 
 int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
                bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words, int sms,
-               cudaStream_t s, int high_passes, uint32_t* d_fix) {
+               cudaStream_t s, int high_passes, uint32_t* d_fix, int top_bits) {
     (void)tile_status_words;
     if (n == 0 || npass == 0) return 0;
     const bool hybrid = high_passes > 0 && high_passes < npass && d_fix && vals && npass % 2 == 0;
@@ -497,6 +508,17 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     for (int p = first; p < npass; ++p) {
         pl.shift[p - first] = all.shift[p];
         pl.mask[p - first] = all.mask[p];
+    }
+    // hybrid: the window of sorted digits ends at the keys' highest significant bit (as the previous build saw it; in-box
+    // Morton keys use 60 of the 63 bits), so all of its 8 * high_passes bits separate keys. The fix-up checks that no key
+    // reaches above the window and otherwise hands over to the fallback passes.
+    const int key_top = all.shift[npass - 1] + (32 - __builtin_clz(all.mask[npass - 1]));  // bits the full plan covers
+    const int top = hybrid ? std::max(8 * high_passes, std::min(top_bits > 0 ? top_bits : key_top, key_top)) : key_top;
+    if (hybrid) {
+        for (int p = 0; p < high_passes; ++p) {
+            pl.shift[p] = top - 8 * (high_passes - p);
+            pl.mask[p] = 0xffu;
+        }
     }
     const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
     static bool attr_set[64] = {};  // > 48 KiB of dynamic shared memory must be opted into, once per function and device
@@ -534,7 +556,7 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     if (!hybrid) return cur;
     // low bits: per-run fix-up; if a run was too long, the conditional kernels below sort the (already permuted,
     // ties still in their original order) items again over every digit. They exit at once when fix[0] == 0.
-    rs_fixup<<<(n + RF_THREADS * RF_IPT - 1) / (RF_THREADS * RF_IPT), RF_THREADS, 0, s>>>(keys[cur], vals[cur], n, all.shift[first], d_fix);
+    rs_fixup<<<(n + RF_THREADS * RF_IPT - 1) / (RF_THREADS * RF_IPT), RF_THREADS, 0, s>>>(keys[cur], vals[cur], n, pl.shift[0], top, d_fix);
     count_launch();
     cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);  // small; the status words are cleared conditionally
     rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[cur], n, all, d_hist, d_fix, reinterpret_cast<uint4*>(d_tile_status),

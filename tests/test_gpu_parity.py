@@ -152,6 +152,25 @@ def test_narrow_phase_edge_cases(cd, co, ctx, mg):
     check_all_stages(cd, co, ctx, xyz, idx, **UNIT)
 
 
+def test_hybrid_sort_window_follows_growing_keys(cd, co, ctx, mg):
+    """the window of sorted digits ends at the highest key bit the PREVIOUS build saw; when the mesh then grows and its
+    keys reach above the window, that build falls back to the full passes and the next one moves the window up"""
+    xyz, idx = mg.soup(120_000, seed=9)
+    small = (xyz * np.float32(1 / 64)).astype(np.float32)   # keys below 2^42
+    op, gp = co.make_params(**UNIT), cd.make_params(**UNIT)
+    mesh = ctx.mesh_from_arrays(small, idx)
+    bvh = ctx.bvh_build(mesh, gp)
+    for frame in (small, small, xyz, xyz, small, xyz):
+        mesh.update(xyz=frame)
+        ctx.bvh_rebuild(bvh, mesh, gp)
+        _, sk, si = bvh.download()
+        rk, ri = co.sort_keys(co.morton_keys(frame, idx, op))
+        assert np.array_equal(sk, rk) and np.array_equal(si, ri)
+    assert np.array_equal(ctx.self_collide(bvh), co.run(xyz, idx, op)[0])
+    bvh.destroy()
+    mesh.destroy()
+
+
 def test_all_keys_identical(cd, co, ctx, mg):
     # every centroid in one Morton cell: the tree is decided by the index tie-break alone
     xyz, idx = mg.soup(3000, h=0.08, seed=4)
