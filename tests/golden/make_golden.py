@@ -97,5 +97,10 @@ if __name__ == "__main__":
     pipeline_fixture("cloth_20x20", *mg.cloth_fold(20, 20), via_obj=True)
     pipeline_fixture("soup_1500_refbox", *mg.soup(1500, seed=42, origin=(0.1, -0.4, -0.3), extent=(2.8, 0.6, 2.2)),
                      via_obj=False)
+    # the multi-GPU workload's generator (two intersecting sheets), scaled uniformly into the reference box
+    sx, si = mg.two_sheets(24, seed=7)
+    o, e = np.array(mg.REF_ORIGIN), np.array(mg.REF_EXTENT)
+    sx = (o + 0.05 * e + sx.astype(np.float64) * (0.9 * e.min())).astype(np.float32)
+    pipeline_fixture("two_sheets_24", sx, si, via_obj=True)
     # narrow-phase / strict-box limit cases: exact touching, coplanar, near misses, degenerate triangles
     pipeline_fixture("edge_cases", *mg.edge_cases()[:2], via_obj=False)

@@ -14,7 +14,7 @@ PIPELINES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD
 
 
 def test_fixtures_present():
-    assert PIPELINES == ["cloth_20x20", "edge_cases", "flag_40x40", "soup_1500_refbox"]
+    assert PIPELINES == ["cloth_20x20", "edge_cases", "flag_40x40", "soup_1500_refbox", "two_sheets_24"]
 
 
 @pytest.mark.parametrize("name", PIPELINES)
