@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "internal.cuh"
 
 using namespace b200cd;
 
@@ -38,24 +39,20 @@ static int cuMemGetAddressRange_shim(void** base, size_t* size, void* ptr) {
 #define API extern "C" __attribute__((visibility("default")))
 
 namespace b200cd {
+int alloc_base_offset(void* ptr, uint64_t* offset_out) {
+    void* base = nullptr;
+    size_t size = 0;
+    if (cuMemGetAddressRange_shim(&base, &size, ptr) != 0) return 1;
+    *offset_out = (uint64_t)((char*)ptr - (char*)base);
+    return 0;
+}
+}  // namespace b200cd
+
+namespace b200cd {
 unsigned long long g_kernel_launches = 0;
 }
 
-namespace {
-
-enum Ev { EV_B0, EV_B1, EV_B2, EV_B3, EV_B4, EV_Q0, EV_Q1, EV_Q2, EV_Q3, EV_U0, EV_U1, EV_D0, EV_D1, EV_COUNT };
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
+namespace b200cd {  // internal helpers shared with dist.cu (declared in internal.cuh)
 
 float ev_ms(b200cd_ctx* ctx, int a, int b) {
     float ms = 0.f;
@@ -64,14 +61,6 @@ float ev_ms(b200cd_ctx* ctx, int a, int b) {
         return 0.f;
     }
     return ms;
-}
-
-template <typename T>
-int dev_alloc(b200cd_ctx* ctx, T** p, uint64_t count) {
-    *p = nullptr;
-    if (count == 0) count = 1;
-    CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
-    return B200CD_OK;
 }
 
 void free_bvh_buffers(b200cd_bvh* b) {
@@ -110,8 +99,8 @@ int id_bits_for(uint32_t n) {
     return n <= 1 ? 1 : b;
 }
 
-int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200cd_bvh** out, uint64_t ghost_cap = 0,
-              uint32_t max_peers = 0) {
+int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200cd_bvh** out, uint64_t ghost_cap,
+              uint32_t max_peers, bool ghost_out) {
     b200cd_bvh* b = new (std::nothrow) b200cd_bvh;
     if (!b) return set_error(ctx, B200CD_E_NOMEM, "host allocation failed");
     b->ctx = ctx;
@@ -146,7 +135,7 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
     A(dev_alloc(ctx, &b->d_leaves, (uint64_t)n + ghost_cap));  // ghost records of a partitioned build live after the local leaves
     if (max_peers) {
         b->ghost_out_cap = ghost_cap;
-        A(dev_alloc(ctx, &b->d_ghost_out, (uint64_t)max_peers * ghost_cap));
+        if (ghost_out) A(dev_alloc(ctx, &b->d_ghost_out, (uint64_t)max_peers * ghost_cap));  // staging of the NCCL send/recv exchange only
         A(dev_alloc(ctx, &b->d_cut_scratch, (uint64_t)ghost_max_k() * 6 + 1));
         A(dev_alloc(ctx, &b->d_block_boxes, ((uint64_t)n / 256 + 1) * 8));
         A(dev_alloc(ctx, &b->d_peers, 1));
@@ -204,7 +193,7 @@ int check_params(b200cd_ctx* ctx, const b200cd_params* p) {
 
 // keys_given: d_keys[0] / d_ids[0] already hold (key, triangle id) of the n triangles of this tree
 // (partitioned multi-GPU build); otherwise K1 computes the keys of the whole mesh and ids are 0..n-1.
-int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd_params* p, bool keys_given = false) {
+int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd_params* p, bool keys_given) {
     cudaStream_t s = ctx->stream;
     const uint32_t n = b->n;
     if (m->pending) return set_error(ctx, B200CD_E_INVALID, "mesh has an asynchronous upload in flight: call b200cd_mesh_wait first");
@@ -288,7 +277,7 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     return B200CD_OK;
 }
 
-}  // namespace
+}  // namespace b200cd
 
 // ------------------------------------------------------------------ context
 
@@ -306,6 +295,7 @@ API const char* b200cd_strerror(int status) {
         case B200CD_E_DEPTH: return "BVH traversal stack exhausted";
         case B200CD_E_NODEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
         case B200CD_E_TOOBIG: return "mesh too large";
+        case B200CD_E_PEER: return "multi-GPU step: a barrier between the ranks timed out";
         default: return "unknown status";
     }
 }
@@ -366,6 +356,9 @@ API int b200cd_destroy(b200cd_ctx* ctx) {
     cudaFree(ctx->d_sort_tmp);
     cudaFree(ctx->d_sort_hist);
     cudaFree(ctx->d_sort_status);
+    cudaFree(ctx->d_uniq_bits);
+    cudaFree(ctx->d_uniq_sums);
+    cudaFree(ctx->d_uniq_out);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     delete ctx;
     return B200CD_OK;
@@ -1182,7 +1175,7 @@ API int b200cd_send_ghosts_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, con
 
 // ------------------------------------------------------------------ query
 
-namespace {
+namespace b200cd {  // query internals shared with dist.cu (declared in internal.cuh)
 
 int grow(b200cd_ctx* ctx, uint2** buf, uint64_t* cap, uint64_t want) {
     if (*cap >= want && *buf) return B200CD_OK;
@@ -1219,6 +1212,22 @@ int sort_pairs_impl(b200cd_ctx* ctx, uint2** d_pairs, uint2** d_tmp, uint64_t co
     return B200CD_OK;
 }
 
+int ensure_entry_lists(b200cd_ctx* ctx, b200cd_bvh* b, uint64_t nquery) {
+    const uint64_t qblocks = (nquery + B200CD_QUERY_GROUP - 1) / B200CD_QUERY_GROUP;
+    if (qblocks > b->entry_blocks) {
+        cudaFree(b->d_entries);
+        cudaFree(b->d_entry_count);
+        b->d_entries = nullptr;
+        b->d_entry_count = nullptr;
+        b->entry_blocks = 0;
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entries), qblocks * B200CD_MAX_ENTRIES * sizeof(Node32)));
+        // counts, then (32-byte aligned) one 8-float union box per group
+        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entry_count), (((qblocks + 7) & ~7ull) + 8 * qblocks) * sizeof(uint32_t)));
+        b->entry_blocks = qblocks;
+    }
+    return B200CD_OK;
+}
+
 int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, uint32_t chunk, int sorted,
               uint64_t* count_out) {
     if (!b->built) return set_error(ctx, B200CD_E_INVALID, "BVH not built");
@@ -1251,18 +1260,8 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
     if (rc == B200CD_OK) rc = grow(ctx, &b->d_out, &b->out_cap, std::max<uint64_t>(b->out_cap, std::max<uint64_t>(nquery / 2 + 4096, hint)));
     if (rc == B200CD_OK && sorted) rc = grow(ctx, &b->d_out_tmp, &b->out_tmp_cap, b->out_cap);
     if (rc != B200CD_OK) return rc;
-    const uint64_t qblocks = ((uint64_t)nquery + B200CD_QUERY_GROUP - 1) / B200CD_QUERY_GROUP;  // entry lists
-    if (qblocks > b->entry_blocks) {
-        cudaFree(b->d_entries);
-        cudaFree(b->d_entry_count);
-        b->d_entries = nullptr;
-        b->d_entry_count = nullptr;
-        b->entry_blocks = 0;
-        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entries), qblocks * B200CD_MAX_ENTRIES * sizeof(Node32)));
-        // counts, then (32-byte aligned) one 8-float union box per group
-        CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->d_entry_count), (((qblocks + 7) & ~7ull) + 8 * qblocks) * sizeof(uint32_t)));
-        b->entry_blocks = qblocks;
-    }
+    rc = ensure_entry_lists(ctx, b, nquery);
+    if (rc != B200CD_OK) return rc;
 
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q0], s));
     bool need_broad = true;
@@ -1389,7 +1388,7 @@ int run_ghost_query(b200cd_ctx* ctx, b200cd_bvh* b, uint64_t nghost, int keep, u
     return set_error(ctx, B200CD_E_CUDA, "ghost query did not converge after growing its buffers");
 }
 
-}  // namespace
+}  // namespace b200cd
 
 API int b200cd_collide_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint64_t nghost, int keep_pairs,
                                      const void** d_pairs_out, uint64_t* count_out) {

@@ -29,6 +29,7 @@
 //     survivors compacted through a per-warp shared-memory queue, then the other 15 axes).
 //   - results are appended the same way (warp-aggregated atomic).
 // -fmad=false: every double operation rounds separately, like the host reference.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -362,7 +363,9 @@ __global__ void __launch_bounds__(BR_THREADS)
 broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, const float* __restrict__ root_box,
              uint32_t n, uint32_t shard, uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base,
              const Node32* __restrict__ entries, const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand,
-             uint64_t cand_cap, unsigned long long* __restrict__ counters) {
+             uint64_t cand_cap, unsigned long long* __restrict__ counters,
+             const unsigned long long* __restrict__ nquery_dev /* optional: the query count lives on the device (ghosts that
+                                                                   peers appended during this step); nquery is then the cap */) {
     __shared__ uint2 queue[BR_WARPS][BR_CQ];
     __shared__ Child s_entry[BR_ENTRIES];
     __shared__ float s_red[BR_WARPS][6];
@@ -371,10 +374,15 @@ broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restric
     const uint32_t lt = (1u << lane) - 1u;
     uint2* wq = queue[warp];
     uint32_t staged = 0;  // warp-uniform
+    if (nquery_dev) nquery = (uint32_t)min((unsigned long long)nquery, *nquery_dev);
+    uint32_t visits = 0, iters = 0, nkeep_sum = 0;  // traversal statistics (b200cd_stats::nodes_visited / warp_steps)
+    bool overflow = false;
+  // one block of 256 queries per iteration; the grid covers every block unless the count is device-side
+  for (uint32_t blk = blockIdx.x; (uint64_t)blk * BR_THREADS < nquery; blk += gridDim.x) {
     if (threadIdx.x == 0) s_nentry = 0;
 
     // this thread's query (sorted leaf position)
-    const uint32_t t = blockIdx.x * BR_THREADS + threadIdx.x;
+    const uint32_t t = blk * BR_THREADS + threadIdx.x;
     // q = where the query's record lives (and what the candidate list reports); qcmp = the position
     // the "only leaves after me" rule compares against (-1 for a ghost query: every local leaf counts)
     uint32_t q = 0xffffffffu;
@@ -419,11 +427,11 @@ broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restric
         for (int w = 1; w < BR_WARPS; ++w) { ulo[k] = fminf(ulo[k], s_red[w][k]); uhi[k] = fmaxf(uhi[k], s_red[w][3 + k]); }
     }
     // keep the entries whose box overlaps the union box (order is irrelevant)
-    const uint32_t nent = foreign ? (n > 1 ? 2u : 1u) : __ldg(entry_count + blockIdx.x);
+    const uint32_t nent = foreign ? (n > 1 ? 2u : 1u) : __ldg(entry_count + blk);
     if (threadIdx.x < nent) {
         Child c;
         if (!foreign) {
-            ld256_nc(entries + (size_t)blockIdx.x * BR_ENTRIES + threadIdx.x, c.a, c.b);
+            ld256_nc(entries + (size_t)blk * BR_ENTRIES + threadIdx.x, c.a, c.b);
         } else if (n > 1) {  // ghost queries start at the root: its two children, ext = last leaf
             const int root = reinterpret_cast<const int*>(root_box)[6];
             ld256_nc(&pairs[root].c[threadIdx.x], c.a, c.b);
@@ -439,7 +447,6 @@ broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restric
 
     int stack[B200CD_MAX_STACK];
     int sp = 0;
-    bool overflow = false;
 
     auto flush = [&]() {
         unsigned long long base = 0;
@@ -475,7 +482,7 @@ broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restric
         stage2(hit && link < 0, ~link, false, 0);
     }
     int node = sp > 0 ? stack[--sp] : -1;
-    uint32_t visits = 0, iters = 0;  // traversal statistics (b200cd_stats::nodes_visited / warp_steps)
+    nkeep_sum += nkeep;
 
     while (__any_sync(0xffffffffu, node >= 0)) {
         bool candL = false, candR = false;
@@ -506,12 +513,14 @@ broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restric
         stage2(candL, leafL, candR, leafR);
     }
     if (staged) flush();
+    __syncthreads();  // s_entry / s_nentry are rewritten by the next iteration
+  }
     if (overflow) atomicOr(counters + 2, ERR_STACK);
     visits = __reduce_add_sync(0xffffffffu, visits);
-    if (lane == 0) {
+    if (lane == 0 && iters) {
         atomicAdd(counters + 3, (unsigned long long)visits);
         atomicAdd(counters + 4, (unsigned long long)iters);
-        atomicAdd(counters + 5, (unsigned long long)nkeep);
+        atomicAdd(counters + 5, (unsigned long long)nkeep_sum);
     }
 }
 
@@ -705,8 +714,15 @@ static int traversal_variant() {
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
                   uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries,
                   uint32_t* d_entry_count, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
-                  cudaStream_t s) {
+                  cudaStream_t s, const unsigned long long* d_nquery, int sms) {
     if (nquery == 0 || n == 0 || (!foreign && n < 2)) return;
+    if (foreign && d_nquery) {  // ghost queries whose count only the device knows: a fixed grid strides over the blocks
+        const uint32_t blocks = std::min<uint32_t>((nquery + BR_THREADS - 1) / BR_THREADS, (uint32_t)std::max(sms, 1) * 8u);
+        broad_kernel_simple<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, 0, 1, BR_THREADS, nquery, 1, ghost_base,
+                                                          d_entries, d_entry_count, d_cand, cand_cap, d_counters, d_nquery);
+        count_launch();
+        return;
+    }
     const bool persistent = traversal_variant() == 2 && !foreign;  // ghost queries (few, no tree over them) use the simple kernel
     const uint32_t gsize = persistent ? BR_PER_WARP : BR_THREADS;  // consecutive queries per entry list
     const uint32_t groups = (nquery + gsize - 1) / gsize;
@@ -737,7 +753,7 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
     } else {
         broad_kernel_simple<<<groups, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery,
                                                           foreign, ghost_base, d_entries, d_entry_count, d_cand, cand_cap,
-                                                          d_counters);
+                                                          d_counters, nullptr);
     }
     count_launch();
 }

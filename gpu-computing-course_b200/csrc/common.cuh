@@ -68,6 +68,10 @@ struct b200cd_ctx {
     uint2* d_sort_tmp = nullptr;  uint64_t sort_tmp_cap = 0;
     uint32_t* d_sort_hist = nullptr;
     uint32_t* d_sort_status = nullptr;  uint64_t sort_status_words = 0;
+    // scratch of b200cd_unique_triangles_device (grow-only): ID bitmap, per-block counts, result
+    uint32_t* d_uniq_bits = nullptr;  uint64_t uniq_words = 0;
+    uint32_t* d_uniq_sums = nullptr;  uint64_t uniq_blocks = 0;
+    uint32_t* d_uniq_out = nullptr;   uint64_t uniq_out_cap = 0;
 };
 
 struct b200cd_mesh {
@@ -256,6 +260,18 @@ void launch_validate(const NodePair* d_pairs, const LeafRec* d_leaves, const flo
 void launch_partition_plan(const uint32_t* d_ghist, const uint32_t* d_lhist, int shift, int world, uint64_t* d_splitters,
                            int32_t* d_counts, cudaStream_t s);
 void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist65536, int sms, cudaStream_t s);
+// dist.cu's range plan: splitters, [source][owner] counts, receive offsets and range sizes from ALL ranks' histograms
+constexpr int DIST_HIST_BLOCK_BINS = 1024;
+constexpr int DIST_HIST_BLOCKS = 65536 / DIST_HIST_BLOCK_BINS;
+struct DistPlan {
+    uint64_t splitters[RS_MAX_SPLIT_P1];                 // world-1 used, ascending
+    uint32_t recv_off[RS_MAX_SPLIT_P1];                  // where my segment starts in every owner's receive buffers
+    uint32_t totals[RS_MAX_SPLIT_P1];                    // triangles each rank owns
+    uint32_t counts[RS_MAX_SPLIT_P1][RS_MAX_SPLIT_P1];   // [source rank][owner rank]
+};
+// d_hists: [world][65536]; d_ghist: 65536 words; d_part: world * DIST_HIST_BLOCKS words (scratch)
+void launch_dist_plan(const uint32_t* d_hists, int world, int rank, int shift, uint32_t* d_ghist, uint32_t* d_part,
+                      DistPlan* d_plan, cudaStream_t s);
 // d_scratch: K*6 + 1 words
 void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t K, uint32_t* d_scratch,
                         float* d_boxes, cudaStream_t s);
@@ -267,12 +283,19 @@ void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxe
 void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                             uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, const float* d_block_boxes,
                             cudaStream_t s);
+// unique.cu: sorted set of the triangle IDs in a pair list (reference main.cu:33-45). d_bits: ceil(id_space / 32) words,
+// d_sums: ceil(words / 1024) + 1 words; *d_sums_total (last word of d_sums) receives the count; d_out: ids, ascending
+void launch_unique_mark(const uint2* d_pairs, uint64_t count, uint32_t id_space, uint32_t* d_bits, cudaStream_t s);
+void launch_unique_count(const uint32_t* d_bits, uint64_t words, uint32_t* d_sums, cudaStream_t s);
+void launch_unique_emit(const uint32_t* d_bits, uint64_t words, const uint32_t* d_sums, uint32_t* d_out, uint64_t out_cap,
+                        cudaStream_t s);
 // collide.cu
 // foreign != 0: the queries are the nquery ghost records stored at leaves[ghost_base ...]; they start at the
 // root and are tested against every local leaf (no "only later positions" rule)
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
                   uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
-                  uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s);
+                  uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s,
+                  const unsigned long long* d_nquery = nullptr /* foreign only: device-side query count (nquery = cap) */, int sms = 148);
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s, bool unshared_vertices = false);
 

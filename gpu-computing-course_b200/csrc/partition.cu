@@ -290,6 +290,88 @@ partition_plan_kernel(const uint32_t* __restrict__ ghist, const uint32_t* __rest
     }
 }
 
+// ---- range plan of the C++ multi-GPU step (dist.cu). Every rank holds EVERY rank's 65536-bin histogram (pushed into its
+// comm block through peer memory), so each rank derives the same splitters and the whole [source][owner] count matrix
+// locally - no second exchange for the counts.
+// Stage 1 (64 blocks x 1024 bins): global histogram = sum over the ranks, plus per-rank sums of each 1024-bin block.
+__global__ void __launch_bounds__(DIST_HIST_BLOCK_BINS)
+dist_hist_reduce_kernel(const uint32_t* hists /* [world][65536], written by the peers */, int world, uint32_t* __restrict__ ghist,
+                        uint32_t* __restrict__ part /* [world][DIST_HIST_BLOCKS] */) {
+    __shared__ uint32_t s_part[RS_MAX_SPLIT_P1];
+    if (threadIdx.x < RS_MAX_SPLIT_P1) s_part[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t bin = blockIdx.x * DIST_HIST_BLOCK_BINS + threadIdx.x;
+    uint32_t sum = 0;
+    for (int src = 0; src < world; ++src) {
+        const uint32_t v = hists[(size_t)src * PP_BINS + bin];
+        sum += v;
+        const uint32_t w = __reduce_add_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_part[src], w);
+    }
+    ghist[bin] = sum;
+    __syncthreads();
+    if (threadIdx.x < (uint32_t)world) part[threadIdx.x * DIST_HIST_BLOCKS + blockIdx.x] = s_part[threadIdx.x];
+}
+
+// Stage 2 (one block): splitter bins from the global histogram (as partition_plan_kernel), then for every
+// (source rank, splitter) the number of the source's keys below the splitter - whole 1024-bin blocks from `part`,
+// the remainder from the source's histogram, one warp per task - and from those the count matrix, where my segment
+// starts in every owner's receive buffer and how many triangles each rank owns.
+__global__ void __launch_bounds__(PP_THREADS)
+dist_plan_kernel(const uint32_t* __restrict__ ghist, const uint32_t* hists, const uint32_t* __restrict__ part, int shift,
+                 int world, int rank, DistPlan* __restrict__ out) {
+    __shared__ uint64_t s_w[PP_THREADS / 32];
+    __shared__ uint32_t s_seg[PP_THREADS];
+    __shared__ uint32_t s_bin[RS_MAX_SPLIT_P1];
+    __shared__ uint32_t s_cum[RS_MAX_SPLIT_P1][RS_MAX_SPLIT_P1];  // [src][j]: src's keys in the bins [0, s_bin[j]]; j = world-1: all
+    const uint32_t tid = threadIdx.x, b0 = tid * PP_PER;
+    pp_segment_sums(ghist, s_seg);
+    const uint64_t sum = s_seg[tid];
+    uint64_t total;
+    const uint64_t excl = pp_block_exclusive(sum, s_w, total);
+    for (int r = 1; r < world; ++r) {
+        const uint64_t target = (uint64_t)r * total / (uint64_t)world;
+        if (target == 0 ? tid == 0 : (excl < target && target <= excl + sum)) {
+            uint32_t bin = b0;
+            uint64_t run = excl;
+            for (int k = 0; k < PP_PER; ++k) {
+                run += ghist[b0 + k];
+                if (run >= target) { bin = b0 + k; break; }
+            }
+            s_bin[r - 1] = min(bin, (uint32_t)PP_BINS - 2u);
+        }
+    }
+    __syncthreads();
+    const uint32_t warp = tid >> 5, lane = tid & 31;
+    for (int task = (int)warp; task < world * world; task += PP_THREADS / 32) {
+        const int src = task / world, j = task % world;
+        const uint32_t B = j + 1 < world ? s_bin[j] + 1u : (uint32_t)PP_BINS;  // bins below the splitter
+        const uint32_t full = B / DIST_HIST_BLOCK_BINS, rem = B % DIST_HIST_BLOCK_BINS;
+        uint32_t acc = 0;
+        for (uint32_t b = lane; b < full; b += 32) acc += part[src * DIST_HIST_BLOCKS + b];
+        for (uint32_t k = lane; k < rem; k += 32) acc += hists[(size_t)src * PP_BINS + full * DIST_HIST_BLOCK_BINS + k];
+        acc = __reduce_add_sync(0xffffffffu, acc);
+        if (lane == 0) s_cum[src][j] = acc;
+    }
+    __syncthreads();
+    if (tid < (uint32_t)(world * world)) {
+        const int src = tid / world, d = tid % world;
+        out->counts[src][d] = s_cum[src][d] - (d ? s_cum[src][d - 1] : 0u);
+    }
+    if (tid < (uint32_t)world) {
+        const int d = tid;
+        uint32_t off = 0, tot = 0;
+        for (int src = 0; src < world; ++src) {
+            const uint32_t c = s_cum[src][d] - (d ? s_cum[src][d - 1] : 0u);
+            if (src < rank) off += c;
+            tot += c;
+        }
+        out->recv_off[d] = off;
+        out->totals[d] = tot;
+        if (d + 1 < world) out->splitters[d] = (uint64_t)(s_bin[d] + 1u) << shift;  // keys >= splitter r-1 belong to rank >= r
+    }
+}
+
 // overall[p] = union of peer p's K coarse boxes (one warp per peer)
 __global__ void __launch_bounds__(32)
 peer_overall_kernel(const float* __restrict__ peer_boxes, uint32_t K, float* __restrict__ overall) {
@@ -318,6 +400,13 @@ void launch_partition_plan(const uint32_t* d_ghist, const uint32_t* d_lhist, int
                            int32_t* d_counts, cudaStream_t s) {
     partition_plan_kernel<<<1, PP_THREADS, 0, s>>>(d_ghist, d_lhist, shift, world, d_splitters, d_counts);
     count_launch();
+}
+
+void launch_dist_plan(const uint32_t* d_hists, int world, int rank, int shift, uint32_t* d_ghist, uint32_t* d_part,
+                      DistPlan* d_plan, cudaStream_t s) {
+    dist_hist_reduce_kernel<<<DIST_HIST_BLOCKS, DIST_HIST_BLOCK_BINS, 0, s>>>(d_hists, world, d_ghist, d_part);
+    dist_plan_kernel<<<1, PP_THREADS, 0, s>>>(d_ghist, d_hists, d_part, shift, world, rank, d_plan);
+    count_launch(2);
 }
 
 void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist, int sms, cudaStream_t s) {

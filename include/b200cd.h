@@ -30,12 +30,14 @@ extern "C" {
 #endif
 
 /* 2: + b200cd_mesh_update_async / _wait / _update_slice_async / _ipc_export / _set_peers, b200cd_partition_plan_device
- * (additions only: every version-1 entry point keeps its signature and meaning) */
-#define B200CD_ABI_VERSION 2
+ * 3: + b200cd_dist_* (the multi-GPU step in C++), b200cd_unique_triangles[_device], b200cd_nccl_unique_id, B200CD_E_PEER
+ * (additions only: every earlier entry point keeps its signature and meaning) */
+#define B200CD_ABI_VERSION 3
 
 typedef struct b200cd_ctx b200cd_ctx;
 typedef struct b200cd_mesh b200cd_mesh;
 typedef struct b200cd_bvh b200cd_bvh;
+typedef struct b200cd_dist b200cd_dist;
 
 enum {
     B200CD_OK = 0,
@@ -47,7 +49,8 @@ enum {
     B200CD_E_CAPACITY = 6,  /* caller's pair buffer too small; *count_out holds the true count */
     B200CD_E_DEPTH = 7,     /* traversal stack exhausted (tree deeper than B200CD_MAX_STACK) */
     B200CD_E_NODEVICE = 8,  /* no usable sm_100 device */
-    B200CD_E_TOOBIG = 9     /* mesh exceeds 2^30 triangles or vertices */
+    B200CD_E_TOOBIG = 9,    /* mesh exceeds 2^30 triangles or vertices */
+    B200CD_E_PEER = 10      /* multi-GPU step: a barrier between the ranks timed out (a peer failed) */
 };
 
 /* Morton normalisation and key width.
@@ -253,6 +256,16 @@ int b200cd_self_collide_device(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t shard,
                                uint32_t chunk, int sorted, const void** d_pairs_out,
                                uint64_t* count_out);
 
+/* Replaces makeAndPrintSet (main.cu:33-45, called at main.cu:154): the second half of the reference's output, the
+ * sorted set of the IDs of every triangle that takes part in at least one colliding pair. Computed on the device
+ * (bitmap over the ID space, per-word population counts, scan, ordered compaction). The _device form takes any
+ * device-resident pair list (uint32_t[2] per pair, IDs < id_space) and returns library-owned device memory valid
+ * until the next call on this context; the host form works on the pair list of the last query of `bvh` and follows
+ * b200cd_self_collide's capacity protocol (B200CD_E_CAPACITY with the true count; ids_out NULL + cap 0 to count). */
+int b200cd_unique_triangles_device(b200cd_ctx* ctx, const void* d_pairs, uint64_t count, uint32_t id_space,
+                                   const void** d_ids_out, uint64_t* count_out);
+int b200cd_unique_triangles(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t* ids_out, uint64_t cap, uint64_t* count_out);
+
 /* Lexicographic sort of a device-resident pair list (e.g. after gathering the
  * per-rank lists on rank 0). id_bits = number of significant bits in a triangle
  * ID (0 = 32). In place; asynchronous on the context's stream. */
@@ -352,6 +365,55 @@ int b200cd_send_ghosts_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const v
                                        uint32_t peer_mask);
 int b200cd_ghost_counter_reset(b200cd_ctx* ctx, b200cd_bvh* bvh);
 int b200cd_ghost_counter_read(b200cd_ctx* ctx, b200cd_bvh* bvh, uint64_t* count_out);
+
+/* ---- the multi-GPU step as ONE call per rank (one process per GPU) -----------------------------------
+ * The partitioned build + query above, driven by the library itself: b200cd_dist_step enqueues every phase on the
+ * context's stream and the ranks exchange histograms, (key, id) pairs, coarse boxes, ghost records, verdicts and
+ * the final pair lists through CUDA-IPC peer memory over NVLink, ordered by flag barriers over the same mappings
+ * (no collective library on the data path, two host reads per step). The pair list rank 0 gets is identical to
+ * b200cd_self_collide(sorted = 1) on one GPU.
+ *   1. every rank: b200cd_dist_create(ctx, rank, world, ntris, ...)
+ *   2. every rank: b200cd_dist_export -> the caller exchanges the blobs between the processes however it likes
+ *      (MPI, torch.distributed, files ...) -> b200cd_dist_connect(all blobs in rank order)
+ *   3. per frame, every rank: b200cd_dist_step(dist, mesh, params, &d_pairs, &count); only rank 0 receives the
+ *      sorted list (library-owned device memory, valid in stream order until the next step)
+ *   4. a barrier of the caller's, then b200cd_dist_destroy (peers must not be inside a step any more).
+ * Every rank must hold the whole mesh (same ntris, same contents). slack >= 1: room for uneven Morton ranges
+ * (capacity per rank = ntris / world * slack + 65536); pair_capacity = room in rank 0's gather buffer
+ * (0 = ntris / 2 + 65536). world = 1 runs the same code on one GPU. */
+#define B200CD_DIST_BLOB_BYTES 512
+typedef struct b200cd_dist_stats {
+    uint32_t rank, world;
+    uint32_t local_triangles;  /* size of this rank's Morton range in the last step */
+    uint32_t retries;          /* steps re-run after growing a buffer (cumulative) */
+    uint64_t ghosts;           /* ghost records received from lower ranks */
+    uint64_t candidates, local_pairs;
+    uint64_t total_pairs;      /* rank 0: pairs in the gathered list */
+    /* device times (CUDA events on the context's stream) of the last step's phases, barriers included */
+    float ms_keys_hist, ms_plan, ms_exchange, ms_build, ms_ghost_send, ms_local_query, ms_ghost_query, ms_gather,
+          ms_sort, ms_step;
+} b200cd_dist_stats;
+int b200cd_dist_create(b200cd_ctx* ctx, uint32_t rank, uint32_t world, uint32_t ntris_total, double slack,
+                       uint64_t pair_capacity, b200cd_dist** out);
+int b200cd_dist_export(b200cd_dist* dist, uint8_t* blob_out /* B200CD_DIST_BLOB_BYTES */);
+int b200cd_dist_connect(b200cd_dist* dist, const uint8_t* blobs /* world x B200CD_DIST_BLOB_BYTES, rank order */);
+int b200cd_dist_step(b200cd_dist* dist, const b200cd_mesh* mesh, const b200cd_params* params, const void** d_pairs_out,
+                     uint64_t* count_out);
+/* a barrier across the ranks on the context's stream (flag barrier over peer memory) */
+int b200cd_dist_barrier(b200cd_dist* dist);
+int b200cd_dist_get_stats(b200cd_dist* dist, b200cd_dist_stats* out);
+/* the rank's partial BVH (owned by dist): b200cd_bvh_validate / b200cd_get_stats work on it */
+int b200cd_dist_bvh(b200cd_dist* dist, b200cd_bvh** out);
+int b200cd_dist_destroy(b200cd_dist* dist);
+
+/* Replicated mode ("each GPU ... receives the BVH, broadcast via NCCL over NVLink"): NCCL is loaded at run time
+ * (dlopen of libnccl.so.2; B200CD_E_NODEVICE if absent). Rank 0 calls b200cd_nccl_unique_id and ships the 128 bytes
+ * to the other ranks; every rank calls b200cd_dist_nccl_init; b200cd_dist_broadcast_bvh then sends the three device
+ * blobs of a BVH built on `root` (traversal nodes, leaf records, sorted ids) to BVHs made with b200cd_bvh_alloc_like
+ * on the other ranks, which query their shard with b200cd_self_collide_shard / _device. */
+int b200cd_nccl_unique_id(uint8_t* id128);
+int b200cd_dist_nccl_init(b200cd_dist* dist, const uint8_t* id128);
+int b200cd_dist_broadcast_bvh(b200cd_dist* dist, b200cd_bvh* bvh, uint32_t root);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,38 @@ REF_API void* ref_from_arrays(const float* xyz, uint32_t nverts, const uint32_t*
     return m;
 }
 
+/* Same as ref_from_arrays, but the sort keys come from the caller instead of morton3D, whose
+ * normalisation is hard-coded for the flag mesh (morton.h:43-58): a unit-cube mesh has x below the
+ * box origin (UB in morton.h:80) and, at 16-64 M triangles, duplicate 60-bit codes, for which the
+ * reference builds a malformed tree (no tie-break in cpu_math.h:10 / bvh.cuh:48). The keys must be
+ * unique; ANY strictly increasing key sequence gives the reference's hierarchy a valid binary tree
+ * over the sorted leaf order, and the emitted pair SET does not depend on the tree.
+ * Everything after the key - thrust::sort_by_key, fillLeafNodesCpu, generateHierarchyParallelCpu,
+ * calBoundingBoxCpu, findCollisionIterativeCpu, checkTriangleContactHelper - is the reference's.
+ * Used by tests/golden/make_checksums.py for the full-size headline workloads. */
+REF_API void* ref_from_arrays_keyed(const float* xyz, uint32_t nverts, const uint32_t* idx, uint32_t ntris,
+                                    const uint64_t* keys) {
+    auto* m = new RefMesh;
+    double t0 = now_ms();
+    m->verts.reserve(nverts);
+    for (uint32_t i = 0; i < nverts; ++i) m->verts.push_back(vec3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+    m->tris.reserve(ntris);
+    m->mortons.reserve(ntris);
+    for (uint32_t t = 0; t < ntris; ++t) {
+        Triangle f;
+        f.vIdx[0] = idx[3 * t]; f.vIdx[1] = idx[3 * t + 1]; f.vIdx[2] = idx[3 * t + 2];
+        vec3f *p1 = &m->verts[f.vIdx[0]], *p2 = &m->verts[f.vIdx[1]], *p3 = &m->verts[f.vIdx[2]];
+        f.ID = t;
+        f.morton = keys[t];
+        f.ax = (p1->x + p2->x + p3->x) / 3; f.ay = (p1->y + p2->y + p3->y) / 3; f.az = (p1->z + p2->z + p3->z) / 3;
+        m->tris.push_back(f);
+        m->mortons.push_back(f.morton);
+    }
+    thrust::sort_by_key(m->mortons.begin(), m->mortons.end(), m->tris.begin());
+    m->ms_load = now_ms() - t0;
+    return m;
+}
+
 REF_API void ref_free(void* h) { delete static_cast<RefMesh*>(h); }
 REF_API uint32_t ref_num_verts(void* h) { return (uint32_t) static_cast<RefMesh*>(h)->verts.size(); }
 REF_API uint32_t ref_num_tris(void* h) { return (uint32_t) static_cast<RefMesh*>(h)->tris.size(); }

@@ -24,6 +24,7 @@ def lib():
         _LIB = C.CDLL(_PATH)
         _LIB.ref_load_obj.restype = C.c_void_p
         _LIB.ref_from_arrays.restype = C.c_void_p
+        _LIB.ref_from_arrays_keyed.restype = C.c_void_p
         _LIB.ref_collide.restype = C.c_uint64
         _LIB.ref_collide_mt.restype = C.c_uint64
         _LIB.ref_morton3D.restype = C.c_uint64
@@ -59,6 +60,17 @@ class RefMesh:
         idx = np.ascontiguousarray(idx, np.uint32)
         return cls(lib().ref_from_arrays(_p(xyz, C.c_float), C.c_uint32(xyz.shape[0]), _p(idx, C.c_uint32),
                                          C.c_uint32(idx.shape[0])))
+
+    @classmethod
+    def from_arrays_keyed(cls, xyz, idx, keys):
+        """caller-supplied UNIQUE sort keys instead of morton3D (whose box is hard-coded, morton.h:43-58); everything
+        after the key is the reference's own code. The pair set does not depend on the keys."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        idx = np.ascontiguousarray(idx, np.uint32)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        assert keys.shape[0] == idx.shape[0]
+        return cls(lib().ref_from_arrays_keyed(_p(xyz, C.c_float), C.c_uint32(xyz.shape[0]), _p(idx, C.c_uint32),
+                                               C.c_uint32(idx.shape[0]), _p(keys, C.c_uint64)))
 
     def close(self):
         if self.h:
