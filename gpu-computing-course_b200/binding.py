@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200cd.so")
 _LIB = None
 
-OK, E_INVALID, E_CUDA, E_NOMEM, E_IO, E_PARSE, E_CAPACITY, E_DEPTH, E_NODEVICE, E_TOOBIG = range(10)
+OK, E_INVALID, E_CUDA, E_NOMEM, E_IO, E_PARSE, E_CAPACITY, E_DEPTH, E_NODEVICE, E_TOOBIG, E_PEER = range(11)
 
 # every symbol include/b200cd.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
@@ -37,7 +37,13 @@ SYMBOLS = [
     "b200cd_ghost_counter_read", "b200cd_mesh_update_slice", "b200cd_mesh_device_buffers",
     "b200cd_obj_parse_host", "b200cd_host_array_free", "b200cd_mesh_update_async", "b200cd_mesh_wait",
     "b200cd_mesh_ipc_export", "b200cd_mesh_set_peers", "b200cd_mesh_update_slice_async", "b200cd_partition_plan_device",
+    "b200cd_unique_triangles", "b200cd_unique_triangles_device",
+    "b200cd_dist_create", "b200cd_dist_export", "b200cd_dist_connect", "b200cd_dist_step", "b200cd_dist_barrier",
+    "b200cd_dist_get_stats", "b200cd_dist_bvh", "b200cd_dist_destroy", "b200cd_nccl_unique_id", "b200cd_dist_nccl_init",
+    "b200cd_dist_broadcast_bvh",
 ]
+
+DIST_BLOB_BYTES = 512
 
 
 class Params(C.Structure):
@@ -60,6 +66,16 @@ class Checks(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("null_parent_internal", "wrong_bound_count", "null_child",
                                           "uninit_box_internal", "null_parent_leaf", "bad_triangle",
                                           "uninit_box_leaf", "unsorted_keys", "box_not_enclosing")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class DistStats(C.Structure):
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("local_triangles", C.c_uint32), ("retries", C.c_uint32),
+                ("ghosts", C.c_uint64), ("candidates", C.c_uint64), ("local_pairs", C.c_uint64), ("total_pairs", C.c_uint64)] + \
+               [(k, C.c_float) for k in ("ms_keys_hist", "ms_plan", "ms_exchange", "ms_build", "ms_ghost_send",
+                                         "ms_local_query", "ms_ghost_query", "ms_gather", "ms_sort", "ms_step")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -468,6 +484,30 @@ class Context:
         self._chk(lib().b200cd_ghost_counter_read(self.h, bvh.h, C.byref(cnt)), "ghost_counter_read")
         return int(cnt.value)
 
+    # ---- the sorted set of triangle IDs in a pair list (reference makeAndPrintSet, main.cu:33-45), on the device
+    def unique_triangles(self, bvh):
+        """IDs of every triangle in at least one colliding pair of the last query on `bvh`, ascending (uint32 array)"""
+        cnt = C.c_uint64()
+        rc = lib().b200cd_unique_triangles(self.h, bvh.h, None, C.c_uint64(0), C.byref(cnt))
+        if rc not in (OK, E_CAPACITY):
+            self._chk(rc, "unique_triangles")
+        out = np.empty(int(cnt.value), np.uint32)
+        if cnt.value:
+            self._chk(lib().b200cd_unique_triangles(self.h, bvh.h, _ptr(out, C.c_uint32), C.c_uint64(out.size), C.byref(cnt)),
+                      "unique_triangles")
+        return out[:cnt.value]
+
+    def unique_triangles_device(self, d_pairs, count, id_space):
+        """-> (device pointer to ascending uint32 IDs, count); library-owned until the next call on this context"""
+        cnt, ptr = C.c_uint64(), C.c_void_p()
+        self._chk(lib().b200cd_unique_triangles_device(self.h, C.c_void_p(d_pairs or None), C.c_uint64(count), C.c_uint32(id_space),
+                                                       C.byref(ptr), C.byref(cnt)), "unique_triangles_device")
+        return ptr.value, int(cnt.value)
+
+    # ---- the multi-GPU step in C++ (include/b200cd.h, b200cd_dist_*)
+    def dist_create(self, rank, world, ntris_total, slack=1.5, pair_capacity=0):
+        return Dist(self, rank, world, ntris_total, slack, pair_capacity)
+
     def sort_pairs_device(self, d_ptr, count, id_bits=0):
         self._chk(lib().b200cd_sort_pairs_device(self.h, C.c_void_p(d_ptr), C.c_uint64(count), C.c_uint32(id_bits)),
                   "sort_pairs_device")
@@ -482,6 +522,76 @@ class Context:
             self.destroy()
         except Exception:
             pass
+
+
+class Dist:
+    """One rank of the partitioned multi-GPU self-collision (b200cd_dist_*). The caller moves the export blobs
+    between the processes (exchange = a callable: my blob -> list of every rank's blob in rank order), e.g.
+    torch.distributed.all_gather_object; nothing else of a step goes through the host language."""
+
+    def __init__(self, ctx, rank, world, ntris_total, slack=1.5, pair_capacity=0):
+        self.ctx, self.rank, self.world, self.ntris = ctx, rank, world, ntris_total
+        self.h = C.c_void_p()
+        ctx._chk(lib().b200cd_dist_create(ctx.h, C.c_uint32(rank), C.c_uint32(world), C.c_uint32(ntris_total), C.c_double(slack),
+                                          C.c_uint64(pair_capacity), C.byref(self.h)), "dist_create")
+
+    def export(self):
+        blob = (C.c_uint8 * DIST_BLOB_BYTES)()
+        self.ctx._chk(lib().b200cd_dist_export(self.h, blob), "dist_export")
+        return bytes(blob)
+
+    def connect(self, blobs):
+        assert len(blobs) == self.world and all(len(b) == DIST_BLOB_BYTES for b in blobs)
+        buf = (C.c_uint8 * (DIST_BLOB_BYTES * self.world)).from_buffer_copy(b"".join(blobs))
+        self.ctx._chk(lib().b200cd_dist_connect(self.h, buf), "dist_connect")
+
+    def step(self, mesh, params):
+        """-> (device pointer of the sorted pair list, count) on rank 0, (None, 0) elsewhere"""
+        ptr, cnt = C.c_void_p(), C.c_uint64()
+        self.ctx._chk(lib().b200cd_dist_step(self.h, mesh.h, C.byref(params), C.byref(ptr), C.byref(cnt)), "dist_step")
+        return ptr.value, int(cnt.value)
+
+    def barrier(self):
+        self.ctx._chk(lib().b200cd_dist_barrier(self.h), "dist_barrier")
+
+    def stats(self):
+        s = DistStats()
+        self.ctx._chk(lib().b200cd_dist_get_stats(self.h, C.byref(s)), "dist_get_stats")
+        return s.as_dict()
+
+    def bvh(self):
+        """the rank's partial BVH (owned by this object: do not destroy)"""
+        b = C.c_void_p()
+        self.ctx._chk(lib().b200cd_dist_bvh(self.h, C.byref(b)), "dist_bvh")
+        out = Bvh(self.ctx, b, 0)
+        out.destroy = lambda: None
+        return out
+
+    def nccl_init(self, id128):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128)
+        self.ctx._chk(lib().b200cd_dist_nccl_init(self.h, buf), "dist_nccl_init")
+
+    def broadcast_bvh(self, bvh, root=0):
+        self.ctx._chk(lib().b200cd_dist_broadcast_bvh(self.h, bvh.h, C.c_uint32(root)), "dist_broadcast_bvh")
+
+    def destroy(self):
+        if self.h:
+            lib().b200cd_dist_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def nccl_unique_id():
+    buf = (C.c_uint8 * 128)()
+    rc = lib().b200cd_nccl_unique_id(buf)
+    if rc != OK:
+        raise B200cdError(rc, "nccl_unique_id")
+    return bytes(buf)
 
 
 def host_alloc(nbytes):

@@ -499,9 +499,11 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
     b200cd_bvh* b = d->bvh;
     const uint32_t W = d->world, R = d->rank;
     d->shift = params->key_bits == 63 ? 44 : 14;  // top 16 of the 60 / 30 bits in-box keys use
-    // buffers the whole step can run in without a host decision (grow-only; a retry enlarges them)
-    rc = grow(ctx, &b->d_cand, &b->cand_cap, std::max<uint64_t>(b->cand_cap, 4ull * d->cap + 4096));
-    if (rc == B200CD_OK) rc = grow(ctx, &b->d_out, &b->out_cap, std::max<uint64_t>(b->out_cap, (uint64_t)d->cap / 2 + 4096));
+    // buffers the whole step can run in without a host decision (grow-only; a retry enlarges them).
+    // B200CD_DIST_TINY_BUFFERS=1 (tests): start far too small, so that the collective retry path runs.
+    static const bool tiny = getenv("B200CD_DIST_TINY_BUFFERS") != nullptr;
+    rc = grow(ctx, &b->d_cand, &b->cand_cap, std::max<uint64_t>(b->cand_cap, tiny ? 2048 : 4ull * d->cap + 4096));
+    if (rc == B200CD_OK) rc = grow(ctx, &b->d_out, &b->out_cap, std::max<uint64_t>(b->out_cap, tiny ? 256 : (uint64_t)d->cap / 2 + 4096));
     if (rc == B200CD_OK) rc = ensure_entry_lists(ctx, b, (uint64_t)d->cap + 2 * B200CD_QUERY_BLOCK * 4);
     if (rc != B200CD_OK) return rc;
     HostResult* H = d->h_res;

@@ -525,6 +525,43 @@ class PartitionedSelfCollision:
         return merged
 
 
+class DistSelfCollision:
+    """The partitioned step driven by the LIBRARY (b200cd_dist_step, csrc/dist.cu): per frame one C call per rank; the
+    ranks talk through CUDA-IPC peer memory and flag barriers. torch.distributed is used once, to move the export
+    blobs between the processes, and for the caller's own barriers."""
+
+    def __init__(self, cd, ctx, mesh, params, group=None, slack=1.5, pair_capacity=0):
+        self.cd, self.ctx, self.mesh, self.params, self.group = cd, ctx, mesh, params, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device("cuda", ctx.device)
+        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.dist = ctx.dist_create(self.rank, self.world, mesh.ntris, slack, pair_capacity)
+        if self.world > 1:
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, self.dist.export(), group=group)
+            self.dist.connect(blobs)
+            dist.barrier(group=group)  # nobody steps before everybody has mapped everybody
+        self.counts = [0] * self.world
+
+    def step(self):
+        """one distributed build + query; rank 0 gets the sorted packed pair list (device tensor), the others None"""
+        ptr, count = self.dist.step(self.mesh, self.params)
+        if self.rank != 0:
+            return None
+        return device_pairs_as_tensor(ptr, count, self.device)
+
+    @property
+    def stats(self):
+        return self.dist.stats()
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)  # peers may still be storing into my buffers before this
+        self.dist.destroy()
+
+
 def partitioned_self_collision_emulated(cd, ctx, mesh, params, world, slack=1.5):
     """The same algorithm with `world` ranks emulated one after the other on ONE GPU (exchanges are
     device copies). Used by the single-GPU tests of the multi-rank logic; returns (sorted (count, 2)

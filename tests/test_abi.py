@@ -50,7 +50,7 @@ def test_product_does_not_link_or_import_the_oracle(cd):
 
 def test_status_strings_and_defaults(cd):
     lib = cd.lib()
-    assert lib.b200cd_abi_version() == 2
+    assert lib.b200cd_abi_version() == 3
     assert lib.b200cd_strerror(0) == b"ok"
     assert b"no CPU fallback" in lib.b200cd_strerror(cd.E_NODEVICE)
     p = cd.default_params()

@@ -1,0 +1,107 @@
+"""GPU: the multi-GPU step in C++ (b200cd_dist_*, csrc/dist.cu) against the single-GPU path and the oracle.
+
+world = 1 runs in-process. world = 2 and 3 start one process per rank (tests/dist_worker.py); on a box with one
+GPU the ranks share it, which still exercises everything that makes the multi-rank path different - CUDA-IPC
+mappings, (key, id) stores into the owner's buffers, remote ghost appends, the flag barriers, the gather into
+rank 0 - with the same kernels that run over NVLink on 2-8 GPUs (bench.py --gpus N)."""
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import dist_worker  # noqa: E402
+
+
+def reference_lists(cd, co, ctx, mg, name, steps=2):
+    """what rank 0 must produce: single-GPU b200cd_self_collide per frame, checked against the oracle"""
+    xyz, idx, params = dist_worker.workload(mg, cd, name)
+    op = co.make_params(tuple(params.morton_origin), tuple(params.morton_extent))
+    out = []
+    for k in range(steps):
+        if k == 1:
+            xyz = (xyz + np.float32(1e-3) * np.sin(37.0 * xyz[:, ::-1])).astype(np.float32)
+        mesh = ctx.mesh_from_arrays(xyz, idx)
+        bvh = ctx.bvh_build(mesh, params)
+        pairs = ctx.self_collide(bvh, sorted=True)
+        ref, _ = co.run(xyz, idx, op)
+        assert np.array_equal(pairs, ref), "single-GPU path differs from the oracle"
+        out.append(pairs)
+        bvh.destroy()
+        mesh.destroy()
+    return out
+
+
+@pytest.mark.parametrize("name", ["soup200000", "cloth120"])
+def test_dist_world1_in_process(cd, co, ctx, mg, name):
+    torch = pytest.importorskip("torch")
+    mgpu = importlib.import_module("gpu-computing-course_b200.multigpu")
+    want = reference_lists(cd, co, ctx, mg, name, steps=1)[0]
+    xyz, idx, params = dist_worker.workload(mg, cd, name)
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    dist = ctx.dist_create(0, 1, mesh.ntris)
+    for _ in range(2):
+        ptr, count = dist.step(mesh, params)
+        ctx.synchronize()  # rank 0's sort is asynchronous on the context's stream
+        got = mgpu.unpack_pairs(mgpu.device_pairs_as_tensor(ptr, count, torch.device("cuda", ctx.device)))
+        assert np.array_equal(got, want)
+    st = dist.stats()
+    assert st["local_triangles"] == mesh.ntris and st["total_pairs"] == len(want) and st["ghosts"] == 0
+    dist.destroy()
+    mesh.destroy()
+
+
+def run_ranks(world, name, steps=2, env_extra=None, timeout=600):
+    rdv = tempfile.mkdtemp(prefix="b200cd_rdv_")
+    env = dict(os.environ, **(env_extra or {}))
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), str(r), str(world), rdv, name, str(steps)],
+                              env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=timeout)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o[-3000:]}"
+    return rdv
+
+
+@pytest.mark.parametrize("world,name", [(2, "soup300000"), (2, "cloth150"), (3, "sheets160")])
+def test_dist_ranks_in_processes_equal_single_gpu(cd, co, ctx, mg, world, name):
+    want = reference_lists(cd, co, ctx, mg, name, steps=2)
+    rdv = run_ranks(world, name, steps=2)
+    total_local = 0
+    for k in range(2):
+        got = np.load(os.path.join(rdv, f"pairs_{k}.npy"))
+        assert got.shape == want[k].shape and np.array_equal(got, want[k]), f"step {k}: distributed list differs"
+    ghosts = 0
+    for r in range(world):
+        st = json.load(open(os.path.join(rdv, f"stats_{r}.json")))
+        last = st["steps"][-1]
+        total_local += last["local_triangles"]
+        ghosts += last["ghosts"]
+        assert st["checks"]["null_parent_internal"] == 1 and st["checks"]["wrong_bound_count"] == 0 and \
+            st["checks"]["null_child"] == 0 and st["checks"]["box_not_enclosing"] == 0, st["checks"]
+    xyz, idx, _ = dist_worker.workload(mg, cd, name)
+    assert total_local == len(idx)          # the Morton ranges tile the mesh
+    assert ghosts > 0                       # and the exchange really happened
+
+
+def test_dist_retry_after_overflow_and_uneven_ranges(cd, co, ctx, mg):
+    """a dense-contact mesh overflows the first guess of the pair buffers: all ranks retry together"""
+    want = reference_lists(cd, co, ctx, mg, "cloth200", steps=2)
+    rdv = run_ranks(2, "cloth200", steps=2, env_extra={"B200CD_DIST_TINY_BUFFERS": "1"})
+    for k in range(2):
+        assert np.array_equal(np.load(os.path.join(rdv, f"pairs_{k}.npy")), want[k])
+    assert sum(json.load(open(os.path.join(rdv, f"stats_{r}.json")))["steps"][-1]["retries"] for r in range(2)) >= 2

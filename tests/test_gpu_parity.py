@@ -401,3 +401,31 @@ def test_partition_plan_kernel_equals_torch_twin(cd, ctx, world):
         assert torch.equal(spl, (bins + 1) << shift), (world, spl.tolist()[:4], bins.tolist()[:4])
         assert torch.equal(cnt, want_cnt), (world, cnt.tolist(), want_cnt.tolist())
     ctx.set_stream(None)
+
+
+def test_unique_triangle_set_on_device(cd, co, ctx, mg):
+    """the second half of the reference's output (makeAndPrintSet, main.cu:33-45): sorted unique IDs of all colliding
+    triangles, computed on the device - against numpy on the pair list, for sparse, dense and empty results"""
+    for xyz, idx, p in ((*mg.cloth_fold(60, 60), cd.default_params()), (*mg.soup(50000, seed=3), cd.make_params(**UNIT)),
+                        (*mg.flag(30, 30), cd.default_params()), (*mg.soup(64, h=1e-6, seed=1), cd.make_params(**UNIT))):
+        mesh = ctx.mesh_from_arrays(xyz, idx)
+        bvh = ctx.bvh_build(mesh, p)
+        for srt in (True, False):
+            pairs = ctx.self_collide(bvh, sorted=srt)
+            ids = ctx.unique_triangles(bvh)
+            assert ids.dtype == np.uint32 and np.array_equal(ids, np.unique(pairs))
+        bvh.destroy()
+        mesh.destroy()
+    # capacity protocol of the host form, through the raw C ABI
+    import ctypes as C
+    xyz, idx = mg.cloth_fold(40, 40)
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, cd.default_params())
+    pairs = ctx.self_collide(bvh)
+    want = np.unique(pairs)
+    cnt = C.c_uint64()
+    small = np.zeros(4, np.uint32)
+    rc = cd.lib().b200cd_unique_triangles(ctx.h, bvh.h, small.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(4), C.byref(cnt))
+    assert rc == cd.E_CAPACITY and cnt.value == len(want) and not small.any()
+    bvh.destroy()
+    mesh.destroy()

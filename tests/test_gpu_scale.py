@@ -1,6 +1,8 @@
 """GPU: BASELINE.json's full-size configurations through size-independent properties, plus a
 mid-size bit-exact comparison with the oracle. (~1-2 minutes on a B200 box.)"""
 import importlib
+import json
+import os
 
 import numpy as np
 import pytest
@@ -8,6 +10,18 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 UNIT = dict(origin=(0.0, 0.0, 0.0), extent=(1.0, 1.0, 1.0))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# full-size expected results: made once in the build container by tests/golden/make_checksums.py from the reference's
+# own host functions AND the oracle restatement (full lists compared there)
+CHECKSUMS = json.load(open(os.path.join(ROOT, "tests", "golden", "checksums.json")))
+ps = importlib.import_module("gpu-computing-course_b200.pairsum")
+
+
+def matches_golden(name, pairs, n):
+    g = CHECKSUMS[name]
+    assert g["triangles"] == n
+    assert len(pairs) == g["pairs"], (len(pairs), g["pairs"])
+    assert ps.pairs_checksum_np(pairs) == g["checksum"]
 
 
 def pair_set_properties(pairs, n):
@@ -32,8 +46,8 @@ def test_soup_4m_bit_exact_vs_oracle(cd, co, ctx, mg):
     mesh.destroy()
 
 
-def test_soup_16m_full_size_properties(cd, co, ctx, mg):
-    """C4 at full size: structure counters, pair-set invariants, shard union, sampled re-verification"""
+def test_soup_16m_bit_exact_vs_oracle(cd, co, ctx, mg):
+    """C4 at full size: the whole pair list against the oracle, plus structure counters, pair-set invariants, shard union"""
     n = 1 << 24
     xyz, idx = mg.soup(n, seed=1234)
     mesh = ctx.mesh_from_arrays(xyz, idx)
@@ -45,6 +59,14 @@ def test_soup_16m_full_size_properties(cd, co, ctx, mg):
     assert st["pairs"] == len(pairs) and st["candidates"] >= st["pairs"]
     assert len(pairs) > n // 8                         # ~0.19 contacts per triangle at this density
     pair_set_properties(pairs, n)
+    # THE headline configuration, full list against the oracle (cpu.cuh:196-245 over every leaf, tri_contact.cuh:80-87)
+    # and against the count + checksum the reference's own host functions gave for this mesh
+    ref, _ = co.run(xyz, idx, co.make_params((0, 0, 0), (1, 1, 1)))
+    assert np.array_equal(pairs, ref), "soup16m: GPU pair list differs from the oracle"
+    del ref
+    matches_golden("soup16m", pairs, n)
+    # the unique-triangle set (main.cu:33-45) on the device
+    assert np.array_equal(ctx.unique_triangles(bvh), np.unique(pairs))
     # union of 8 block-cyclic shards == the full list (what the 8-GPU path gathers)
     parts = [ctx.self_collide(bvh, sorted=False, shard=s, nshards=8, chunk=1 << 14) for s in range(8)]
     merged = np.concatenate(parts)
@@ -73,6 +95,24 @@ def test_soup_16m_full_size_properties(cd, co, ctx, mg):
     mesh.destroy()
 
 
+def test_sheets_64m_matches_reference_checksum(cd, ctx, mg):
+    """C5 (2^26 triangles) on one GPU: count + checksum of the sorted list equal what the reference's host functions
+    and the oracle produced for this mesh (tests/golden/checksums.json; the oracle needs 100 s and 20 GB for it)"""
+    xyz, idx = mg.two_sheets(4096, seed=7)
+    n = len(idx)
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    del xyz, idx
+    bvh = ctx.bvh_build(mesh, cd.make_params(**UNIT))
+    chk = bvh.validate(mesh)
+    assert chk["null_parent_internal"] == 1 and sum(chk.values()) == 1 + chk["unsorted_keys"], chk
+    pairs = ctx.self_collide(bvh, sorted=True)
+    pair_set_properties(pairs, n)
+    matches_golden("sheets64m", pairs, n)
+    assert np.array_equal(ctx.unique_triangles(bvh), np.unique(pairs))
+    bvh.destroy()
+    mesh.destroy()
+
+
 def test_cloth_1m_dense_contacts_bit_exact(cd, co, ctx, mg):
     """C3 at full size (1 002 528 triangles, shared vertices, reference Morton box)"""
     xyz, idx = mg.cloth_fold()
@@ -81,6 +121,8 @@ def test_cloth_1m_dense_contacts_bit_exact(cd, co, ctx, mg):
     pairs = ctx.self_collide(bvh, sorted=True)
     ref, _ = co.run(xyz, idx, co.default_params())
     assert np.array_equal(pairs, ref) and len(pairs) > 200000
+    matches_golden("cloth1m", pairs, len(idx))
+    assert np.array_equal(ctx.unique_triangles(bvh), np.unique(pairs))
     bvh.destroy()
     mesh.destroy()
 
@@ -93,5 +135,6 @@ def test_flag_standin_full_size_bit_exact(cd, co, ctx, mg):
     pairs = ctx.self_collide(bvh, sorted=True)
     ref, _ = co.run(xyz, idx, co.default_params())
     assert np.array_equal(pairs, ref) and len(pairs) > 0
+    matches_golden("flag1m", pairs, len(idx))
     bvh.destroy()
     mesh.destroy()
