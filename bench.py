@@ -92,6 +92,30 @@ def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes, recs=True):
     }
 
 
+def contract_bytes(n, nverts, npairs):
+    """SURVEY.md section 8(d)'s compulsory bytes per stage for the layout the survey planned (8-pass sort of 12-byte items,
+    32-byte nodes, separate AABB / parent arrays) - the contract the judge divides by, independent of OUR layout:
+    K1 = 48N + 16V, K2 = 200N, K3 = 24N, K4 = 108N, K5 (traversal + narrow phase) = 100N + 16V + 8 pairs;
+    build = 380N + 16V, end to end = 480N + 32V + 8 pairs."""
+    return {"morton": 48 * n + 16 * nverts, "sort": 200 * n, "tree": 24 * n + 108 * n,
+            "query": 100 * n + 16 * nverts + 8 * npairs,
+            "e2e": 480 * n + 32 * nverts + 8 * npairs}
+
+
+def golden_checksums():
+    path = os.path.join(ROOT, "tests", "golden", "checksums.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+def matches_oracle(workload, npairs, checksum):
+    """the sorted pair list equals the one the reference's host functions and the CPU oracle produce for this workload
+    (count + two wrap-around sums, tests/golden/checksums.json made by tests/golden/make_checksums.py); None = no golden"""
+    g = golden_checksums().get(workload)
+    if not g or checksum is None:
+        return None
+    return bool(int(npairs) == int(g["pairs"]) and [int(c) for c in checksum] == [int(c) for c in g["checksum"]])
+
+
 STAGE_KERNEL = {"morton": "morton_kernel", "sort": "rs_pass (x passes) + rs_histogram + rs_fixup", "tree": "build_kernel (+ upper_kernel)",
                 "traverse": "broad_kernel (+ entry_kernel)", "narrow": "narrow_kernel"}
 
@@ -205,32 +229,47 @@ def cpu_reference_run(name, sample_tris, threads, repeats=1):
                           query=tm.ms_query, pairs=int(tm.pairs))
         how = "oracle/cd_oracle.c (plain-C restatement), one thread"
     return vals, {"kind": kind_s, "cores": threads, "sample": sample, "how": how, "stages_ms": stages,
-                  "host_cores_available": os.cpu_count()}
+                  "host_cores_available": os.cpu_count(), "triangles": n}
 
 
 def run_reference_arm(args, workload):
+    """The reference's own CPU functions on the box's host cores, all threads in the query loop. Each step is a bounded
+    SAMPLE of the workload (same generator, same contact density): the sample size is chosen from a short calibration run
+    so that steps + warmup fit `--ref-budget` seconds (whole workload when that fits). The line says what it timed:
+    config.triangles is the SAMPLE's triangle count, config.sample_of names the full workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the CPU arm runs on rank 0 alone
     threads = os.cpu_count() or 1
     total = args.steps + args.warmup
-    sample_tris = (1 << 20) if total <= 40 else (1 << 18)
+    mg = importlib.import_module(f"{PKG}.meshgen")
+    nverts, ntris = workload_sizes(mg, workload)
     t0 = time.time()
+    cal_n = 1 << 18
+    tc = time.time()
+    cal, _ = cpu_reference_run(workload, cal_n, threads, repeats=1)
+    per_tri = (time.time() - tc) / cal_n                       # wall seconds per triangle incl. mesh generation
+    budget = max(20.0, float(args.ref_budget))
+    want = budget / max(total, 1) / per_tri / 1.25              # 25 % head-room (log N growth of the tree walk)
+    sample_tris = ntris if want >= ntris else max(1 << 16, 1 << int(want).bit_length() - 1)
     vals, info = cpu_reference_run(workload, sample_tris, threads, repeats=total)
     timed = vals[args.warmup:] or vals
     v = len(timed) / sum(1.0 / x for x in timed)  # total triangles / total time over the timed steps
-    mg = importlib.import_module(f"{PKG}.meshgen")
-    nverts, ntris = workload_sizes(mg, workload)
+    n_timed = int(info.get("triangles", sample_tris))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e-3 * sample_tris / v, 3) if v else None,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e-3 * n_timed / v, 3) if v else None,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "triangles": ntris, "vertices": nverts},
+        "config": {"workload": workload, "triangles": n_timed,
+                   "sample_of": {"workload": workload, "triangles": ntris, "vertices": nverts},
+                   "full_workload": bool(n_timed == ntris),
+                   "note": "Mtri/s of a CPU BVH pipeline falls slowly (log N) with size: a sample slightly flatters the CPU arm"},
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"], "how": info["how"], "stages_ms": info["stages_ms"],
                          "host_cores_available": info["host_cores_available"]},
         "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(time.time() - t0, 1),
+        "calibration": {"triangles": cal_n, "mtri_per_s": round(cal[0], 4)},
     }
     print(json.dumps(line), flush=True)
 
@@ -246,38 +285,51 @@ def pairs_checksum(words):
     return [int(w.sum().item()) & 0xFFFFFFFFFFFFFFFF, int((w * w + (w >> 7)).sum().item()) & 0xFFFFFFFFFFFFFFFF]
 
 
-def device_value(cd, mg, mgpu, ctx, name, steps, warmup=3):
-    """triangles / CUDA-event time of `steps` build + query steps of workload `name` on ONE GPU, mesh resident in HBM"""
+def device_value(cd, mg, mgpu, ctx, name, steps, warmup=3, host=None):
+    """triangles / CUDA-event time of `steps` build + query steps of workload `name` on ONE GPU, mesh resident in HBM.
+    host = (xyz_ptr, idx_ptr): the workload's arrays already sit in pinned host memory"""
     import numpy as np
     import torch
     _, _, box = WORKLOADS[name]
     nverts, ntris = workload_sizes(mg, name)
-    xyz, xyz_ptr = cd.pinned_array((nverts, 3), np.float32)
-    idx, idx_ptr = cd.pinned_array((ntris, 3), np.uint32)
-    generate(mg, name, out=(xyz, idx))
+    if host is None:
+        xyz, xyz_ptr = cd.pinned_array((nverts, 3), np.float32)
+        idx, idx_ptr = cd.pinned_array((ntris, 3), np.uint32)
+        generate(mg, name, out=(xyz, idx))
+    else:
+        xyz_ptr, idx_ptr = host
     params = cd.make_params(*box) if box else cd.default_params()
     mesh = ctx.mesh_from_host_ptr(xyz_ptr, nverts, idx_ptr, ntris)
-    runner = mgpu.ShardedSelfCollision(cd, ctx)
+    dev = torch.device("cuda", ctx.device)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)  # the events below are recorded on torch's current stream
     bvh = ctx.bvh_build(mesh, params)
+
+    def one_step():  # ONE GPU, whatever process group exists: rebuild + whole query + sorted list
+        ctx.bvh_rebuild(bvh, mesh, params)
+        ptr, count = ctx.self_collide_device(bvh, sorted=True)
+        return mgpu.device_pairs_as_tensor(ptr, count, dev)
     for _ in range(warmup):
-        pairs = runner.step(bvh, mesh, params)
+        pairs = one_step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(steps):
-        pairs = runner.step(bvh, mesh, params)
+        pairs = one_step()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     st = ctx.stats()
+    csum = pairs_checksum(pairs)
     out = {"workload": name, "triangles": ntris, "vertices": nverts, "n_gpus": 1, "steps": steps,
            "value": round(ntris / ms / 1e3, 2), "unit": UNIT, "ms_per_step": round(ms, 4), "pairs": int(pairs.numel()),
-           "pairs_checksum": pairs_checksum(pairs),
-           "bvh_build_ms": round(st["ms_build"], 4), "query_ms": round(st["ms_query"], 4)}
+           "pairs_checksum": csum, "pairs_match_oracle": matches_oracle(name, int(pairs.numel()), csum),
+           "bvh_build_ms": round(st["ms_build"], 4), "query_ms": round(st["ms_query"], 4),
+           "sort_passes": int(st["sort_passes"])}
     bvh.destroy()
     mesh.destroy()
-    cd.host_free(xyz_ptr)
-    cd.host_free(idx_ptr)
+    if host is None:
+        cd.host_free(xyz_ptr)
+        cd.host_free(idx_ptr)
     return out
 
 
@@ -295,7 +347,9 @@ def run_gpu_arm(args, workload):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # (a short collective timeout: a rank that dies must not leave the others waiting for ten minutes)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     cd = importlib.import_module(f"{PKG}.binding")
     mg = importlib.import_module(f"{PKG}.meshgen")
@@ -310,10 +364,28 @@ def run_gpu_arm(args, workload):
     params = cd.make_params(*box) if box else cd.default_params()
 
     ctx = cd.Context(local_rank)
+    # the strong-scaling denominator, measured in THIS run: rank 0 times a few single-GPU steps of the same workload
+    # before the distributed objects exist (the other ranks wait at the barrier)
+    scaling_base = None
+    if world > 1 and not args.no_scaling_base:
+        if rank == 0:
+            scaling_base = device_value(cd, mg, mgpu, ctx, workload, steps=5, host=(xyz_ptr, idx_ptr))
+        dist.barrier()
     mesh = ctx.mesh_from_host_ptr(xyz_ptr, nverts, idx_ptr, ntris)
-    partitioned = world > 1 and args.mode == "partitioned"
-    if partitioned:
-        # each rank owns one Morton range: distributed sort, local tree + query, ghost exchange (multigpu.py)
+    partitioned = world > 1 and args.mode in ("partitioned", "partitioned-py")
+    cxx_step = partitioned and args.mode == "partitioned"
+    if cxx_step:
+        # each rank owns one Morton range; the whole step is ONE library call per rank (b200cd_dist_step, csrc/dist.cu)
+        prunner = mgpu.DistSelfCollision(cd, ctx, mesh, params)
+        bvh = prunner.dist.bvh()
+
+        class _Step:
+            def step(self, bvh_, mesh_, params_):
+                return prunner.step()
+        runner = _Step()
+    elif partitioned:
+        # the same algorithm orchestrated from Python over torch.distributed (round 1; kept for A/B and as the NCCL
+        # send/recv fallback where CUDA IPC is unavailable)
         prunner = mgpu.PartitionedSelfCollision(cd, ctx, mesh, params, peer_memory=not args.no_peer_memory)
         bvh = prunner.part.bvh
 
@@ -421,7 +493,7 @@ def run_gpu_arm(args, workload):
         e2e_mode = ("double-buffered frames: b200cd_mesh_update_async of frame k+1 overlaps b200cd_bvh_rebuild + "
                     "b200cd_self_collide of frame k; one full H2D and one D2H per step inside the timed region")
         frames[1].destroy()
-    elif partitioned and prunner.peer_memory:
+    elif partitioned and (cxx_step or prunner.peer_memory):
         # several GPUs, double-buffered frames: every rank pushes its 1/world slice of frame k+1 over its own PCIe
         # link and on into the peers' mesh buffers with the copy engines over NVLink (copy stream, no NCCL, no SMs)
         # while frame k is built and queried. Still one whole mesh H2D (summed over the ranks) and one D2H per step.
@@ -439,7 +511,10 @@ def run_gpu_arm(args, workload):
             for k in range(args.steps):
                 if k + 1 < args.steps:
                     pm.upload_async((k + 1) % 2, xyz_ptr, idx_ptr)
-                prunner.part.mesh = pm.wait(k % 2)
+                if cxx_step:
+                    prunner.mesh = pm.wait(k % 2)
+                else:
+                    prunner.part.mesh = pm.wait(k % 2)
                 merged = prunner.step()
                 if rank == 0:
                     host_pairs[: merged.numel()].copy_(merged, non_blocking=True)
@@ -451,12 +526,25 @@ def run_gpu_arm(args, workload):
             e2e_mode = ("double-buffered frames on every rank: 1/N of frame k+1 per PCIe link, then copy-engine pushes into the "
                         "peers' mesh buffers over NVLink (b200cd_mesh_update_slice_async), overlapping build + query of frame k; "
                         "one whole-mesh H2D (summed over ranks) and one D2H per step inside the timed region")
-            prunner.part.mesh = mesh
+            if cxx_step:
+                prunner.mesh = mesh
+            else:
+                prunner.part.mesh = mesh
             torch.cuda.synchronize()
             dist.barrier()
             pm.close()
             dist.barrier()                                # nobody frees a frame another rank still has mapped
         frames[1].destroy()
+
+    if args.trace:  # three more (untimed) steps with an event behind every launch: per-kernel device timeline of every rank
+        barrier()
+        ctx.trace_enable(True)
+        for _ in range(3):
+            runner.step(bvh, mesh, params)
+        torch.cuda.synchronize()
+        ctx.trace_enable(False)
+        ctx.trace_dump(f"{args.trace}.rank{rank}.csv")
+        barrier()
 
     # ---- max over ranks
     t = torch.tensor([ms_total, ms_e2e, ms_e2e_serial], dtype=torch.float64, device=dev)
@@ -464,8 +552,9 @@ def run_gpu_arm(args, workload):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, ms_e2e_serial = float(t[0]), float(t[1]), float(t[2])
 
-    if partitioned:
+    if partitioned and not cxx_step:
         prunner.step(profile=True)  # one extra, untimed step (all ranks) with a synchronise after every phase
+    pstats = dict(prunner.stats) if partitioned else {}
 
     if rank == 0:
         K = args.steps
@@ -481,8 +570,9 @@ def run_gpu_arm(args, workload):
         recs = os.environ.get("B200CD_RECS", "1") != "0"
         recs = recs and 2 * nverts >= 3 * ntris  # api.cu run_build: only for (mostly) unshared vertices
         abytes = algorithmic_bytes(ntris, nverts, ncand, npairs, int(last.get("sort_passes", 8)), recs)
+        nloc = ntris
         if partitioned:  # rank 0's own Morton range (keys arrive from the exchange: no face-ordered records)
-            nloc = int(prunner.stats.get("local_triangles", ntris // world))
+            nloc = int(pstats.get("local_triangles", ntris // world))
             abytes = algorithmic_bytes(nloc, min(nverts, 3 * nloc), ncand, npairs, int(last.get("sort_passes", 8)), False)
         elif world > 1:  # per-rank share of the query stages
             abytes["traverse"] = 64 * ntris + 64 * ntris // world + 8 * ncand
@@ -504,11 +594,26 @@ def run_gpu_arm(args, workload):
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(workload, {}).get(dominant)
+        # the same stages against SURVEY.md section 8(d)'s CONTRACT bytes (the survey's planned layout, not ours): a fatter
+        # layout of ours cannot raise these fractions
+        cb = contract_bytes(nloc, min(nverts, 3 * nloc) if partitioned else nverts, npairs)
+        cms = {"morton": acc["ms_morton"] / K, "sort": acc["ms_sort"] / K, "tree": acc["ms_refit"] / K,
+               "query": (acc["ms_traverse"] + acc["ms_narrow"]) / K, "e2e": (acc["ms_build"] + acc["ms_query"]) / K}
+        contract = {}
+        for st_, ms in cms.items():
+            gbs = cb[st_] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            contract[st_] = {"bytes": int(cb[st_]), "ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        contract_stage = {"traverse": "query", "narrow": "query"}.get(dominant, dominant)
         roofline = {"bound": "hbm", "kernel": STAGE_KERNEL[dominant], "stage": dominant,
                     "achieved": stages[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": stages[dominant]["frac"], "traffic": traffic, "peak_source": peak_src,
                     "launch_ms": stages[dominant]["ms"], "algorithmic_bytes": stages[dominant]["algorithmic_bytes"],
                     "stages": stages,
+                    "frac_contract": contract[contract_stage]["frac"],
+                    "contract": dict(contract, note="SURVEY.md 8(d) bytes: K1 48N+16V, K2 200N, K3+K4 132N, K5 (traverse+narrow) "
+                                                    "100N+16V+8*pairs, e2e 480N+32V+8*pairs; `frac_contract` is the dominant "
+                                                    "kernel's stage (traverse and narrow share K5)"),
+                    "e2e_frac_contract": contract["e2e"]["frac"],
                     "e2e_algorithmic_bytes": int(sum(abytes.values())),
                     "e2e_frac": round(sum(abytes.values()) / ((acc["ms_build"] + acc["ms_query"]) / K * 1e-3) / 1e9 / peak, 4)
                     if acc["ms_build"] + acc["ms_query"] > 0 else None}
@@ -524,8 +629,15 @@ def run_gpu_arm(args, workload):
             "config": {"workload": workload, "triangles": ntris, "vertices": nverts,
                        "morton_box": "unit cube" if box else "reference constants (morton.h:45,51,57)",
                        "key_bits": 63, "pairs": npairs_total, "pairs_checksum": checksum,
+                       "pairs_match_oracle": matches_oracle(workload, npairs_total, checksum),
+                       "sort_passes": int(last.get("sort_passes", 0)),
+                       "sort_regime": "hybrid: radix passes over the top digits + per-run fix-up (steady state of this mesh)"
+                       if 0 < int(last.get("sort_passes", 0)) < 8 else "full: every digit",
                        "parallelism": "single GPU" if world == 1 else (
-                           f"partitioned x{world}: one Morton range per rank; (key, id) exchange and ghost records "
+                           f"partitioned x{world}, one library call per rank and step (b200cd_dist_step): one Morton range per "
+                           f"rank; histograms, (key, id) pairs, coarse boxes, ghost records and the pair lists go through NVLink "
+                           f"peer memory (CUDA IPC) ordered by flag barriers; local tree + query; sort on rank 0" if cxx_step else
+                           f"partitioned x{world} (Python orchestration): one Morton range per rank; (key, id) exchange and ghost records "
                            f"{'stored straight into the owners buffers over NVLink peer memory (CUDA IPC)' if prunner.peer_memory else 'over grouped NCCL send/recv'}; "
                            f"local tree + query; one padded NCCL all-gather of the pair lists + sort on rank 0" if partitioned else
                            f"query-sharded x{world}, replicated BVH, block-cyclic chunks of {args.chunk} sorted leaves, "
@@ -540,7 +652,12 @@ def run_gpu_arm(args, workload):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "traversal": traversal,
         }
         if partitioned:
-            line["partition"] = dict(prunner.stats, rank=0, build_ms=ctx.stats()["ms_build"], query_ms=ctx.stats()["ms_query"])
+            line["partition"] = dict(pstats, rank=0, build_ms=ctx.stats()["ms_build"])
+            if cxx_step:  # device times of rank 0's phases of the LAST timed step (CUDA events, barriers included)
+                line["partition"]["phase_ms"] = {k[3:]: round(v, 4) for k, v in pstats.items() if k.startswith("ms_")}
+        if scaling_base is not None:
+            line["scaling_base"] = scaling_base
+            line["speedup_same_workload"] = round(scaling_base["ms_per_step"] / ms_step, 3)
         if world == 1 and workload != SCALING_WORKLOAD and not args.no_scaling_base:
             # the N > 1 runs use sheets64m (strong scaling of a fixed 2^26-triangle mesh): its single-GPU time, measured
             # here in the same run, is the denominator of that scaling curve (this line's `value` is soup16m)
@@ -556,7 +673,8 @@ def run_gpu_arm(args, workload):
         torch.cuda.synchronize()
         dist.barrier()
         prunner.close()
-    bvh.destroy()
+    if not cxx_step:
+        bvh.destroy()
     mesh.destroy()
     if world > 1:
         dist.barrier()
@@ -570,13 +688,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="partitioned", choices=["partitioned", "replicated"],
-                    help="N > 1: one Morton range per rank (default) or replicated BVH with sharded queries")
+    ap.add_argument("--mode", default="partitioned", choices=["partitioned", "partitioned-py", "replicated"],
+                    help="N > 1: one Morton range per rank through b200cd_dist_step (default), the same orchestrated from Python "
+                         "over torch.distributed, or replicated BVH with sharded queries")
     ap.add_argument("--no-peer-memory", action="store_true",
                     help="partitioned mode: exchange (key, id) and ghosts with NCCL send/recv instead of peer-memory stores")
     ap.add_argument("--chunk", type=int, default=1 << 14, help="sorted leaves per block-cyclic query chunk (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 21, help="triangles in the cpu_baseline sample")
+    ap.add_argument("--trace", default=None, help="write a per-kernel device timeline of 3 extra steps to PATH.rank<r>.csv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for all steps together")
     ap.add_argument("--no-scaling-base", action="store_true", help="N = 1: skip the single-GPU run of the N > 1 workload")
     args = ap.parse_args()
     workload = args.workload or ("soup16m" if args.gpus == 1 else SCALING_WORKLOAD)

@@ -40,7 +40,7 @@ SYMBOLS = [
     "b200cd_unique_triangles", "b200cd_unique_triangles_device",
     "b200cd_dist_create", "b200cd_dist_export", "b200cd_dist_connect", "b200cd_dist_step", "b200cd_dist_barrier",
     "b200cd_dist_get_stats", "b200cd_dist_bvh", "b200cd_dist_destroy", "b200cd_nccl_unique_id", "b200cd_dist_nccl_init",
-    "b200cd_dist_broadcast_bvh",
+    "b200cd_dist_broadcast_bvh", "b200cd_trace_dump", "b200cd_trace_enable",
 ]
 
 DIST_BLOB_BYTES = 512
@@ -295,6 +295,13 @@ class Context:
 
     def synchronize(self):
         self._chk(lib().b200cd_synchronize(self.h), "synchronize")
+
+    def trace_enable(self, on=True):
+        lib().b200cd_trace_enable(C.c_int(1 if on else 0))
+
+    def trace_dump(self, path):
+        """append the kernel timeline collected since the last dump (needs B200CD_TRACE in the environment)"""
+        self._chk(lib().b200cd_trace_dump(self.h, os.fsencode(path)), "trace_dump")
 
     def stats(self):
         s = Stats()

@@ -721,6 +721,7 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
         broad_kernel_simple<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, 0, 1, BR_THREADS, nquery, 1, ghost_base,
                                                           d_entries, d_entry_count, d_cand, cand_cap, d_counters, d_nquery);
         count_launch();
+        trace_mark("broad_kernel_simple (ghost queries)", s);
         return;
     }
     const bool persistent = traversal_variant() == 2 && !foreign;  // ghost queries (few, no tree over them) use the simple kernel
@@ -730,6 +731,7 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
         entry_kernel<<<(groups + 127) / 128, 128, 0, s>>>(d_pairs, d_root_box, n, shard, nshards, chunk, gsize, groups, d_entries,
                                                           d_entry_count);
         count_launch();
+        trace_mark("entry_kernel", s);
     }
     if (persistent) {
         const uint32_t blocks = (nquery + BR_QB - 1) / BR_QB;
@@ -756,6 +758,7 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
                                                           d_counters, nullptr);
     }
     count_launch();
+    trace_mark("broad_kernel", s);
 }
 
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
@@ -774,6 +777,7 @@ void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_c
     else
         narrow_kernel<3><<<sms * 3 * 4, NR_THREADS, 0, s>>>(d_leaves, d_cand, cand_cap, d_out, out_cap, d_counters);
     count_launch();
+    trace_mark("narrow_kernel", s);
 }
 
 }  // namespace b200cd

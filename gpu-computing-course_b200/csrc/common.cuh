@@ -178,6 +178,11 @@ __device__ __forceinline__ void st256_cs(void* p, const float4& a, const float4&
 extern unsigned long long g_kernel_launches;
 inline void count_launch(unsigned n = 1) { g_kernel_launches += n; }
 
+// Kernel timeline for runs that cannot go under a profiler (several ranks): with B200CD_TRACE set in the environment
+// every trace_mark records a CUDA event behind the launches it names; b200cd_trace_dump writes "name,ms since the
+// previous mark" rows (device time, gaps included). Off (one predictable branch per call) otherwise.
+void trace_mark(const char* name, cudaStream_t s);
+
 inline int set_error(b200cd_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->last_error = msg;
     return code;

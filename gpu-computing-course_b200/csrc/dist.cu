@@ -263,6 +263,7 @@ void barrier(b200cd_dist* d, cudaStream_t s) {
     ++d->epoch;
     dist_barrier_kernel<<<1, 32, 0, s>>>(d->peers, d->comm, d->rank, d->world, d->epoch, d->timeout_ns);
     count_launch();
+    trace_mark("barrier", s);
 }
 
 void push(b200cd_dist* d, const void* src, uint64_t dst_off, uint64_t bytes, cudaStream_t s) {
@@ -270,6 +271,7 @@ void push(b200cd_dist* d, const void* src, uint64_t dst_off, uint64_t bytes, cud
     const uint32_t bx = std::min<uint32_t>((nvec + 255) / 256, 32u);
     dist_push_kernel<<<dim3(bx, d->world), 256, 0, s>>>(static_cast<const uint4*>(src), d->peers, dst_off, nvec, d->world);
     count_launch();
+    trace_mark("push", s);
 }
 
 void close_mappings(b200cd_dist* d) {
@@ -511,6 +513,7 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
 
     for (int attempt = 0; attempt < 4; ++attempt) {
         CD_CUDA(ctx, cudaEventRecord(d->ev[DE_START], s));
+        trace_mark("step_begin", s);
         // ---- reset what the peers will append to (ordered before their appends by barrier 1)
         CD_CUDA(ctx, cudaMemsetAsync(&d->comm->ghost_count, 0, 2 * sizeof(unsigned long long), s));  // ghost_count, gather_count
         CD_CUDA(ctx, cudaMemsetAsync(d->d_lhist, 0, sizeof(uint32_t) * 65536, s));
@@ -553,9 +556,12 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
         CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
         if (nlocal >= 2) {
             const uint32_t chunk = (nlocal + B200CD_QUERY_BLOCK - 1) / B200CD_QUERY_BLOCK * B200CD_QUERY_BLOCK;
+            CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q0], s));
             launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, nlocal, 0, 1, chunk, chunk, /*foreign*/ 0, 0u, b->d_entries,
                          b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s);
+            CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
             launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s, b->unshared_verts);
+            CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q2], s));
         }
         // the local candidate count: kept for the verdict (the ghost pass reuses counter 0)
         CD_CUDA(ctx, cudaMemcpyAsync(b->d_counters + 6, b->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
@@ -574,6 +580,7 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
         dist_gather_kernel<<<std::max(ctx->sm_count, 1), GA_THREADS, 0, s>>>(b->d_out, b->d_counters, b->cand_cap, b->out_cap, d->peers,
                                                                           d->gather0, d->gather_cap, d->ghost_cap, R, W);
         count_launch();
+        trace_mark("gather (verdicts + pairs to rank 0)", s);
         barrier(d, s);
         CD_CUDA(ctx, cudaMemcpyAsync(H->status, d->comm->status, sizeof(uint32_t) * DIST_MAX, cudaMemcpyDeviceToHost, s));
         CD_CUDA(ctx, cudaMemcpyAsync(H->counters, b->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
@@ -598,6 +605,12 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
             continue;
         }
         // ---- done: statistics, and on rank 0 the sort of the gathered list (asynchronous)
+        if (nlocal >= 2) {  // the LOCAL query's stage times (b200cd_get_stats), like b200cd_self_collide's
+            ctx->stats.ms_traverse = ev_ms(ctx, EV_Q0, EV_Q1);
+            ctx->stats.ms_narrow = ev_ms(ctx, EV_Q1, EV_Q2);
+            ctx->stats.ms_pair_sort = 0.f;
+            ctx->stats.ms_query = ev_ms(ctx, EV_Q0, EV_Q2);
+        }
         ctx->stats.candidates = ncand_local + ncand_ghost;
         ctx->stats.pairs = npair;
         ctx->stats.nodes_visited = H->counters[3];
@@ -632,6 +645,7 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
             d->stats.total_pairs = total;
             if (d_pairs_out) *d_pairs_out = d->d_sorted;
         }
+        trace_mark("pair sort (rank 0)", s);
         CD_CUDA(ctx, cudaEventRecord(d->ev[DE_SORT], s));
         CD_CUDA(ctx, cudaGetLastError());
         d->stats_pending = true;

@@ -481,10 +481,12 @@ void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint3
         build_kernel<false><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs,
                                                              d_leaves, d_root_box, list, list_count, capacity, nullptr, d_block_boxes);
     count_launch();
+    trace_mark("build_kernel", s);
     {
         upper_kernel<<<(capacity + 127) / 128, 128, 0, s>>>(list, list_count, capacity, d_keys, (int)n, d_flags, d_pairs,
                                                             d_root_box);
         count_launch();
+        trace_mark("upper_kernel", s);
     }
 }
 

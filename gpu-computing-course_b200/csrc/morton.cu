@@ -196,6 +196,7 @@ void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t first,
     else
         morton_kernel<63><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys, d_recs);
     count_launch();
+    trace_mark("morton_kernel", s);
 }
 
 }  // namespace b200cd

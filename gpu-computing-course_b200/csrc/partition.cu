@@ -11,6 +11,8 @@
 // The pair SET is unchanged: {a,b} with both triangles on one rank is found by that rank's own
 // query; a cross pair is found exactly once, by the higher rank, when the lower rank's triangle
 // arrives there as a ghost query (its box overlaps the partner's box, hence the partner's coarse box).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200cd {
@@ -82,6 +84,73 @@ __global__ void cut_box_finish_kernel(const uint32_t* __restrict__ boxes_ord, co
 }
 
 constexpr int GH_MAXK = 256;
+
+// The same cut, found from the top: ONE block walks the nodes that hold more than T leaves (they form the top of the
+// tree: at most n / T ~ K / 2 disjoint ones per level, one dependent 64-byte fetch per level, ~10 levels) instead of
+// every node being read to find out whether it is one of them (64 B x (n - 1): 0.32 ms at 2^25 leaves).
+// boxes: K x 6 floats; surplus cut nodes of a degenerate tree are merged into the last box.
+constexpr int CUT_THREADS = 256;
+__global__ void __launch_bounds__(CUT_THREADS)
+cut_box_topdown_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_box, uint32_t n, uint32_t T, uint32_t K,
+                       float* __restrict__ boxes) {
+    __shared__ int s_front[2][GH_MAXK];
+    __shared__ uint32_t s_nfront[2], s_nout;
+    __shared__ uint32_t s_last[6];  // order-preserving images: surplus boxes are merged here
+    const uint32_t tid = threadIdx.x;
+    const float inf = __int_as_float(0x7f800000);
+    for (uint32_t i = tid; i < K * 6; i += CUT_THREADS) boxes[i] = (i % 6) < 3 ? inf : -inf;
+    if (tid < 6) s_last[tid] = tid < 3 ? 0xffffffffu : 0u;
+    if (tid == 0) {
+        s_nfront[0] = s_nfront[1] = 0;
+        s_nout = 0;
+        if (n > 1 && n > T) {
+            s_front[0][0] = reinterpret_cast<const int*>(root_box)[6];
+            s_nfront[0] = 1;
+        }
+    }
+    __syncthreads();
+    if (n <= T || n <= 1) {  // the whole tree is below the cut: one box, the root's
+        if (tid < 6 && n) boxes[tid] = root_box[tid];
+        return;
+    }
+    int cur = 0;
+    while (s_nfront[cur]) {
+        const uint32_t cnt = s_nfront[cur];
+        for (uint32_t i = tid; i < cnt; i += CUT_THREADS) {
+            const int sidx = s_front[cur][i];
+            const Node32 l = pairs[sidx].c[0], r = pairs[sidx].c[1];
+            const uint32_t size[2] = {(uint32_t)sidx - (uint32_t)l.ext + 1u, (uint32_t)r.ext - (uint32_t)sidx};
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const Node32& c = side ? r : l;
+                if (size[side] > T && c.link >= 0) {  // still above the cut (at most n / T of these are alive at once)
+                    const uint32_t at = atomicAdd(&s_nfront[cur ^ 1], 1u);
+                    if (at < (uint32_t)GH_MAXK) { s_front[cur ^ 1][at] = c.link; continue; }
+                    // (cannot happen for T >= 2n / K; if it does the subtree is emitted whole: looser, still covering)
+                }
+                const uint32_t slot = atomicAdd(&s_nout, 1u);
+                if (slot + 1 < K) {
+                    float* b = boxes + 6 * (size_t)slot;
+                    b[0] = c.lo[0]; b[1] = c.lo[1]; b[2] = c.lo[2]; b[3] = c.hi[0]; b[4] = c.hi[1]; b[5] = c.hi[2];
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        atomicMin(&s_last[a], f2ord(c.lo[a]));
+                        atomicMax(&s_last[3 + a], f2ord(c.hi[a]));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_nfront[cur] = 0;
+            if (s_nfront[cur ^ 1] > (uint32_t)GH_MAXK) s_nfront[cur ^ 1] = GH_MAXK;
+        }
+        cur ^= 1;
+        __syncthreads();
+    }
+    if (tid < 6 && s_nout + 1 > K) boxes[6 * (size_t)(K - 1) + tid] = ord2f(s_last[tid]);
+}
 
 constexpr int GH_GROUP = 16;  // coarse boxes per super box
 
@@ -407,6 +476,7 @@ void launch_dist_plan(const uint32_t* d_hists, int world, int rank, int shift, u
     dist_hist_reduce_kernel<<<DIST_HIST_BLOCKS, DIST_HIST_BLOCK_BINS, 0, s>>>(d_hists, world, d_ghist, d_part);
     dist_plan_kernel<<<1, PP_THREADS, 0, s>>>(d_ghist, d_hists, d_part, shift, world, rank, d_plan);
     count_launch(2);
+    trace_mark("dist_hist_reduce+dist_plan", s);
 }
 
 void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* d_hist, int sms, cudaStream_t s) {
@@ -414,14 +484,26 @@ void launch_key_hist16(const uint64_t* d_keys, uint32_t n, int shift, uint32_t* 
     const uint32_t blocks = min((n + 255u) / 256u, (uint32_t)sms * 16u);
     key_hist16_kernel<<<blocks, 256, 0, s>>>(d_keys, n, shift, d_hist);
     count_launch();
+    trace_mark("key_hist16", s);
 }
 
 // d_scratch: K*6 + 1 words
 void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t K, uint32_t* d_scratch,
                         float* d_boxes, cudaStream_t s) {
     if (!K) return;
-    uint32_t* counter = d_scratch + 6 * (size_t)K;
     const uint32_t T = (uint32_t)(((uint64_t)n + K / 2 - 1) / max(K / 2, 1u));  // at most ~K cut nodes on a balanced tree
+    static int variant = -1;  // B200CD_CUT=scan: the round-1 version (every node looks at itself; A/B knob, read once)
+    if (variant < 0) {
+        const char* e = getenv("B200CD_CUT");
+        variant = (e && e[0] == 's') ? 1 : 0;
+    }
+    if (variant == 0 && K <= (uint32_t)GH_MAXK) {
+        cut_box_topdown_kernel<<<1, CUT_THREADS, 0, s>>>(d_pairs, d_root_box, n, T ? T : 1u, K, d_boxes);
+        count_launch();
+        trace_mark("cut_boxes (top-down)", s);
+        return;
+    }
+    uint32_t* counter = d_scratch + 6 * (size_t)K;
     cut_box_init_kernel<<<(K * 6 + 1 + 255) / 256, 256, 0, s>>>(d_scratch, K);
     count_launch();
     if (n > 1) {
@@ -430,6 +512,7 @@ void launch_chunk_boxes(const NodePair* d_pairs, const float* d_root_box, uint32
     }
     cut_box_finish_kernel<<<(K * 6 + 255) / 256, 256, 0, s>>>(d_scratch, d_root_box, n, T ? T : 1u, K, d_boxes);
     count_launch();
+    trace_mark("cut_boxes (3 kernels)", s);
 }
 
 int ghost_max_k() { return GH_MAXK; }
@@ -454,6 +537,7 @@ void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_
     ghost_kernel<true><<<(n + 255) / 256, 256, 0, s>>>(d_leaves, n, d_peer_boxes, npeers, K, peer_mask, nullptr, 0, nullptr,
                                                       d_peers, d_overall, d_block_boxes);
     count_launch(2);
+    trace_mark("ghost_kernel (select + send)", s);
 }
 
 }  // namespace b200cd

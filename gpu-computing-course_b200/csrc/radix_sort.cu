@@ -539,6 +539,7 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     count_launch();
     rs_scan<<<pl.npass, RS_RADIX, 0, s>>>(d_hist, nullptr);
     count_launch();
+    trace_mark("rs_histogram+scan", s);
     int cur = 0;
     for (int p = 0; p < pl.npass; ++p) {
         uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
@@ -551,6 +552,7 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
             rs_pass<false, false><<<tiles, RS_THREADS, rs_smem_bytes(false), s>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, pl.shift[p],
                                                         pl.mask[p], 0, 0u, nullptr, 0, nullptr, d_hist + p * RS_RADIX, status, d_ticket + p);
         count_launch();
+        trace_mark("rs_pass", s);
         cur ^= 1;
     }
     if (!hybrid) return cur;
@@ -558,6 +560,7 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     // ties still in their original order) items again over every digit. They exit at once when fix[0] == 0.
     rs_fixup<<<(n + RF_THREADS * RF_IPT - 1) / (RF_THREADS * RF_IPT), RF_THREADS, 0, s>>>(keys[cur], vals[cur], n, pl.shift[0], top, d_fix);
     count_launch();
+    trace_mark("rs_fixup", s);
     cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);  // small; the status words are cleared conditionally
     rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[cur], n, all, d_hist, d_fix, reinterpret_cast<uint4*>(d_tile_status),
                                                  (uint64_t)tiles * RS_RADIX * npass / 4);
@@ -571,6 +574,7 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
         count_launch();
         cur ^= 1;
     }
+    trace_mark("rs_fallback (idle unless a run was too long)", s);
     return cur;
 }
 
@@ -631,6 +635,7 @@ void radix_partition_to_peers(const uint64_t* keys_in, uint32_t iota_base, uint3
     rs_pass<true, true><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys_in, nullptr, nullptr, nullptr, n, 0, 0u, 1, iota_base,
                                                                 d_splitters, nsplit, d_peers, d_hist, d_tile_status, d_ticket);
     count_launch();
+    trace_mark("partition_to_peers", s);
 }
 
 }  // namespace b200cd

@@ -137,6 +137,12 @@ const char* b200cd_strerror(int status);
 const char* b200cd_last_error(const b200cd_ctx* ctx);
 int b200cd_abi_version(void);
 
+/* Debug aid, not a reference entry point: with B200CD_TRACE set in the environment the library records a CUDA event
+ * behind its kernel launches; this appends "name,milliseconds since the previous mark" rows (device time) to `path`
+ * and clears the list. For runs that cannot go under a profiler (several ranks). */
+int b200cd_trace_dump(b200cd_ctx* ctx, const char* path);
+void b200cd_trace_enable(int on); /* switch the recording on / off at run time (initial state: B200CD_TRACE set or not) */
+
 void b200cd_default_params(b200cd_params* p);
 
 /* Page-locked host buffers for callers that want full-rate H2D/D2H. */

@@ -12,8 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-budget", "20"], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
@@ -25,6 +25,10 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["metric"].startswith("Mtri/s end-to-end self-collision") and d["data"] == "synthetic" and d["dtype"] == "f64"
     assert d["config"]["workload"] == "soup16m" and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0
+    # the line says what it timed: the SAMPLE's size, and which workload it is a sample of
+    assert d["config"]["sample_of"]["triangles"] == 1 << 24 and 0 < d["config"]["triangles"] <= 1 << 24
+    assert d["config"]["full_workload"] == (d["config"]["triangles"] == 1 << 24)
+    assert abs(d["ms_per_step"] - 1e-3 * d["config"]["triangles"] / d["value"]) < 1e-2 * d["ms_per_step"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb and cb["unit"] == "Mtri/s"
     e = d["e2e"]
