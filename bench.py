@@ -397,7 +397,11 @@ def run_gpu_arm(args, workload):
         runner = _Step()
     else:
         runner = mgpu.ShardedSelfCollision(cd, ctx, chunk=args.chunk)  # binds the library to torch's current stream
-        bvh = ctx.bvh_build(mesh, params)
+        if world > 1 and args.replicate == "broadcast":  # rank 0 alone builds; the others receive the BVH over NCCL
+            runner.broadcaster = mgpu.BvhBroadcaster(cd, ctx, ntris)
+            bvh = ctx.bvh_build(mesh, params) if rank == 0 else ctx.bvh_alloc_like(ntris)
+        else:
+            bvh = ctx.bvh_build(mesh, params)
 
     def barrier():
         if world > 1:
@@ -640,7 +644,7 @@ def run_gpu_arm(args, workload):
                            f"partitioned x{world} (Python orchestration): one Morton range per rank; (key, id) exchange and ghost records "
                            f"{'stored straight into the owners buffers over NVLink peer memory (CUDA IPC)' if prunner.peer_memory else 'over grouped NCCL send/recv'}; "
                            f"local tree + query; one padded NCCL all-gather of the pair lists + sort on rank 0" if partitioned else
-                           f"query-sharded x{world}, replicated BVH, block-cyclic chunks of {args.chunk} sorted leaves, "
+                           f"query-sharded x{world}, replicated BVH ({'built on rank 0, broadcast with NCCL (b200cd_dist_broadcast_bvh)' if args.replicate == 'broadcast' else 'built on every rank'}), block-cyclic chunks of {args.chunk} sorted leaves, "
                            f"NCCL gather + sort on rank 0"),
                        "l2_policy": "inputs larger than L2 (mesh + BVH >> 126 MB); no explicit flush"},
             "bvh_build_ms": round(acc["ms_build"] / K, 4), "query_ms": round(acc["ms_query"] / K, 4),
@@ -662,6 +666,28 @@ def run_gpu_arm(args, workload):
             # the N > 1 runs use sheets64m (strong scaling of a fixed 2^26-triangle mesh): its single-GPU time, measured
             # here in the same run, is the denominator of that scaling curve (this line's `value` is soup16m)
             line["scaling_base"] = device_value(cd, mg, mgpu, ctx, SCALING_WORKLOAD, steps=max(3, min(args.steps, 5)))
+        if world == 1 and box is None and not args.no_gpu_reference:
+            # the reference's OWN GPU kernels (bvh.cuh:125,146,258, collision.cuh:73 with main.cu:92-142's launch grids),
+            # compiled for sm_100a from /root/reference into oracle/_ref, on this same B200 and mesh: needs a mesh inside the
+            # reference's hard-coded Morton box with unique codes (flag1m, cloth1m). Its Morton codes and sort run on the HOST
+            # (load_obj.h:91,107) and are not in these four numbers.
+            try:
+                from oracle import refcd
+                if refcd.available():
+                    rm = refcd.RefMesh.from_arrays(xyz, idx)
+                    rp, rms = rm.gpu_run(repeats=5)
+                    host_ms = rm.timing()["load"]
+                    rm.close()
+                    rsum = sum(rms.values())
+                    line["gpu_reference_baseline"] = {
+                        "what": "reference CUDA kernels, unmodified, sm_100a build, same GPU, same mesh; minimum of 5 runs",
+                        "stages_ms": {k: round(v, 4) for k, v in rms.items()}, "gpu_ms": round(rsum, 4),
+                        "mtri_per_s_gpu_stages_only": round(ntris / rsum / 1e3, 2),
+                        "host_morton_and_sort_ms": round(host_ms, 1),
+                        "pairs": int(len(rp)), "pairs_equal_ours": bool(len(rp) == npairs_total),
+                        "ours_ms_per_step": round(ms_step, 4), "ours_over_reference_gpu_stages": round(rsum / ms_step, 2)}
+            except Exception as e:  # noqa: BLE001
+                line["gpu_reference_baseline"] = {"unavailable": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             vals, info = cpu_reference_run(workload, args.cpu_sample, 1)
             line["cpu_baseline"] = {"value": round(vals[0], 4), "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
@@ -673,6 +699,8 @@ def run_gpu_arm(args, workload):
         torch.cuda.synchronize()
         dist.barrier()
         prunner.close()
+    elif world > 1 and getattr(runner, "broadcaster", None) is not None:
+        runner.broadcaster.close()
     if not cxx_step:
         bvh.destroy()
     mesh.destroy()
@@ -691,12 +719,15 @@ def main():
     ap.add_argument("--mode", default="partitioned", choices=["partitioned", "partitioned-py", "replicated"],
                     help="N > 1: one Morton range per rank through b200cd_dist_step (default), the same orchestrated from Python "
                          "over torch.distributed, or replicated BVH with sharded queries")
+    ap.add_argument("--replicate", default="rebuild", choices=["rebuild", "broadcast"],
+                    help="--mode replicated: every rank builds the (deterministic) BVH, or rank 0 builds and NCCL broadcasts it")
     ap.add_argument("--no-peer-memory", action="store_true",
                     help="partitioned mode: exchange (key, id) and ghosts with NCCL send/recv instead of peer-memory stores")
     ap.add_argument("--chunk", type=int, default=1 << 14, help="sorted leaves per block-cyclic query chunk (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 21, help="triangles in the cpu_baseline sample")
     ap.add_argument("--trace", default=None, help="write a per-kernel device timeline of 3 extra steps to PATH.rank<r>.csv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="flag1m / cloth1m: skip the reference's own GPU kernels")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for all steps together")
     ap.add_argument("--no-scaling-base", action="store_true", help="N = 1: skip the single-GPU run of the N > 1 workload")
     args = ap.parse_args()

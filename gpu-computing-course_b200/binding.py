@@ -28,7 +28,7 @@ SYMBOLS = [
     "b200cd_mesh_update", "b200cd_mesh_info", "b200cd_mesh_download", "b200cd_mesh_destroy",
     "b200cd_bvh_build", "b200cd_bvh_rebuild", "b200cd_bvh_refit", "b200cd_bvh_download", "b200cd_bvh_validate",
     "b200cd_bvh_destroy", "b200cd_self_collide", "b200cd_self_collide_shard", "b200cd_self_collide_device",
-    "b200cd_sort_pairs_device", "b200cd_bvh_view_get", "b200cd_bvh_alloc_like",
+    "b200cd_sort_pairs_device", "b200cd_bvh_alloc_like",
     "b200cd_morton_keys_device", "b200cd_key_histogram_device", "b200cd_bvh_alloc_partial", "b200cd_bvh_key_buffers",
     "b200cd_partition_keys_device", "b200cd_bvh_build_partial", "b200cd_bvh_chunk_boxes_device",
     "b200cd_select_ghosts_device", "b200cd_bvh_ghost_buffer", "b200cd_collide_ghosts_device",
@@ -79,11 +79,6 @@ class DistStats(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
-
-
-class BvhView(C.Structure):
-    _fields_ = [("d_nodes", C.c_void_p), ("nodes_bytes", C.c_uint64), ("d_leaves", C.c_void_p),
-                ("leaves_bytes", C.c_uint64), ("d_ids", C.c_void_p), ("ids_bytes", C.c_uint64), ("ntris", C.c_uint32)]
 
 
 NODE32 = np.dtype([("lo", np.float32, 3), ("hi", np.float32, 3), ("left", np.int32), ("right", np.int32)])
@@ -253,11 +248,6 @@ class Bvh:
         out = Checks()
         self.ctx._chk(lib().b200cd_bvh_validate(self.ctx.h, self.h, mesh.h if mesh else None, C.byref(out)), "bvh_validate")
         return out.as_dict()
-
-    def view(self):
-        v = BvhView()
-        self.ctx._chk(lib().b200cd_bvh_view_get(self.ctx.h, self.h, C.byref(v)), "bvh_view_get")
-        return v
 
     def destroy(self):
         if self.h:

@@ -46,7 +46,7 @@ def main(argv=None):
     print(f"\nCollision pair ({len(pairs)} triangle pairs in total):")           # main.cu:149
     for a, b in pairs:
         print("%07u - %07u" % (a, b))                                            # main.cu:151
-    ids = sorted(set(pairs.reshape(-1).tolist()))
+    ids = ctx.unique_triangles(bvh).tolist()                                     # makeAndPrintSet (main.cu:33-45), on the device
     print(f"\n\nCollision Triangles:（{len(ids)} points in total）:")    # main.cu:40
     for t in ids:
         print(t)

@@ -852,15 +852,6 @@ API int b200cd_bvh_destroy(b200cd_bvh* bvh) {
     return B200CD_OK;
 }
 
-API int b200cd_bvh_view_get(b200cd_ctx* ctx, b200cd_bvh* bvh, b200cd_bvh_view* out) {
-    if (!ctx || !bvh || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
-    out->d_nodes = bvh->d_pairs;   out->nodes_bytes = bvh->n > 1 ? sizeof(NodePair) * (uint64_t)(bvh->n - 1) : 0;
-    out->d_leaves = bvh->d_leaves; out->leaves_bytes = sizeof(LeafRec) * (uint64_t)bvh->n;
-    out->d_ids = bvh->d_ids[bvh->cur]; out->ids_bytes = 4ull * bvh->n;
-    out->ntris = bvh->n;
-    return B200CD_OK;
-}
-
 API int b200cd_bvh_alloc_like(b200cd_ctx* ctx, uint32_t ntris, b200cd_bvh** out) {
     if (!ctx || !out) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
     *out = nullptr;

@@ -3,7 +3,7 @@
 SURVEY.md §8(e): the query shards naturally (queries are independent, the BVH is read-only) and
 has ONE exchange step, at the end. Each rank holds the whole BVH — built locally from the
 replicated mesh (the build is deterministic, so all ranks hold bit-identical trees and nothing
-crosses NVLink) or received from rank 0 (broadcast_bvh) — traverses its own subset of the
+crosses NVLink) or received from rank 0 (BvhBroadcaster: NCCL broadcast by the library) — traverses its own subset of the
 Morton-sorted query triangles (b200cd_self_collide_device with shard/nshards/chunk) and the
 per-rank pair lists are gathered on rank 0 and sorted there (b200cd_sort_pairs_device).
 
@@ -140,23 +140,32 @@ def unpack_pairs(words):
     return np.ascontiguousarray(a).view(np.uint32).reshape(-1, 2)
 
 
-def broadcast_bvh(cd, ctx, bvh, ntris, src=0, group=None):
-    """Replicate a BVH built on rank `src`: NCCL broadcast of the three device blobs
-    (traversal nodes, leaf records, sorted ids). Other ranks pass bvh=None and get a new handle."""
-    rank = dist.get_rank(group)
-    if rank != src:
-        bvh = ctx.bvh_alloc_like(ntris)
-    v = bvh.view()
-    dev = torch.device("cuda", ctx.device)
-    for ptr, nbytes in ((v.d_nodes, v.nodes_bytes), (v.d_leaves, v.leaves_bytes), (v.d_ids, v.ids_bytes)):
-        if nbytes:
-            t = torch.as_tensor(_DeviceSpan(ptr, nbytes // 8), device=dev) if nbytes % 8 == 0 else None
-            if t is None:  # ids blob with an odd triangle count: 4-byte view
-                span = _DeviceSpan(ptr, nbytes // 4)
-                span.__cuda_array_interface__["typestr"] = "<i4"
-                t = torch.as_tensor(span, device=dev)
-            dist.broadcast(t, src=src, group=group)
-    return bvh
+class BvhBroadcaster:
+    """Replicated mode, "each GPU ... receives the BVH, broadcast via NCCL over NVLink" (BASELINE.json north_star): the
+    LIBRARY owns an NCCL communicator (b200cd_dist_nccl_init; the 128-byte unique id travels through torch.distributed
+    once) and b200cd_dist_broadcast_bvh sends the three device blobs of a BVH built on `src` - traversal nodes, leaf
+    records, sorted ids - to BVHs of the same shape on the other ranks."""
+
+    def __init__(self, cd, ctx, ntris, group=None):
+        self.cd, self.ctx, self.group, self.ntris = cd, ctx, group, ntris
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ctx.set_stream(torch.cuda.current_stream(torch.device("cuda", ctx.device)).cuda_stream)
+        self.dist = ctx.dist_create(self.rank, self.world, 0)       # only the communicator is used
+        box = [cd.nccl_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        self.dist.nccl_init(box[0])
+
+    def receive_or_send(self, bvh, src=0):
+        """rank `src` passes its built BVH; the others pass None (a BVH is allocated) or a BVH from an earlier call"""
+        if self.rank != src and bvh is None:
+            bvh = self.ctx.bvh_alloc_like(self.ntris)
+        self.dist.broadcast_bvh(bvh, src)
+        return bvh
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.dist.destroy()
 
 
 class ShardedSelfCollision:
@@ -168,12 +177,17 @@ class ShardedSelfCollision:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = torch.device("cuda", ctx.device)
         self.counts = [0] * self.world
+        self.broadcaster = None  # set to a BvhBroadcaster: rank 0 alone builds and the others RECEIVE the BVH over NCCL
         # library kernels, NCCL transfers and the final sort are ordered on ONE stream: torch's current one
         ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def step(self, bvh, mesh, params, rebuild=True):
         """one build + sharded query + gather; returns the device tensor of all pairs on rank 0"""
-        if rebuild:
+        if rebuild and self.broadcaster is not None:
+            if self.rank == 0:
+                self.ctx.bvh_rebuild(bvh, mesh, params)
+            self.broadcaster.receive_or_send(bvh, 0)
+        elif rebuild:
             self.ctx.bvh_rebuild(bvh, mesh, params)
         # per-rank lists stay unsorted: the merged list is sorted once, on rank 0
         ptr, count = self.ctx.self_collide_device(bvh, sorted=(self.world == 1), shard=self.rank,

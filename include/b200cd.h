@@ -277,17 +277,8 @@ int b200cd_unique_triangles(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t* ids_out,
  * ID (0 = 32). In place; asynchronous on the context's stream. */
 int b200cd_sort_pairs_device(b200cd_ctx* ctx, void* d_pairs, uint64_t count, uint32_t id_bits);
 
-/* Device views for replicating a built BVH to other ranks (NCCL broadcast is
- * done by the caller on these buffers): three blobs — traversal nodes, leaf
- * records, sorted ids. b200cd_bvh_alloc_like creates an empty BVH of the same
- * shape on the receiving rank. */
-typedef struct b200cd_bvh_view {
-    void* d_nodes;   uint64_t nodes_bytes;
-    void* d_leaves;  uint64_t leaves_bytes;
-    void* d_ids;     uint64_t ids_bytes;
-    uint32_t ntris;
-} b200cd_bvh_view;
-int b200cd_bvh_view_get(b200cd_ctx* ctx, b200cd_bvh* bvh, b200cd_bvh_view* out);
+/* An empty BVH of the shape of one built over `ntris` triangles: the receiving side of b200cd_dist_broadcast_bvh
+ * (replicated multi-GPU mode: rank 0 builds, the others receive nodes, leaf records and sorted ids over NCCL). */
 int b200cd_bvh_alloc_like(b200cd_ctx* ctx, uint32_t ntris, b200cd_bvh** out);
 
 /* ---- partitioned multi-GPU build ------------------------------------------

@@ -21,6 +21,11 @@
  *     which is what the reference's GPU path uses (bvh.cuh:48); zeroed node storage
  *     (Node() leaves isLeaf/idx/childCount uninitialised, bvh.cuh:38-42); a pair
  *     buffer that grows (main.cu:81 fixes it at 500 pairs).
+ *   also here (ref_gpu_run): the reference's own GPU KERNELS - fillLeafNodes (bvh.cuh:125),
+ *     generateHierarchyParallel (bvh.cuh:146), calBoundingBox (bvh.cuh:258), findCollisions
+ *     (collision.cuh:73) - launched with the grids of main.cu:92,99,107,140-142 on whatever GPU is
+ *     present (sm_100a SASS), timed with CUDA events like main.cu:91-94. bench.py prints them as
+ *     `gpu_reference_baseline` next to our numbers for the flag-sized mesh.
  *   not linked: findCollisionsCpu (cpu.cuh:247-271) reads threadIdx in host code;
  *     it is dropped by -fvisibility=hidden + --gc-sections.
  */
@@ -34,6 +39,7 @@
 
 #include "load_obj.h"
 #include "cpu.cuh"
+#include "collision.cuh"   // the reference's GPU kernels (findCollisions; bvh.cuh's kernels come with cpu.cuh)
 
 int clzll(unsigned long long x, int) { return x ? __builtin_clzll(x) : 64; }
 
@@ -254,6 +260,85 @@ REF_API void ref_get_pairs(void* h, uint32_t* out) {
 REF_API void ref_get_timing(void* h, double* ms5) {
     auto* m = static_cast<RefMesh*>(h);
     ms5[0] = m->ms_load; ms5[1] = m->ms_fill; ms5[2] = m->ms_hier; ms5[3] = m->ms_refit; ms5[4] = m->ms_query;
+}
+
+/* ---- the reference's GPU path (main.cu:78-146) on the mesh held by `h` ----
+ * Ours: zeroed node arrays and pair counter (main.cu:82-85 cudaMalloc only: the reference relies on fresh
+ * allocations being zero), a pair buffer of `pair_cap` pairs instead of 500 (main.cu:81; the
+ * kernel appends unguarded, collision.cuh:40-42, so pair_cap must exceed the true count), `repeats` timed runs
+ * (stage times = minimum over the runs). Returns 0, or a negative code: -1 no device, -2 CUDA error,
+ * -3 more pairs than pair_cap. ms4 = {fillLeafNodes, generateHierarchyParallel, calBoundingBox, findCollisions}. */
+REF_API int ref_gpu_run(void* h, uint32_t pair_cap, int repeats, float* ms4, uint64_t* count_out) {
+    auto* m = static_cast<RefMesh*>(h);
+    const size_t n = m->tris.size();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return -1; }
+    if (n < 2) return -2;
+    vec3f* v_ptr = nullptr; Triangle* t_ptr = nullptr; unsigned long long* m_ptr = nullptr;
+    Node *leaf_nodes = nullptr, *internal_nodes = nullptr;
+    unsigned int *collision_list = nullptr, *test_val = nullptr, *wrong = nullptr;
+    cudaEvent_t ev[5];
+    bool ok = true;
+    auto C = [&](cudaError_t e) { if (e != cudaSuccess) ok = false; };
+    for (auto& e : ev) C(cudaEventCreate(&e));
+    C(cudaMalloc((void**)&v_ptr, m->verts.size() * sizeof(vec3f)));
+    C(cudaMalloc((void**)&t_ptr, n * sizeof(Triangle)));
+    C(cudaMalloc((void**)&m_ptr, n * sizeof(unsigned long long)));
+    C(cudaMalloc((void**)&collision_list, 2 * (size_t)pair_cap * sizeof(unsigned int)));
+    C(cudaMalloc((void**)&test_val, sizeof(unsigned int)));
+    C(cudaMalloc((void**)&wrong, 5 * sizeof(unsigned int)));
+    C(cudaMalloc((void**)&leaf_nodes, n * sizeof(Node)));
+    C(cudaMalloc((void**)&internal_nodes, (n - 1) * sizeof(Node)));
+    if (ok) {
+        C(cudaMemcpy(v_ptr, m->verts.data(), m->verts.size() * sizeof(vec3f), cudaMemcpyHostToDevice));
+        C(cudaMemcpy(t_ptr, m->tris.data(), n * sizeof(Triangle), cudaMemcpyHostToDevice));
+        C(cudaMemcpy(m_ptr, m->mortons.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    float best[4] = {1e30f, 1e30f, 1e30f, 1e30f};
+    unsigned int count = 0;
+    for (int r = 0; ok && r < (repeats < 1 ? 1 : repeats); ++r) {
+        C(cudaMemset(leaf_nodes, 0, n * sizeof(Node)));
+        C(cudaMemset(internal_nodes, 0, (n - 1) * sizeof(Node)));
+        C(cudaMemset(test_val, 0, sizeof(unsigned int)));
+        C(cudaMemset(wrong, 0, 5 * sizeof(unsigned int)));
+        C(cudaEventRecord(ev[0], 0));
+        fillLeafNodes<<<128, 128>>>(t_ptr, (int)n, leaf_nodes);                                      // main.cu:92
+        C(cudaEventRecord(ev[1], 0));
+        generateHierarchyParallel<<<128, 128>>>(m_ptr, (int)n, leaf_nodes, internal_nodes, wrong);   // main.cu:99
+        C(cudaEventRecord(ev[2], 0));
+        calBoundingBox<<<128, 128>>>(leaf_nodes, v_ptr, (unsigned int)n);                            // main.cu:107
+        C(cudaEventRecord(ev[3], 0));
+        dim3 blocks(128, 128), threads(128);                                                         // main.cu:140-141
+        findCollisions<<<blocks, threads>>>(&internal_nodes[0], leaf_nodes, v_ptr, (unsigned int)n, test_val, collision_list);
+        C(cudaEventRecord(ev[4], 0));
+        C(cudaEventSynchronize(ev[4]));
+        C(cudaGetLastError());
+        for (int k = 0; ok && k < 4; ++k) {
+            float ms = 0.f;
+            C(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            if (ms < best[k]) best[k] = ms;
+        }
+        C(cudaMemcpy(&count, test_val, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        if (count > pair_cap) break;
+    }
+    int rc = ok ? 0 : -2;
+    if (ok && count > pair_cap) rc = -3;
+    if (rc == 0) {
+        m->npairs = count;
+        m->pairs.assign(2 * (size_t)count + 2, 0u);
+        if (count) C(cudaMemcpy(m->pairs.data(), collision_list, 2 * (size_t)count * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        unsigned int w = 0;
+        C(cudaMemcpy(&w, wrong, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        m->wrong_parent = w;
+        for (int k = 0; k < 4; ++k) ms4[k] = best[k];
+        if (count_out) *count_out = count;
+        if (!ok) rc = -2;
+    }
+    cudaFree(v_ptr); cudaFree(t_ptr); cudaFree(m_ptr); cudaFree(collision_list); cudaFree(test_val); cudaFree(wrong);
+    cudaFree(leaf_nodes); cudaFree(internal_nodes);
+    for (auto& e : ev) cudaEventDestroy(e);
+    cudaGetLastError();
+    return rc;
 }
 
 /* ---- unit hooks on the reference predicates ---- */

@@ -30,7 +30,7 @@ def lib():
         _LIB.ref_morton3D.restype = C.c_uint64
         _LIB.ref_morton3D.argtypes = [C.c_double] * 3
         for f in ("ref_free", "ref_num_verts", "ref_num_tris", "ref_get_mesh", "ref_get_sorted", "ref_build",
-                  "ref_get_nodes", "ref_collide", "ref_get_pairs", "ref_get_timing"):
+                  "ref_get_nodes", "ref_collide", "ref_get_pairs", "ref_get_timing", "ref_gpu_run"):
             getattr(_LIB, f).argtypes = None
         _LIB.ref_num_verts.restype = C.c_uint32
         _LIB.ref_num_tris.restype = C.c_uint32
@@ -113,6 +113,22 @@ class RefMesh:
         if cnt:
             lib().ref_get_pairs(self.h, _p(out, C.c_uint32))
         return out
+
+    def gpu_run(self, pair_cap=None, repeats=3):
+        """the reference's own GPU kernels (main.cu:92,99,107,142 launch configurations) on this mesh, on the current
+        CUDA device -> (pairs (count, 2) uint32 in discovery order, {stage: ms}); raises without a device"""
+        cap = int(pair_cap or max(500, self.n))
+        ms = (C.c_float * 4)()
+        cnt = C.c_uint64()
+        rc = lib().ref_gpu_run(self.h, C.c_uint32(cap), C.c_int(repeats), ms, C.byref(cnt))
+        if rc != 0:
+            raise RuntimeError({-1: "no CUDA device", -2: "CUDA error in the reference kernels",
+                                -3: "more pairs than pair_cap"}.get(rc, f"ref_gpu_run: {rc}"))
+        out = np.empty((cnt.value, 2), np.uint32)
+        if cnt.value:
+            lib().ref_get_pairs(self.h, _p(out, C.c_uint32))
+        return out, dict(zip(("fillLeafNodes", "generateHierarchyParallel", "calBoundingBox", "findCollisions"),
+                             [float(x) for x in ms]))
 
     def timing(self):
         t = np.zeros(5, np.float64)

@@ -1,7 +1,9 @@
-"""torchrun --nproc-per-node N tests/run_multigpu_check.py  (needs N >= 2 B200s; not collected by pytest)
+"""torchrun --nproc-per-node N tests/run_multigpu_check.py  (needs N >= 2 B200s; not collected by pytest -
+tests/test_gpu_dist.py covers the multi-rank step on the driver's single-GPU box with ranks sharing the GPU)
 
-Checks on real GPUs that the partitioned build (peer-memory and NCCL variants) and the sharded upload give
-exactly the replicated / single-GPU pair list."""
+Checks on real GPUs, over NVLink, that every multi-GPU mode gives exactly the single-GPU pair list: the C++ step
+(b200cd_dist_step), the replicated BVH (built everywhere, or built on rank 0 and broadcast with NCCL by the library),
+the Python-orchestrated partitioned build (peer-memory and NCCL send/recv variants), and the sharded uploads."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -46,9 +48,42 @@ for name, (xyz, idx), box in (("soup4m", mg.soup(1 << 22, seed=5), ((0,0,0),(1,1
     for m in fr:
         m.destroy()
     bvh = ctx.bvh_build(mesh, p)
+    single = ctx.self_collide(bvh, sorted=True)            # what ONE GPU gives (every rank computes it for itself)
     sh = mgpu.ShardedSelfCollision(cd, ctx)
     ref = sh.step(bvh, mesh, p)
     ref_np = mgpu.unpack_pairs(ref) if rank == 0 else None
+    if rank == 0:
+        assert np.array_equal(ref_np, single), "replicated + sharded query differs from the single-GPU list"
+        print(name, "replicated (every rank builds) OK", len(single), flush=True)
+    # replicated, BVH received: rank 0 builds, the library broadcasts nodes / leaf records / ids with NCCL
+    bc = mgpu.BvhBroadcaster(cd, ctx, mesh.ntris)
+    rbvh = bvh if rank == 0 else None
+    for it in range(2):
+        if rank == 0:
+            ctx.bvh_rebuild(bvh, mesh, p)
+        rbvh = bc.receive_or_send(rbvh, 0)
+        got = sh.step(rbvh, mesh, p, rebuild=False)
+        if rank == 0:
+            assert np.array_equal(mgpu.unpack_pairs(got), single), "broadcast BVH: sharded query differs"
+    if rank != 0:
+        chk = rbvh.validate()                               # the received tree passes the reference's self-checks
+        assert chk["null_parent_internal"] == 1 and chk["wrong_bound_count"] == 0 and chk["null_child"] == 0, chk
+        rbvh.destroy()
+    bc.close()
+    if rank == 0: print(name, "replicated (BVH broadcast over NCCL by the library) OK", flush=True)
+    # the multi-GPU step in C++ (b200cd_dist_step): one call per rank and frame
+    ds = mgpu.DistSelfCollision(cd, ctx, mesh, p)
+    for it in range(3):
+        got = ds.step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            g = mgpu.unpack_pairs(got)
+            ok = np.array_equal(g, single)
+            st = ds.stats
+            print(name, "b200cd_dist_step iter", it, "pairs", len(g), "OK" if ok else "MISMATCH",
+                  {k: st[k] for k in ("local_triangles", "ghosts", "retries", "ms_step")}, flush=True)
+            assert ok
+    ds.close()
     for pm in (True, False):
         pr = mgpu.PartitionedSelfCollision(cd, ctx, mesh, p, peer_memory=pm)
         for it in range(3):

@@ -79,3 +79,17 @@ def test_create_fails_loudly_without_device_or_with_bad_args(cd):
     assert lib.b200cd_get_stats(None, None) == cd.E_INVALID
     assert lib.b200cd_mesh_info(None, None, None) == cd.E_INVALID
     assert lib.b200cd_destroy(None) == cd.OK
+
+
+def test_cxx_example_is_built_and_fails_loudly_without_a_gpu(cd):
+    """examples/ref_main.cpp (the reference's main() on the C ABI) links libb200cd.so; no GPU -> a status, not exit()"""
+    exe = os.path.join(ROOT, "gpu-computing-course_b200", "lib", "b200cd_run")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples")])
+    assert os.path.exists(exe)
+    assert "libb200cd.so" in subprocess.check_output(["ldd", exe], text=True)
+    h = C.c_void_p()
+    if cd.lib().b200cd_create(C.c_int(0), C.byref(h)) == cd.OK:
+        cd.lib().b200cd_destroy(h)
+        return  # GPU box: tests/test_gpu_example.py runs it for real
+    out = subprocess.run([exe, "whatever.obj"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "no CPU fallback" in out.stderr
