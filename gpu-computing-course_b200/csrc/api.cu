@@ -122,6 +122,8 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_fix);
     if (b->h_fix) cudaFreeHost(b->h_fix);
     if (b->ev_fix) cudaEventDestroy(b->ev_fix);
+    for (int i = 0; i < 4; ++i)
+        if (b->ev_sort[i]) cudaEventDestroy(b->ev_sort[i]);
     cudaFree(b->d_flags);
     cudaFree(b->d_build_scratch);
     cudaFree(b->d_pairs);
@@ -132,6 +134,7 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_cut_scratch);
     cudaFree(b->d_peers);
     cudaFree(b->d_ghost_in_count);
+    cudaFree(b->d_ghost_list);
     cudaFree(b->d_root_box);
     cudaFree(b->d_cand);
     cudaFree(b->d_entries);
@@ -179,14 +182,18 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
         if (rc == B200CD_OK && (cudaMallocHost(reinterpret_cast<void**>(&b->h_fix), 4 * sizeof(uint32_t)) != cudaSuccess ||
                                 cudaEventCreateWithFlags(&b->ev_fix, cudaEventDisableTiming) != cudaSuccess))
             rc = set_error(ctx, B200CD_E_NOMEM, "cudaMallocHost failed");
+        for (int i = 0; i < 4 && rc == B200CD_OK; ++i)
+            if (cudaEventCreate(&b->ev_sort[i]) != cudaSuccess) rc = set_error(ctx, B200CD_E_NOMEM, "cudaEventCreate failed");
     }
     A(dev_alloc(ctx, &b->d_pairs, n));
     A(dev_alloc(ctx, &b->d_leaves, (uint64_t)n + ghost_cap));  // ghost records of a partitioned build live after the local leaves
     if (max_peers) {
         b->ghost_out_cap = ghost_cap;
+        b->max_peers = ghost_out ? max_peers : 0;
         if (ghost_out) A(dev_alloc(ctx, &b->d_ghost_out, (uint64_t)max_peers * ghost_cap));  // staging of the NCCL send/recv exchange only
         A(dev_alloc(ctx, &b->d_cut_scratch, (uint64_t)ghost_max_k() * 6 + 1));
         A(dev_alloc(ctx, &b->d_block_boxes, ((uint64_t)n / 256 + 1) * 8));
+        A(dev_alloc(ctx, &b->d_ghost_list, (uint64_t)n / 256 + 3));
         A(dev_alloc(ctx, &b->d_peers, 1));
         A(dev_alloc(ctx, &b->d_ghost_in_count, 2));
     }
@@ -289,17 +296,25 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
             if (b->fix_pending && landed == cudaSuccess) {
                 b->fix_pending = false;
                 const uint32_t overflow = b->h_fix[0] & 1u, longest = b->h_fix[1], in_runs = b->h_fix[2];
+                float pass_ms = 0.f, fix_ms = 0.f;  // (the copy of h_fix landed behind them on the same stream)
+                if (cudaEventElapsedTime(&pass_ms, b->ev_sort[0], b->ev_sort[1]) != cudaSuccess ||
+                    cudaEventElapsedTime(&fix_ms, b->ev_sort[2], b->ev_sort[3]) != cudaSuccess) {
+                    cudaGetLastError();
+                    pass_ms = fix_ms = 0.f;
+                }
                 // (bit 1 of h_fix[0]: a key reached above the digit window - the fallback sorted that build; the window
                 // only ever moves up, so a mesh whose keys hover around a power of two does not fall back every frame)
                 if ((int)b->h_fix[3] > b->sort_top) b->sort_top = (int)b->h_fix[3];
                 if (overflow || longest > 24) {           // prefix too short for this mesh: sort more digits, for good
                     b->sort_high = overflow ? 8 : std::min(8, b->sort_high + 1);
                     b->sort_locked = true;
-                } else if ((uint64_t)in_runs * 4 > n && b->sort_high < 8) {
-                    // more than a quarter of the items sit in runs the fix-up has to order one thread per run (serial,
-                    // divergent: ~0.04 us per item in a run, against 0.009 us per item of the whole array for one more radix
-                    // pass; measured on the 2^25-triangle half of the two sheets: fix-up 1.31 ms behind 4 passes vs 0.09 ms
-                    // behind 5 passes of 0.29 ms each). For good, so that a mesh near the threshold does not flip every frame.
+                } else if (fix_ms > 1.3f * pass_ms && pass_ms > 0.f && b->sort_high < 8) {
+                    // The fix-up orders every run with ONE thread (serial insertion, divergent): cheap while runs are rare and
+                    // short, slow once most items sit in runs of 10+ (measured on the 2^25-triangle half of the two sheets:
+                    // 1.31 ms behind 4 passes against 0.09 ms behind 5 passes of 0.29 ms each). Its cost depends on the run
+                    // length distribution, so it is MEASURED (events around the previous build's fix-up and last pass): when
+                    // it exceeds one more radix pass plus the fix-up's floor (two reads of the keys, ~0.3 pass) the next build
+                    // sorts one digit more. For good, so that a mesh near the threshold does not flip every frame.
                     ++b->sort_high;
                     b->sort_locked = true;
                 } else if (!b->sort_locked && b->sort_high > 4 && longest <= 3 && (uint64_t)in_runs * 1024 < n) {
@@ -309,7 +324,7 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
             high = b->sort_high < 8 ? b->sort_high : 0;
         }
         b->cur = radix_sort(b->d_keys, b->d_ids, n, passes, npass, /*iota*/ !keys_given, b->d_hist, b->d_tile_status,
-                            b->tile_status_words, ctx->sm_count, s, high, b->d_fix, b->sort_top);
+                            b->tile_status_words, ctx->sm_count, s, high, b->d_fix, b->sort_top, high ? b->ev_sort : nullptr);
         if (high) {
             CD_CUDA(ctx, cudaMemcpyAsync(b->h_fix, b->d_fix, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CD_CUDA(ctx, cudaEventRecord(b->ev_fix, s));
@@ -971,6 +986,9 @@ API int b200cd_select_ghosts_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void
     if (!ctx || !bvh || !d_peer_boxes || !counts_out || npeers == 0 || npeers > 32 || K == 0 || K > (uint32_t)ghost_max_k())
         return set_error(ctx, B200CD_E_INVALID, "bad argument");
     if (!bvh->built || !bvh->d_ghost_out) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
+    // one outgoing list per peer was allocated: a larger npeers (or mask bits at or above it) would write past them
+    if (npeers > bvh->max_peers) return set_error(ctx, B200CD_E_INVALID, "npeers exceeds the max_peers given to b200cd_bvh_alloc_partial");
+    if (npeers < 32 && (peer_mask >> npeers)) return set_error(ctx, B200CD_E_INVALID, "peer_mask has bits at or above npeers");
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->stream;
     unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(ctx->d_scalars);  // 32 x u64 = 64 words
@@ -1165,6 +1183,7 @@ API int b200cd_bvh_set_peers(b200cd_ctx* ctx, b200cd_bvh* bvh, uint32_t nranks, 
     t.ghost_cap = bvh->ghost_cap;
     CD_CUDA(ctx, cudaMemcpyAsync(bvh->d_peers, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bvh->nranks = nranks;
     return B200CD_OK;
 }
 
@@ -1181,7 +1200,8 @@ API int b200cd_partition_counts_device(b200cd_ctx* ctx, const void* d_keys, uint
 API int b200cd_partition_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, const void* d_keys, uint32_t first_id, uint32_t count,
                                          const void* d_splitters, uint32_t nsplit, const void* d_recv_offsets) {
     if (!ctx || !bvh || !d_recv_offsets || (count && !d_keys) || (nsplit && !d_splitters) || nsplit > 15) return set_error(ctx, B200CD_E_INVALID, "bad argument");
-    if (!bvh->d_peers) return set_error(ctx, B200CD_E_INVALID, "b200cd_bvh_set_peers has not been called");
+    if (!bvh->d_peers || bvh->nranks == 0) return set_error(ctx, B200CD_E_INVALID, "b200cd_bvh_set_peers has not been called");
+    if (nsplit + 1 != bvh->nranks) return set_error(ctx, B200CD_E_INVALID, "nsplit + 1 differs from the nranks given to b200cd_bvh_set_peers");
     if (radix_tile_status_words(count, 1) > bvh->tile_status_words) return set_error(ctx, B200CD_E_INVALID, "slice larger than the BVH's scratch");
     DeviceGuard g(ctx->device);
     radix_partition_to_peers(static_cast<const uint64_t*>(d_keys), first_id, count, static_cast<const uint64_t*>(d_splitters),
@@ -1213,10 +1233,13 @@ API int b200cd_send_ghosts_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, con
     if (!ctx || !bvh || !d_peer_boxes || npeers == 0 || npeers > RS_MAX_SPLIT_P1 || K == 0 || K > (uint32_t)ghost_max_k())
         return set_error(ctx, B200CD_E_INVALID, "bad argument");
     if (!bvh->built || !bvh->d_peers) return set_error(ctx, B200CD_E_INVALID, "BVH not built / peers not set");
+    // the peer table holds entries for the ranks given to b200cd_bvh_set_peers only: anything else would index NULLs
+    if (npeers != bvh->nranks) return set_error(ctx, B200CD_E_INVALID, "npeers differs from the nranks given to b200cd_bvh_set_peers");
+    if (npeers < 32 && (peer_mask >> npeers)) return set_error(ctx, B200CD_E_INVALID, "peer_mask has bits at or above npeers");
     DeviceGuard g(ctx->device);
     if (!bvh->d_cut_scratch) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
     launch_ghosts_to_peers(bvh->d_leaves, bvh->n, static_cast<const float*>(d_peer_boxes), npeers, K, peer_mask, bvh->d_peers,
-                           reinterpret_cast<float*>(bvh->d_cut_scratch), bvh->d_block_boxes, ctx->stream);
+                           reinterpret_cast<float*>(bvh->d_cut_scratch), bvh->d_block_boxes, ctx->stream, bvh->d_ghost_list, ctx->sm_count);
     CD_CUDA(ctx, cudaGetLastError());
     return B200CD_OK;
 }
@@ -1318,7 +1341,7 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
         if (need_broad) {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
             launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, shard, nshards, chunk, nquery, /*foreign*/ 0, 0u, b->d_entries,
-                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s);
+                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s, nullptr, ctx->sm_count, !b->unshared_verts);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
         } else {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), s));

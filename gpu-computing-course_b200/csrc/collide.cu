@@ -188,7 +188,13 @@ constexpr int BR_REFILL = 24;                          // refill when this many 
 constexpr int BR_KEEP = 32;                            // start subtrees kept per group after the union-box filter
 constexpr int BR_CQ = 128;                             // candidate staging per warp: < 64 carried + <= 64 new per step
 
-template <int MIN_BLOCKS>  // resident CTAs per SM the register allocation is bounded for (6 -> 40 registers, 48 warps)
+// FILTER (meshes with shared vertices): a staged candidate whose two triangles share a vertex INDEX can never be a
+// contact (triangle.cuh:18-30, applied at collision.cuh:38 before the narrow phase) - and on a mesh those are almost
+// all the candidates (every triangle's ~12 edge / vertex neighbours overlap its box: 6.2 candidates per triangle on the
+// two sheets against 0.002 contacts). They are dropped when the warp's staging buffer is flushed: two 16-byte loads per
+// candidate (the index halves of the two leaf records), 32 candidates at a time, off the dependent node-fetch chain -
+// instead of 8 bytes written, 8 bytes and 2 x 32 bytes read again by the narrow phase for each of them.
+template <int MIN_BLOCKS, bool FILTER>  // resident CTAs per SM the register allocation is bounded for (6 -> 40 registers, 48 warps)
 __global__ void __launch_bounds__(BR_THREADS, MIN_BLOCKS)
 broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, uint32_t n, uint32_t shard,
              uint32_t nshards, uint32_t chunk, uint32_t nquery, uint32_t ngroups, int refill, const Node32* __restrict__ entries,
@@ -236,6 +242,29 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
     int sp = 0;
     uint32_t overflow = 0;  // a word, not a bool: nvcc packs bools into byte lanes and re-packs them (PRMT) on every path
 
+    // drop the staged candidates whose triangles share a vertex index (compaction in place, warp-wide)
+    auto filter = [&]() {
+        uint32_t kept = 0;
+        for (uint32_t i0 = 0; i0 < staged; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            bool keep = false;
+            uint2 c = make_uint2(0, 0);
+            if (i < staged) {
+                c = wq[i];
+                // second half of a leaf record: v2.z, vi[0], vi[1], vi[2] (16 bytes at offset 32)
+                const float4 a = __ldg(reinterpret_cast<const float4*>(leaves + c.x) + 2);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(leaves + c.y) + 2);
+                const uint32_t a0 = __float_as_uint(a.y), a1 = __float_as_uint(a.z), a2 = __float_as_uint(a.w);
+                const uint32_t b0 = __float_as_uint(b.y), b1 = __float_as_uint(b.z), b2 = __float_as_uint(b.w);
+                keep = !(a0 == b0 || a0 == b1 || a0 == b2 || a1 == b0 || a1 == b1 || a1 == b2 || a2 == b0 || a2 == b1 || a2 == b2);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);  // (every lane has read its slot: slots below are free to overwrite)
+            if (keep) wq[kept + __popc(m & lt)] = c;
+            kept += __popc(m);
+            __syncwarp();
+        }
+        staged = kept;
+    };
     auto flush = [&]() {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(counters + 0, (unsigned long long)staged);
@@ -254,7 +283,14 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
             if (candR) wq[staged + nL + __popc(bR & lt)] = make_uint2(q, (uint32_t)leafR);
             staged += nL + __popc(bR);
             __syncwarp();
-            if (staged >= BR_FLUSH) flush();
+            if (staged >= BR_FLUSH) {
+                if (FILTER) {
+                    filter();
+                    if (staged >= 32) flush();  // the few survivors wait for company (< 32 carried + <= 64 new < BR_CQ)
+                } else {
+                    flush();
+                }
+            }
         }
     };
 
@@ -348,6 +384,7 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
         }
         stage2((uint32_t)q, candL, leafL, candR, leafR);
     }
+    if (FILTER && staged) filter();
     if (staged) flush();
     if (overflow) atomicOr(counters + 2, ERR_STACK);
     visits = __reduce_add_sync(0xffffffffu, visits);
@@ -714,7 +751,7 @@ static int traversal_variant() {
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
                   uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries,
                   uint32_t* d_entry_count, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
-                  cudaStream_t s, const unsigned long long* d_nquery, int sms) {
+                  cudaStream_t s, const unsigned long long* d_nquery, int sms, bool shared_vertices) {
     if (nquery == 0 || n == 0 || (!foreign && n < 2)) return;
     if (foreign && d_nquery) {  // ghost queries whose count only the device knows: a fixed grid strides over the blocks
         const uint32_t blocks = std::min<uint32_t>((nquery + BR_THREADS - 1) / BR_THREADS, (uint32_t)std::max(sms, 1) * 8u);
@@ -746,12 +783,24 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
             const char* e = getenv("B200CD_BROAD_OCC");
             occ = (e && e[0] == '5') ? 5 : 6;
         }
-        if (occ == 5)
-            broad_kernel<5><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
-                                                          d_entries, d_entry_count, d_cand, cand_cap, d_counters);
+        static int filt = -1;  // B200CD_BROAD_FILTER=0: never drop shared-vertex candidates in the traversal (A/B knob)
+        if (filt < 0) {
+            const char* e = getenv("B200CD_BROAD_FILTER");
+            filt = (e && e[0] == '0') ? 0 : 1;
+        }
+        const bool filter = filt && shared_vertices;
+        if (filter && occ == 5)
+            broad_kernel<5, true><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
+                                                                d_entries, d_entry_count, d_cand, cand_cap, d_counters);
+        else if (filter)
+            broad_kernel<6, true><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
+                                                                d_entries, d_entry_count, d_cand, cand_cap, d_counters);
+        else if (occ == 5)
+            broad_kernel<5, false><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
+                                                                 d_entries, d_entry_count, d_cand, cand_cap, d_counters);
         else
-            broad_kernel<6><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
-                                                          d_entries, d_entry_count, d_cand, cand_cap, d_counters);
+            broad_kernel<6, false><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
+                                                                 d_entries, d_entry_count, d_cand, cand_cap, d_counters);
     } else {
         broad_kernel_simple<<<groups, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery,
                                                           foreign, ghost_base, d_entries, d_entry_count, d_cand, cand_cap,

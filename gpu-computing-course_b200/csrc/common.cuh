@@ -7,7 +7,10 @@
 
 #include "b200cd.h"
 
-#define B200CD_MAX_STACK 96  // traversal stack entries per query (tree depth <= 60 key bits + tie-break)
+// traversal stack entries per query: a query first parks every start subtree of its group that it overlaps (at most
+// B200CD_MAX_ENTRIES = 64) and then descends (at most one parked sibling per level: depth <= 63 key bits + 30 tie-break
+// bits = 93), so 160 covers the worst case of both together; only the entries actually used are ever touched
+#define B200CD_MAX_STACK 160
 #define B200CD_QUERY_BLOCK 256  // consecutive sorted leaves per traversal block (query chunks are multiples of this)
 #define B200CD_QUERY_GROUP 128  // smallest run of consecutive sorted leaves that shares one list of start subtrees
 #define B200CD_MAX_ENTRIES 64   // start subtrees recorded per group
@@ -107,7 +110,10 @@ struct b200cd_bvh {
     uint32_t* d_cut_scratch = nullptr;        // coarse-box reduction scratch (256*6+1 words)
     b200cd::PeerTable* d_peers = nullptr;     // peer-memory destinations (b200cd_bvh_set_peers)
     unsigned long long* d_ghost_in_count = nullptr;  // ghosts appended to MY ghost records by the peers (and by me)
+    uint2* d_ghost_list = nullptr;            // [cap / 256 + 2] (block, peer mask) items of the ghost selection's pre-filter
     uint64_t ghost_out_cap = 0;
+    uint32_t max_peers = 0;  // outgoing ghost lists allocated (b200cd_bvh_alloc_partial)
+    uint32_t nranks = 0;     // ranks given to b200cd_bvh_set_peers (0: not set)
     uint32_t nverts = 0;
     bool built = false;
     bool unshared_verts = false;  // mesh with (mostly) unshared vertices, V >= 1.5 N: a triangle soup (set by the build)
@@ -127,6 +133,7 @@ struct b200cd_bvh {
     int sort_high = 5;                 // digits sorted by radix passes (8 = plain full sort)
     int sort_top = 0;                  // significant key bits seen by the previous build (0 = unknown: all 63)
     bool sort_locked = false;          // a longer prefix was needed once: never try a shorter one again
+    cudaEvent_t ev_sort[4] = {};       // around the last radix pass and around the fix-up of the previous hybrid sort (timed)
     // hierarchy
     uint32_t* d_flags = nullptr;       // n-1 arrival counters of the splits merged through global memory
     void* d_build_scratch = nullptr;   // pending-subtree list of the tree build (lbvh.cu)
@@ -222,7 +229,8 @@ struct RadixPass { int shift; int bits; };
 // [3] significant key bits (highest set bit + 1). top_bits (0 = all): where the window of sorted digits ends.
 int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
                bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words,
-               int sms, cudaStream_t s, int high_passes = 0, uint32_t* d_fix = nullptr, int top_bits = 0);
+               int sms, cudaStream_t s, int high_passes = 0, uint32_t* d_fix = nullptr, int top_bits = 0,
+               cudaEvent_t* ev4 = nullptr /* hybrid: events recorded around the last radix pass [0,1] and the fix-up [2,3] */);
 // stable range partition (multi-GPU): bucket = number of device-resident splitters <= key; needs
 // d_hist >= 2*256+1 words and d_tile_status >= radix_tile_status_words(n, 1); counts land in d_hist[256..]
 void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t iota_base, uint64_t* keys_out,
@@ -287,7 +295,8 @@ void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxe
 // same selection, but the records are appended straight into the peers' ghost buffers (remote atomics + stores)
 void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                             uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, const float* d_block_boxes,
-                            cudaStream_t s);
+                            cudaStream_t s, uint2* d_list = nullptr /* scratch: n / 256 + 2 entries; enables the block pre-filter */,
+                            int sms = 148);
 // unique.cu: sorted set of the triangle IDs in a pair list (reference main.cu:33-45). d_bits: ceil(id_space / 32) words,
 // d_sums: ceil(words / 1024) + 1 words; *d_sums_total (last word of d_sums) receives the count; d_out: ids, ascending
 void launch_unique_mark(const uint2* d_pairs, uint64_t count, uint32_t id_space, uint32_t* d_bits, cudaStream_t s);
@@ -300,7 +309,8 @@ void launch_unique_emit(const uint32_t* d_bits, uint64_t words, const uint32_t* 
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
                   uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
                   uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s,
-                  const unsigned long long* d_nquery = nullptr /* foreign only: device-side query count (nquery = cap) */, int sms = 148);
+                  const unsigned long long* d_nquery = nullptr /* foreign only: device-side query count (nquery = cap) */, int sms = 148,
+                  bool shared_vertices = false /* a mesh (V < 1.5 N): drop vertex-sharing candidates in the traversal */);
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s, bool unshared_vertices = false);
 

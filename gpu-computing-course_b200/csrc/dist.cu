@@ -551,14 +551,14 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
         // ---- ghosts for the higher ranks leave while the local query runs
         if (mask_higher && nlocal)
             launch_ghosts_to_peers(b->d_leaves, nlocal, &d->comm->boxes[0][0], W, DIST_K, mask_higher, b->d_peers,
-                                   reinterpret_cast<float*>(b->d_cut_scratch), b->d_block_boxes, s);
+                                   reinterpret_cast<float*>(b->d_cut_scratch), b->d_block_boxes, s, b->d_ghost_list, ctx->sm_count);
         CD_CUDA(ctx, cudaEventRecord(d->ev[DE_GHOST_SEND], s));
         CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
         if (nlocal >= 2) {
             const uint32_t chunk = (nlocal + B200CD_QUERY_BLOCK - 1) / B200CD_QUERY_BLOCK * B200CD_QUERY_BLOCK;
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q0], s));
             launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, nlocal, 0, 1, chunk, chunk, /*foreign*/ 0, 0u, b->d_entries,
-                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s);
+                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s, nullptr, ctx->sm_count, !b->unshared_verts);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
             launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s, b->unshared_verts);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q2], s));

@@ -493,7 +493,7 @@ uint64_t radix_tile_status_words(uint32_t n, int npass) {
 
 int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
                bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words, int sms,
-               cudaStream_t s, int high_passes, uint32_t* d_fix, int top_bits) {
+               cudaStream_t s, int high_passes, uint32_t* d_fix, int top_bits, cudaEvent_t* ev4) {
     (void)tile_status_words;
     if (n == 0 || npass == 0) return 0;
     const bool hybrid = high_passes > 0 && high_passes < npass && d_fix && vals && npass % 2 == 0;
@@ -544,6 +544,7 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     for (int p = 0; p < pl.npass; ++p) {
         uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
         const int iota = (iota_values && p == 0) ? 1 : 0;
+        if (hybrid && ev4 && p == pl.npass - 1) cudaEventRecord(ev4[0], s);
         if (vals)
             rs_pass<true, false><<<tiles, RS_THREADS, rs_smem_bytes(true), s>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n,
                                                        pl.shift[p], pl.mask[p], iota, 0u, nullptr, 0, nullptr,
@@ -553,13 +554,16 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
                                                         pl.mask[p], 0, 0u, nullptr, 0, nullptr, d_hist + p * RS_RADIX, status, d_ticket + p);
         count_launch();
         trace_mark("rs_pass", s);
+        if (hybrid && ev4 && p == pl.npass - 1) cudaEventRecord(ev4[1], s);
         cur ^= 1;
     }
     if (!hybrid) return cur;
     // low bits: per-run fix-up; if a run was too long, the conditional kernels below sort the (already permuted,
     // ties still in their original order) items again over every digit. They exit at once when fix[0] == 0.
+    if (ev4) cudaEventRecord(ev4[2], s);
     rs_fixup<<<(n + RF_THREADS * RF_IPT - 1) / (RF_THREADS * RF_IPT), RF_THREADS, 0, s>>>(keys[cur], vals[cur], n, pl.shift[0], top, d_fix);
     count_launch();
+    if (ev4) cudaEventRecord(ev4[3], s);
     trace_mark("rs_fixup", s);
     cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);  // small; the status words are cleared conditionally
     rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[cur], n, all, d_hist, d_fix, reinterpret_cast<uint4*>(d_tile_status),
