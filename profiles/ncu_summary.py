@@ -46,6 +46,14 @@ def main(path):
             except ValueError:
                 cells.append(v)
         gbs = "-"
+        try:  # section captures carry the rate instead of the two byte counters: traffic = rate x duration
+            i = hdr.index("dram__bytes.sum.per_second")
+            rate = float(r[i].replace(",", "")) * {"byte/s": 1, "Kbyte/s": 1e3, "Mbyte/s": 1e6, "Gbyte/s": 1e9, "Tbyte/s": 1e12}[units[i]]
+            t, u = vals["time"]
+            secs = t * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}[u]
+            gbs = f"{rate / 1e9:.0f} ({rate * secs / 1e9:.3f} GB)"
+        except Exception:
+            pass
         try:
             def to_bytes(x):
                 f, u = x
