@@ -376,12 +376,17 @@ def run_gpu_arm(args, workload):
     cxx_step = partitioned and args.mode == "partitioned"
     if cxx_step:
         # each rank owns one Morton range; the whole step is ONE library call per rank (b200cd_dist_step, csrc/dist.cu)
-        prunner = mgpu.DistSelfCollision(cd, ctx, mesh, params)
+        # (pipelined frames: rank 0 sorts frame k's gathered list on a side stream while all ranks start frame k + 1;
+        #  --sync-sort keeps that sort on the main stream)
+        prunner = mgpu.DistSelfCollision(cd, ctx, mesh, params, async_sort=not args.sync_sort)
         bvh = prunner.dist.bvh()
 
         class _Step:
             def step(self, bvh_, mesh_, params_):
                 return prunner.step()
+
+            def wait(self):  # the last step's list is complete in stream order after this
+                prunner.wait_sorted()
         runner = _Step()
     elif partitioned:
         # the same algorithm orchestrated from Python over torch.distributed (round 1; kept for A/B and as the NCCL
@@ -403,6 +408,9 @@ def run_gpu_arm(args, workload):
         else:
             bvh = ctx.bvh_build(mesh, params)
 
+    if not hasattr(runner, "wait"):
+        runner.wait = lambda: None
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -412,6 +420,7 @@ def run_gpu_arm(args, workload):
     merged = None
     for _ in range(max(args.warmup, 3)):
         merged = runner.step(bvh, mesh, params)
+    runner.wait()
     npairs_total = int(merged.numel()) if rank == 0 else 0
     checksum = pairs_checksum(merged) if rank == 0 else None
     host_pairs = torch.empty(max(npairs_total, 1) + 1024, dtype=torch.int64).pin_memory() if rank == 0 else None
@@ -435,6 +444,7 @@ def run_gpu_arm(args, workload):
         for k in stage_keys:
             acc[k] += st[k]
         last = st
+    runner.wait()  # the final step's sorted list is part of the timed work
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -456,6 +466,7 @@ def run_gpu_arm(args, workload):
         else:                                             # 1/world of the mesh per PCIe link + NVLink all-gather
             mgpu.upload_mesh_sharded(ctx, mesh, xyz_ptr, idx_ptr)
             merged = runner.step(bvh, mesh, params)
+            runner.wait()
             if rank == 0:
                 host_pairs[: merged.numel()].copy_(merged, non_blocking=True)
                 d2h = 8 * int(merged.numel())
@@ -471,6 +482,7 @@ def run_gpu_arm(args, workload):
     ms_e2e_serial = ev2.elapsed_time(ev3)
     ms_e2e = ms_e2e_serial
     e2e_mode = "serial calls: b200cd_mesh_update, b200cd_bvh_rebuild, b200cd_self_collide (one frame at a time)"
+    ms_e2e_verts = None  # the same stream of frames when only the VERTICES change (a deforming mesh: static topology)
     if world == 1:
         # double-buffered frames (b200cd_mesh_update_async / b200cd_mesh_wait): the H2D of frame k+1 runs on the
         # copy stream while frame k is built and queried from the other mesh object. Still one H2D of the whole
@@ -479,21 +491,26 @@ def run_gpu_arm(args, workload):
         for k in range(2):                                # warm-up: allocates the second staging buffer, events, copy stream
             frames[k].update_async_from_ptr(xyz_ptr, idx_ptr)
             frames[k].wait()
-        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev4.record()
-        frames[0].update_async_from_ptr(xyz_ptr, idx_ptr)
-        for k in range(args.steps):
-            cur = frames[k % 2]
-            if k + 1 < args.steps:
-                frames[(k + 1) % 2].update_async_from_ptr(xyz_ptr, idx_ptr)
-            cur.wait()
-            ctx.bvh_rebuild(bvh, cur, params)
-            cnt = ctx.self_collide_into(bvh, host_pairs.data_ptr(), host_pairs.numel(), sorted=True)
-            d2h = 8 * cnt
-        ev5.record()
-        barrier()
-        ms_e2e = ev4.elapsed_time(ev5)
+
+        def stream_frames(index_ptr):
+            nonlocal d2h
+            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e_a.record()
+            frames[0].update_async_from_ptr(xyz_ptr, index_ptr)
+            for k in range(args.steps):
+                cur = frames[k % 2]
+                if k + 1 < args.steps:
+                    frames[(k + 1) % 2].update_async_from_ptr(xyz_ptr, index_ptr)
+                cur.wait()
+                ctx.bvh_rebuild(bvh, cur, params)
+                cnt = ctx.self_collide_into(bvh, host_pairs.data_ptr(), host_pairs.numel(), sorted=True)
+                d2h = 8 * cnt
+            e_b.record()
+            barrier()
+            return e_a.elapsed_time(e_b)
+        ms_e2e = stream_frames(idx_ptr)
+        ms_e2e_verts = stream_frames(None)
         e2e_mode = ("double-buffered frames: b200cd_mesh_update_async of frame k+1 overlaps b200cd_bvh_rebuild + "
                     "b200cd_self_collide of frame k; one full H2D and one D2H per step inside the timed region")
         frames[1].destroy()
@@ -508,32 +525,38 @@ def run_gpu_arm(args, workload):
                 pm.upload_async(k, xyz_ptr, idx_ptr)
                 pm.wait(k)
             torch.cuda.synchronize()
-            ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            ev4.record()
-            pm.upload_async(0, xyz_ptr, idx_ptr)
-            for k in range(args.steps):
-                if k + 1 < args.steps:
-                    pm.upload_async((k + 1) % 2, xyz_ptr, idx_ptr)
+
+            def set_mesh(m):
                 if cxx_step:
-                    prunner.mesh = pm.wait(k % 2)
+                    prunner.mesh = m
                 else:
-                    prunner.part.mesh = pm.wait(k % 2)
-                merged = prunner.step()
-                if rank == 0:
-                    host_pairs[: merged.numel()].copy_(merged, non_blocking=True)
-                    d2h = 8 * int(merged.numel())
-                torch.cuda.current_stream().synchronize()
-            ev5.record()
-            barrier()
-            ms_e2e = ev4.elapsed_time(ev5)
+                    prunner.part.mesh = m
+
+            def stream_frames(index_ptr):
+                nonlocal merged, d2h
+                e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                e_a.record()
+                pm.upload_async(0, xyz_ptr, index_ptr)
+                for k in range(args.steps):
+                    if k + 1 < args.steps:
+                        pm.upload_async((k + 1) % 2, xyz_ptr, index_ptr)
+                    set_mesh(pm.wait(k % 2))
+                    merged = prunner.step()
+                    runner.wait()
+                    if rank == 0:
+                        host_pairs[: merged.numel()].copy_(merged, non_blocking=True)
+                        d2h = 8 * int(merged.numel())
+                    torch.cuda.current_stream().synchronize()
+                e_b.record()
+                barrier()
+                return e_a.elapsed_time(e_b)
+            ms_e2e = stream_frames(idx_ptr)
+            ms_e2e_verts = stream_frames(None)
             e2e_mode = ("double-buffered frames on every rank: 1/N of frame k+1 per PCIe link, then copy-engine pushes into the "
                         "peers' mesh buffers over NVLink (b200cd_mesh_update_slice_async), overlapping build + query of frame k; "
                         "one whole-mesh H2D (summed over ranks) and one D2H per step inside the timed region")
-            if cxx_step:
-                prunner.mesh = mesh
-            else:
-                prunner.part.mesh = mesh
+            set_mesh(mesh)
             torch.cuda.synchronize()
             dist.barrier()
             pm.close()
@@ -545,16 +568,18 @@ def run_gpu_arm(args, workload):
         ctx.trace_enable(True)
         for _ in range(3):
             runner.step(bvh, mesh, params)
+        runner.wait()
         torch.cuda.synchronize()
         ctx.trace_enable(False)
         ctx.trace_dump(f"{args.trace}.rank{rank}.csv")
         barrier()
 
     # ---- max over ranks
-    t = torch.tensor([ms_total, ms_e2e, ms_e2e_serial], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_e2e_serial, ms_e2e_verts or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, ms_e2e_serial = float(t[0]), float(t[1]), float(t[2])
+    ms_e2e_verts = float(t[3]) if ms_e2e_verts else None
 
     if partitioned and not cxx_step:
         prunner.step(profile=True)  # one extra, untimed step (all ranks) with a synchronise after every phase
@@ -652,7 +677,12 @@ def run_gpu_arm(args, workload):
                     "ms_per_step": round(ms_e2e / K, 4), "mode": e2e_mode,
                     "serial_value": round(ntris / (ms_e2e_serial / K) / 1e3, 2),
                     "serial_ms_per_step": round(ms_e2e_serial / K, 4),
-                    "h2d_gbs": round(h2d / (ms_e2e / K * 1e-3) / 1e9, 1)},
+                    "h2d_gbs": round(h2d / (ms_e2e / K * 1e-3) / 1e9, 1),
+                    # NOT the headline: a deforming mesh keeps its topology, so a caller streams vertex positions only
+                    # (12 B x V per frame; the index array was uploaded once, outside the timed region)
+                    "vertex_frames": None if not ms_e2e_verts else {
+                        "value": round(ntris / (ms_e2e_verts / K) / 1e3, 2), "ms_per_step": round(ms_e2e_verts / K, 4),
+                        "h2d_bytes_per_step": 12 * nverts}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "traversal": traversal,
         }
         if partitioned:
@@ -721,6 +751,8 @@ def main():
                          "over torch.distributed, or replicated BVH with sharded queries")
     ap.add_argument("--replicate", default="rebuild", choices=["rebuild", "broadcast"],
                     help="--mode replicated: every rank builds the (deterministic) BVH, or rank 0 builds and NCCL broadcasts it")
+    ap.add_argument("--sync-sort", action="store_true",
+                    help="N > 1: rank 0 sorts the gathered pair list on the main stream instead of a side stream (no frame pipelining)")
     ap.add_argument("--no-peer-memory", action="store_true",
                     help="partitioned mode: exchange (key, id) and ghosts with NCCL send/recv instead of peer-memory stores")
     ap.add_argument("--chunk", type=int, default=1 << 14, help="sorted leaves per block-cyclic query chunk (N > 1)")

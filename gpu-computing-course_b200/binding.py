@@ -39,7 +39,7 @@ SYMBOLS = [
     "b200cd_mesh_ipc_export", "b200cd_mesh_set_peers", "b200cd_mesh_update_slice_async", "b200cd_partition_plan_device",
     "b200cd_unique_triangles", "b200cd_unique_triangles_device",
     "b200cd_dist_create", "b200cd_dist_export", "b200cd_dist_connect", "b200cd_dist_step", "b200cd_dist_barrier",
-    "b200cd_dist_get_stats", "b200cd_dist_bvh", "b200cd_dist_destroy", "b200cd_nccl_unique_id", "b200cd_dist_nccl_init",
+    "b200cd_dist_get_stats", "b200cd_dist_bvh", "b200cd_dist_destroy", "b200cd_dist_set_async_sort", "b200cd_dist_wait_sorted", "b200cd_nccl_unique_id", "b200cd_dist_nccl_init",
     "b200cd_dist_broadcast_bvh", "b200cd_trace_dump", "b200cd_trace_enable",
 ]
 
@@ -547,6 +547,13 @@ class Dist:
         ptr, cnt = C.c_void_p(), C.c_uint64()
         self.ctx._chk(lib().b200cd_dist_step(self.h, mesh.h, C.byref(params), C.byref(ptr), C.byref(cnt)), "dist_step")
         return ptr.value, int(cnt.value)
+
+    def set_async_sort(self, on=True):
+        """rank 0's final sort on a side stream (pipelined frames); call wait_sorted() before reading a step's list"""
+        self.ctx._chk(lib().b200cd_dist_set_async_sort(self.h, C.c_int(1 if on else 0)), "dist_set_async_sort")
+
+    def wait_sorted(self):
+        self.ctx._chk(lib().b200cd_dist_wait_sorted(self.h), "dist_wait_sorted")
 
     def barrier(self):
         self.ctx._chk(lib().b200cd_dist_barrier(self.h), "dist_barrier")

@@ -168,6 +168,14 @@ struct b200cd_dist {
     uint2* d_sorted = nullptr;       // rank 0: the gathered list, sorted
     uint2* d_sorted_tmp = nullptr;
     uint64_t sorted_cap = 0;
+    // rank 0's final sort can run on a side stream (b200cd_dist_set_async_sort), off the other ranks' critical path:
+    // they would otherwise wait for it at the first barrier of the next step
+    bool async_sort = false, sort_pending = false;
+    cudaStream_t sort_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_sorted = nullptr;
+    uint32_t* d_sort_hist = nullptr;      // radix scratch of that sort (the context's own may be in use on the main stream)
+    uint32_t* d_sort_status = nullptr;
+    uint64_t sort_status_words = 0;
     HostResult* h_res = nullptr;
     cudaEvent_t ev[DE_COUNT] = {};
     b200cd_dist_stats stats{};
@@ -339,7 +347,10 @@ API int b200cd_dist_create(b200cd_ctx* ctx, uint32_t rank, uint32_t world, uint3
         A(cudaMalloc(reinterpret_cast<void**>(&d->d_plan), sizeof(DistPlan)));
         A(cudaMalloc(reinterpret_cast<void**>(&d->d_boxes), sizeof(float) * DIST_K * 6));
         A(cudaMallocHost(reinterpret_cast<void**>(&d->h_res), sizeof(HostResult)));
-        if (!ctx->d_sort_hist) A(cudaMalloc(reinterpret_cast<void**>(&ctx->d_sort_hist), radix_hist_words(8) * sizeof(uint32_t)));
+        A(cudaMalloc(reinterpret_cast<void**>(&d->d_sort_hist), radix_hist_words(8) * sizeof(uint32_t)));
+        A(cudaStreamCreateWithFlags(&d->sort_stream, cudaStreamNonBlocking));
+        A(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&d->ev_sorted, cudaEventDisableTiming));
         for (int i = 0; i < DE_COUNT && rc == B200CD_OK; ++i) A(cudaEventCreate(&d->ev[i]));
     }
     if (rc == B200CD_OK) {
@@ -457,6 +468,14 @@ API int b200cd_dist_destroy(b200cd_dist* d) {
     cudaFree(d->d_part);
     cudaFree(d->d_plan);
     cudaFree(d->d_boxes);
+    if (d->sort_stream) {
+        cudaStreamSynchronize(d->sort_stream);
+        cudaStreamDestroy(d->sort_stream);
+    }
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    if (d->ev_sorted) cudaEventDestroy(d->ev_sorted);
+    cudaFree(d->d_sort_hist);
+    cudaFree(d->d_sort_status);
     cudaFree(d->d_sorted);
     cudaFree(d->d_sorted_tmp);
     if (d->h_res) cudaFreeHost(d->h_res);
@@ -473,6 +492,30 @@ API int b200cd_dist_barrier(b200cd_dist* d) {
     DeviceGuard g(d->ctx->device);
     barrier(d, d->ctx->stream);
     CD_CUDA(d->ctx, cudaGetLastError());
+    return B200CD_OK;
+}
+
+// Pipelined frames: with on != 0 rank 0's final sort of the gathered list runs on a side stream, so the rank (and with it
+// every other rank, at the next step's first barrier) goes straight on to the next frame. The list b200cd_dist_step
+// returned is then valid once b200cd_dist_wait_sorted has been called (it makes the context's stream wait for that sort,
+// no host blocking) - call it before reading the list; the next b200cd_dist_step does it implicitly.
+API int b200cd_dist_set_async_sort(b200cd_dist* d, int on) {
+    if (!d) return B200CD_E_INVALID;
+    DeviceGuard g(d->ctx->device);
+    if (!on && d->sort_pending) {
+        CD_CUDA(d->ctx, cudaStreamWaitEvent(d->ctx->stream, d->ev_sorted, 0));
+        d->sort_pending = false;
+    }
+    d->async_sort = on != 0;
+    return B200CD_OK;
+}
+
+API int b200cd_dist_wait_sorted(b200cd_dist* d) {
+    if (!d) return B200CD_E_INVALID;
+    if (!d->sort_pending) return B200CD_OK;
+    DeviceGuard g(d->ctx->device);
+    CD_CUDA(d->ctx, cudaStreamWaitEvent(d->ctx->stream, d->ev_sorted, 0));
+    d->sort_pending = false;
     return B200CD_OK;
 }
 
@@ -638,10 +681,24 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
                 CD_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d->d_sorted_tmp), want * sizeof(uint2)));
                 d->sorted_cap = want;
             }
+            if (d->sort_pending) {  // the previous step's sort (side stream) still owns d_sorted / d_sorted_tmp
+                CD_CUDA(ctx, cudaStreamWaitEvent(s, d->ev_sorted, 0));
+                d->sort_pending = false;
+            }
             if (total) CD_CUDA(ctx, cudaMemcpyAsync(d->d_sorted, d->d_gather, total * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
-            rc = sort_pairs_impl(ctx, &d->d_sorted, &d->d_sorted_tmp, total, id_bits_for(d->ntris_total), &ctx->d_sort_hist,
-                                 &ctx->d_sort_status, &ctx->sort_status_words, s);
+            cudaStream_t ss = s;
+            if (d->async_sort) {  // fork: the sort runs beside whatever this rank enqueues next on its main stream
+                CD_CUDA(ctx, cudaEventRecord(d->ev_fork, s));
+                CD_CUDA(ctx, cudaStreamWaitEvent(d->sort_stream, d->ev_fork, 0));
+                ss = d->sort_stream;
+            }
+            rc = sort_pairs_impl(ctx, &d->d_sorted, &d->d_sorted_tmp, total, id_bits_for(d->ntris_total), &d->d_sort_hist,
+                                 &d->d_sort_status, &d->sort_status_words, ss);
             if (rc != B200CD_OK) return rc;
+            if (d->async_sort) {
+                CD_CUDA(ctx, cudaEventRecord(d->ev_sorted, ss));
+                d->sort_pending = true;
+            }
             d->stats.total_pairs = total;
             if (d_pairs_out) *d_pairs_out = d->d_sorted;
         }

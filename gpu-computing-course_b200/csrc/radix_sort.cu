@@ -79,30 +79,35 @@ struct Digit<false> {  // bit field
     __device__ __forceinline__ uint32_t operator()(uint64_t k) const { return (uint32_t)((k >> shift) & mask); }
 };
 template <>
-struct Digit<true> {   // range partition
-    int nsplit;
-    uint64_t split[RS_MAX_SPLIT];
+struct Digit<true> {   // range partition: number of splitters <= key
+    // 16 ascending u64 in SHARED memory: the nsplit splitters, padded with ~0 (no key reaches it: keys use 63 bits).
+    // Branch-free binary search, 4 shared loads + compares per key (a linear scan over 15 splitters held in registers
+    // cost 45+ instructions per call, three calls per key: a third of the fused partition + exchange kernel's issue slots)
+    const uint64_t* sp;
     __device__ __forceinline__ uint32_t operator()(uint64_t k) const {
-        uint32_t d = 0;
-#pragma unroll
-        for (int j = 0; j < RS_MAX_SPLIT; ++j) d += (j < nsplit && split[j] <= k) ? 1u : 0u;
+        uint32_t d = (sp[7] <= k) ? 8u : 0u;
+        d += (sp[d + 3] <= k) ? 4u : 0u;
+        d += (sp[d + 1] <= k) ? 2u : 0u;
+        d += (sp[d] <= k) ? 1u : 0u;
         return d;
     }
 };
+__device__ __forceinline__ void load_splitters(uint64_t* s_split, const uint64_t* __restrict__ splitters, int nsplit) {
+    if (threadIdx.x < 16) s_split[threadIdx.x] = ((int)threadIdx.x < nsplit) ? __ldg(splitters + threadIdx.x) : ~0ull;
+    __syncthreads();
+}
 template <bool SPLIT>
-__device__ __forceinline__ Digit<SPLIT> make_digit(int shift, uint32_t mask, const uint64_t* __restrict__ splitters, int nsplit);
+__device__ __forceinline__ Digit<SPLIT> make_digit(int shift, uint32_t mask, const uint64_t* s_split);
 template <>
-__device__ __forceinline__ Digit<false> make_digit<false>(int shift, uint32_t mask, const uint64_t* __restrict__, int) {
+__device__ __forceinline__ Digit<false> make_digit<false>(int shift, uint32_t mask, const uint64_t*) {
     Digit<false> dg;
     dg.shift = shift; dg.mask = mask;
     return dg;
 }
 template <>
-__device__ __forceinline__ Digit<true> make_digit<true>(int, uint32_t, const uint64_t* __restrict__ splitters, int nsplit) {
+__device__ __forceinline__ Digit<true> make_digit<true>(int, uint32_t, const uint64_t* s_split) {
     Digit<true> dg;
-    dg.nsplit = nsplit;
-#pragma unroll
-    for (int j = 0; j < RS_MAX_SPLIT; ++j) dg.split[j] = (j < nsplit) ? __ldg(splitters + j) : ~0ull;
+    dg.sp = s_split;
     return dg;
 }
 
@@ -113,9 +118,10 @@ __global__ void __launch_bounds__(RH_THREADS) rs_histogram_split(const uint64_t*
                                                                  const uint64_t* __restrict__ splitters, int nsplit,
                                                                  uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[RS_MAX_SPLIT + 1];
+    __shared__ uint64_t s_split[16];
     if (threadIdx.x <= RS_MAX_SPLIT) sh[threadIdx.x] = 0;
-    __syncthreads();
-    const Digit<true> dg = make_digit<true>(0, 0, splitters, nsplit);
+    load_splitters(s_split, splitters, nsplit);
+    const Digit<true> dg = make_digit<true>(0, 0, s_split);
     for (uint32_t i = blockIdx.x * RH_THREADS + threadIdx.x; i < n; i += gridDim.x * RH_THREADS) {
         const uint32_t d = dg(__ldg(keys + i));
         const uint32_t peers = __match_any_sync(__activemask(), d);
@@ -219,7 +225,9 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
 #ifdef RS_PROFILE
     long long t_prev = clock64();
 #endif
-    const Digit<SPLIT> digit_of = make_digit<SPLIT>(shift, mask, splitters, nsplit);
+    __shared__ uint64_t s_split[16];
+    if (SPLIT) load_splitters(s_split, splitters, nsplit);
+    const Digit<SPLIT> digit_of = make_digit<SPLIT>(shift, mask, s_split);
   for (;;) {  // one tile per CTA, or (COND) a ticket loop over all tiles
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < RS_WARPS * (RS_RADIX + 1); i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
@@ -322,8 +330,11 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
         // mask in one instruction but issues only about once per 130 cycles per SM sub-partition on B200
         // (measured: 8.5 k of a tile's 30 k cycles went into 8 rounds of it).
         uint32_t peers = 0xffffffffu;
+        // (range partition: at most 16 buckets -> 4 digit bits + the "in range" bit 8 are enough)
+        constexpr int NBALLOT = SPLIT ? 5 : RS_BITS + 1;
 #pragma unroll
-        for (int b = 0; b < RS_BITS + 1; ++b) {
+        for (int bb = 0; bb < NBALLOT; ++bb) {
+            const int b = (SPLIT && bb == 4) ? RS_BITS : bb;
             const bool bit = (d >> b) & 1u;
             const uint32_t vote = __ballot_sync(0xffffffffu, bit);
             peers &= bit ? vote : ~vote;

@@ -544,7 +544,7 @@ class DistSelfCollision:
     ranks talk through CUDA-IPC peer memory and flag barriers. torch.distributed is used once, to move the export
     blobs between the processes, and for the caller's own barriers."""
 
-    def __init__(self, cd, ctx, mesh, params, group=None, slack=1.5, pair_capacity=0):
+    def __init__(self, cd, ctx, mesh, params, group=None, slack=1.5, pair_capacity=0, async_sort=False):
         self.cd, self.ctx, self.mesh, self.params, self.group = cd, ctx, mesh, params, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -557,13 +557,23 @@ class DistSelfCollision:
             self.dist.connect(blobs)
             dist.barrier(group=group)  # nobody steps before everybody has mapped everybody
         self.counts = [0] * self.world
+        # pipelined frames: rank 0 sorts frame k's list on a side stream while every rank starts on frame k + 1
+        self.async_sort = bool(async_sort)
+        if self.async_sort:
+            self.dist.set_async_sort(True)
 
-    def step(self):
-        """one distributed build + query; rank 0 gets the sorted packed pair list (device tensor), the others None"""
+    def step(self, wait=False):
+        """one distributed build + query; rank 0 gets the sorted packed pair list (device tensor), the others None.
+        With async_sort the tensor's contents are valid after wait_sorted() (or pass wait=True)"""
         ptr, count = self.dist.step(self.mesh, self.params)
+        if wait:
+            self.dist.wait_sorted()
         if self.rank != 0:
             return None
         return device_pairs_as_tensor(ptr, count, self.device)
+
+    def wait_sorted(self):
+        self.dist.wait_sorted()
 
     @property
     def stats(self):
@@ -688,6 +698,9 @@ class PeerMeshFrames:
         frame in pinned host memory of this rank. Returns the bytes this rank pushes over PCIe."""
         m = self.meshes[k]
         v0, nv, t0, nt = self.slice_of(m)
+        if not idx_host_ptr:  # vertex positions only (the topology of a deforming mesh does not change)
+            m.update_slice_async_from_ptr(xyz_host_ptr + 12 * v0, v0, nv, None, 0, 0)
+            return 12 * nv
         m.update_slice_async_from_ptr(xyz_host_ptr + 12 * v0, v0, nv, idx_host_ptr + 12 * t0, t0, nt)
         return 12 * nv + 12 * nt
 

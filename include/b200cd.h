@@ -396,6 +396,12 @@ int b200cd_dist_export(b200cd_dist* dist, uint8_t* blob_out /* B200CD_DIST_BLOB_
 int b200cd_dist_connect(b200cd_dist* dist, const uint8_t* blobs /* world x B200CD_DIST_BLOB_BYTES, rank order */);
 int b200cd_dist_step(b200cd_dist* dist, const b200cd_mesh* mesh, const b200cd_params* params, const void** d_pairs_out,
                      uint64_t* count_out);
+/* Pipelined frames: with on != 0 rank 0 sorts the gathered list on a side stream and goes straight on to the next frame
+ * (the other ranks would otherwise wait for that sort at the next step's first barrier). The list the last
+ * b200cd_dist_step returned is then valid after b200cd_dist_wait_sorted, which makes the context's stream wait for the
+ * sort without blocking the host; the next b200cd_dist_step does it implicitly before it reuses the buffers. */
+int b200cd_dist_set_async_sort(b200cd_dist* dist, int on);
+int b200cd_dist_wait_sorted(b200cd_dist* dist);
 /* a barrier across the ranks on the context's stream (flag barrier over peer memory) */
 int b200cd_dist_barrier(b200cd_dist* dist);
 int b200cd_dist_get_stats(b200cd_dist* dist, b200cd_dist_stats* out);

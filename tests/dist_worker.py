@@ -73,7 +73,10 @@ def main():
         if k == 1:                                      # a second frame: same topology, moved vertices
             xyz = (xyz + np.float32(1e-3) * np.sin(37.0 * xyz[:, ::-1])).astype(np.float32)
             mesh.update(xyz=xyz)
+        if k == 1:
+            dist.set_async_sort(True)                   # second frame: rank 0's final sort on a side stream
         ptr, count = dist.step(mesh, params)
+        dist.wait_sorted()                              # (no-op unless the sort went to the side stream)
         ctx.synchronize()                               # the list is valid in stream order on the CONTEXT's stream
         if rank == 0:
             pairs = mgpu.unpack_pairs(mgpu.device_pairs_as_tensor(ptr, count, torch.device("cuda", dev)))
