@@ -584,6 +584,10 @@ def run_gpu_arm(args, workload):
     if partitioned and not cxx_step:
         prunner.step(profile=True)  # one extra, untimed step (all ranks) with a synchronise after every phase
     pstats = dict(prunner.stats) if partitioned else {}
+    all_pstats = None
+    if partitioned and cxx_step:  # every rank's view of the last step (range size, ghosts received, phase times)
+        all_pstats = [None] * world
+        dist.all_gather_object(all_pstats, {k: (round(v, 4) if isinstance(v, float) else v) for k, v in pstats.items()})
 
     if rank == 0:
         K = args.steps
@@ -689,6 +693,9 @@ def run_gpu_arm(args, workload):
             line["partition"] = dict(pstats, rank=0, build_ms=ctx.stats()["ms_build"])
             if cxx_step:  # device times of rank 0's phases of the LAST timed step (CUDA events, barriers included)
                 line["partition"]["phase_ms"] = {k[3:]: round(v, 4) for k, v in pstats.items() if k.startswith("ms_")}
+                line["partition"]["ranks"] = [{"rank": r["rank"], "local_triangles": r["local_triangles"], "ghosts_received": r["ghosts"],
+                                               "local_pairs": r["local_pairs"], "ms_build": r["ms_build"],
+                                               "ms_local_query": r["ms_local_query"], "ms_step": r["ms_step"]} for r in all_pstats]
         if scaling_base is not None:
             line["scaling_base"] = scaling_base
             line["speedup_same_workload"] = round(scaling_base["ms_per_step"] / ms_step, 3)

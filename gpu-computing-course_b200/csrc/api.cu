@@ -193,7 +193,8 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
         if (ghost_out) A(dev_alloc(ctx, &b->d_ghost_out, (uint64_t)max_peers * ghost_cap));  // staging of the NCCL send/recv exchange only
         A(dev_alloc(ctx, &b->d_cut_scratch, (uint64_t)ghost_max_k() * 6 + 1));
         A(dev_alloc(ctx, &b->d_block_boxes, ((uint64_t)n / 256 + 1) * 8));
-        A(dev_alloc(ctx, &b->d_ghost_list, (uint64_t)n / 256 + 3));
+        A(dev_alloc(ctx, &b->d_ghost_list, ghost_list_words(n, max_peers)));
+        b->ghost_list_cap = ghost_list_items(n, max_peers);
         A(dev_alloc(ctx, &b->d_peers, 1));
         A(dev_alloc(ctx, &b->d_ghost_in_count, 2));
     }
@@ -305,18 +306,34 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
                 // (bit 1 of h_fix[0]: a key reached above the digit window - the fallback sorted that build; the window
                 // only ever moves up, so a mesh whose keys hover around a power of two does not fall back every frame)
                 if ((int)b->h_fix[3] > b->sort_top) b->sort_top = (int)b->h_fix[3];
+                const bool slow_fix = pass_ms > 0.f && fix_ms > 1.3f * pass_ms;
+                b->sort_slow_streak = slow_fix ? b->sort_slow_streak + 1 : 0;
                 if (overflow || longest > 24) {           // prefix too short for this mesh: sort more digits, for good
                     b->sort_high = overflow ? 8 : std::min(8, b->sort_high + 1);
                     b->sort_locked = true;
-                } else if (fix_ms > 1.3f * pass_ms && pass_ms > 0.f && b->sort_high < 8) {
+                    b->sort_trial = false;
+                } else if (b->sort_trial && pass_ms > 0.f) {
+                    // verdict on the extra digit tried last time: keep it only if fix-up + one more pass beat the old fix-up
+                    b->sort_trial = false;
+                    if (fix_ms + pass_ms >= b->sort_fix_before) {
+                        --b->sort_high;                   // no gain (e.g. runs of truly equal keys, which no digit separates)
+                        b->sort_time_frozen = true;
+                    }
+                } else if (!b->sort_time_frozen && b->sort_high < 8 &&
+                           (b->sort_slow_streak >= 3 || (pass_ms > 0.f && fix_ms > 3.f * pass_ms))) {
                     // The fix-up orders every run with ONE thread (serial insertion, divergent): cheap while runs are rare and
                     // short, slow once most items sit in runs of 10+ (measured on the 2^25-triangle half of the two sheets:
                     // 1.31 ms behind 4 passes against 0.09 ms behind 5 passes of 0.29 ms each). Its cost depends on the run
                     // length distribution, so it is MEASURED (events around the previous build's fix-up and last pass): when
                     // it exceeds one more radix pass plus the fix-up's floor (two reads of the keys, ~0.3 pass) the next build
-                    // sorts one digit more. For good, so that a mesh near the threshold does not flip every frame.
+                    // sorts one digit more - after three slow builds in a row, or at once when it cost more than three passes
+                    // (one mildly slow measurement can be another stream's copy or a time slice) - and the build after that
+                    // checks that it paid off.
                     ++b->sort_high;
                     b->sort_locked = true;
+                    b->sort_trial = true;
+                    b->sort_fix_before = fix_ms;
+                    b->sort_slow_streak = 0;
                 } else if (!b->sort_locked && b->sort_high > 4 && longest <= 3 && (uint64_t)in_runs * 1024 < n) {
                     --b->sort_high;                       // one digit less multiplies the occupancy of a cell by up to 256
                 }
@@ -1239,7 +1256,7 @@ API int b200cd_send_ghosts_to_peers_device(b200cd_ctx* ctx, b200cd_bvh* bvh, con
     DeviceGuard g(ctx->device);
     if (!bvh->d_cut_scratch) return set_error(ctx, B200CD_E_INVALID, "BVH was not allocated for a partitioned build");
     launch_ghosts_to_peers(bvh->d_leaves, bvh->n, static_cast<const float*>(d_peer_boxes), npeers, K, peer_mask, bvh->d_peers,
-                           reinterpret_cast<float*>(bvh->d_cut_scratch), bvh->d_block_boxes, ctx->stream, bvh->d_ghost_list, ctx->sm_count);
+                           reinterpret_cast<float*>(bvh->d_cut_scratch), bvh->d_block_boxes, ctx->stream, bvh->d_ghost_list, bvh->ghost_list_cap, ctx->sm_count);
     CD_CUDA(ctx, cudaGetLastError());
     return B200CD_OK;
 }

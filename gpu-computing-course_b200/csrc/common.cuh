@@ -110,7 +110,8 @@ struct b200cd_bvh {
     uint32_t* d_cut_scratch = nullptr;        // coarse-box reduction scratch (256*6+1 words)
     b200cd::PeerTable* d_peers = nullptr;     // peer-memory destinations (b200cd_bvh_set_peers)
     unsigned long long* d_ghost_in_count = nullptr;  // ghosts appended to MY ghost records by the peers (and by me)
-    uint2* d_ghost_list = nullptr;            // [cap / 256 + 2] (block, peer mask) items of the ghost selection's pre-filter
+    uint32_t* d_ghost_list = nullptr;         // ghost_list_words(cap, peers): (block, peer, box mask) items of the ghost selection's pre-filter
+    uint32_t ghost_list_cap = 0;
     uint64_t ghost_out_cap = 0;
     uint32_t max_peers = 0;  // outgoing ghost lists allocated (b200cd_bvh_alloc_partial)
     uint32_t nranks = 0;     // ranks given to b200cd_bvh_set_peers (0: not set)
@@ -133,6 +134,10 @@ struct b200cd_bvh {
     int sort_high = 5;                 // digits sorted by radix passes (8 = plain full sort)
     int sort_top = 0;                  // significant key bits seen by the previous build (0 = unknown: all 63)
     bool sort_locked = false;          // a longer prefix was needed once: never try a shorter one again
+    int sort_slow_streak = 0;          // consecutive builds whose measured fix-up cost more than 1.3 radix passes
+    bool sort_trial = false;           // the last build tried one digit more because of that: its timing decides
+    bool sort_time_frozen = false;     // the trial did not pay off: stop escalating on time
+    float sort_fix_before = 0.f;       // the fix-up time that triggered the trial
     cudaEvent_t ev_sort[4] = {};       // around the last radix pass and around the fix-up of the previous hybrid sort (timed)
     // hierarchy
     uint32_t* d_flags = nullptr;       // n-1 arrival counters of the splits merged through global memory
@@ -295,8 +300,10 @@ void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxe
 // same selection, but the records are appended straight into the peers' ghost buffers (remote atomics + stores)
 void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                             uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, const float* d_block_boxes,
-                            cudaStream_t s, uint2* d_list = nullptr /* scratch: n / 256 + 2 entries; enables the block pre-filter */,
-                            int sms = 148);
+                            cudaStream_t s, uint32_t* d_list = nullptr /* scratch of ghost_list_words(): enables the block pre-filter */,
+                            uint32_t list_cap = 0 /* (block, peer) items the scratch holds */, int sms = 148);
+inline uint32_t ghost_list_items(uint32_t n, uint32_t peers) { return (n / 256 + 1) * (peers ? peers : 1); }  // worst case: all pairs
+inline uint64_t ghost_list_words(uint32_t n, uint32_t peers) { return 4 + 10ull * ghost_list_items(n, peers); }
 // unique.cu: sorted set of the triangle IDs in a pair list (reference main.cu:33-45). d_bits: ceil(id_space / 32) words,
 // d_sums: ceil(words / 1024) + 1 words; *d_sums_total (last word of d_sums) receives the count; d_out: ids, ascending
 void launch_unique_mark(const uint2* d_pairs, uint64_t count, uint32_t id_space, uint32_t* d_bits, cudaStream_t s);

@@ -171,6 +171,7 @@ struct b200cd_dist {
     // rank 0's final sort can run on a side stream (b200cd_dist_set_async_sort), off the other ranks' critical path:
     // they would otherwise wait for it at the first barrier of the next step
     bool async_sort = false, sort_pending = false;
+    uint64_t sort_deferred = 0;      // pairs copied into d_sorted whose sort has not been ENQUEUED yet (async mode)
     cudaStream_t sort_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_sorted = nullptr;
     uint32_t* d_sort_hist = nullptr;      // radix scratch of that sort (the context's own may be in use on the main stream)
@@ -265,6 +266,27 @@ dist_gather_kernel(const uint2* __restrict__ pairs, const unsigned long long* __
 // ---------------------------------------------------------------- host helpers
 
 int set_dist_error(b200cd_dist* d, int code, const std::string& msg) { return set_error(d ? d->ctx : nullptr, code, msg); }
+
+// Async mode: the host work of launching the sort (10 launches) is put off until the NEXT step has enqueued its first
+// phase (or until somebody asks for the list), so that rank 0 reaches the next step's first barrier with the others.
+int launch_deferred_sort(b200cd_dist* d) {
+    if (!d->sort_deferred) return B200CD_OK;
+    b200cd_ctx* ctx = d->ctx;
+    const uint64_t total = d->sort_deferred;
+    d->sort_deferred = 0;
+    CD_CUDA(ctx, cudaStreamWaitEvent(d->sort_stream, d->ev_fork, 0));
+    uint2* const promised = d->d_sorted;  // the address b200cd_dist_step has already handed to the caller
+    int rc = sort_pairs_impl(ctx, &d->d_sorted, &d->d_sorted_tmp, total, id_bits_for(d->ntris_total), &d->d_sort_hist,
+                             &d->d_sort_status, &d->sort_status_words, d->sort_stream);
+    if (rc != B200CD_OK) return rc;
+    if (d->d_sorted != promised) {  // (a pair sort runs 2 x ceil(id_bits / 8) passes - an even number - and lands where it started)
+        CD_CUDA(ctx, cudaMemcpyAsync(promised, d->d_sorted, total * sizeof(uint2), cudaMemcpyDeviceToDevice, d->sort_stream));
+        std::swap(d->d_sorted, d->d_sorted_tmp);
+    }
+    CD_CUDA(ctx, cudaEventRecord(d->ev_sorted, d->sort_stream));
+    d->sort_pending = true;
+    return B200CD_OK;
+}
 
 void barrier(b200cd_dist* d, cudaStream_t s) {
     if (d->world < 2) return;
@@ -455,6 +477,7 @@ API int b200cd_dist_connect(b200cd_dist* d, const uint8_t* blobs) {
 API int b200cd_dist_destroy(b200cd_dist* d) {
     if (!d) return B200CD_OK;
     DeviceGuard g(d->ctx->device);
+    launch_deferred_sort(d);
     cudaStreamSynchronize(d->ctx->stream);
     close_mappings(d);
     if (d->nccl) {
@@ -502,6 +525,10 @@ API int b200cd_dist_barrier(b200cd_dist* d) {
 API int b200cd_dist_set_async_sort(b200cd_dist* d, int on) {
     if (!d) return B200CD_E_INVALID;
     DeviceGuard g(d->ctx->device);
+    if (!on) {
+        int rc = launch_deferred_sort(d);
+        if (rc != B200CD_OK) return rc;
+    }
     if (!on && d->sort_pending) {
         CD_CUDA(d->ctx, cudaStreamWaitEvent(d->ctx->stream, d->ev_sorted, 0));
         d->sort_pending = false;
@@ -512,8 +539,10 @@ API int b200cd_dist_set_async_sort(b200cd_dist* d, int on) {
 
 API int b200cd_dist_wait_sorted(b200cd_dist* d) {
     if (!d) return B200CD_E_INVALID;
-    if (!d->sort_pending) return B200CD_OK;
     DeviceGuard g(d->ctx->device);
+    int rc = launch_deferred_sort(d);
+    if (rc != B200CD_OK) return rc;
+    if (!d->sort_pending) return B200CD_OK;
     CD_CUDA(d->ctx, cudaStreamWaitEvent(d->ctx->stream, d->ev_sorted, 0));
     d->sort_pending = false;
     return B200CD_OK;
@@ -566,6 +595,8 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
         push(d, d->d_lhist, offsetof(CommBlock, hist) + sizeof(uint32_t) * 65536ull * R, sizeof(uint32_t) * 65536ull, s);
         barrier(d, s);
         CD_CUDA(ctx, cudaEventRecord(d->ev[DE_HIST], s));
+        rc = launch_deferred_sort(d);  // (rank 0, async mode) the previous frame's sort, now that this frame is under way
+        if (rc != B200CD_OK) return rc;
         // ---- the plan: splitters, count matrix, receive offsets, range sizes (identical on every rank)
         launch_dist_plan(&d->comm->hist[0][0], (int)W, (int)R, d->shift, d->d_ghist, d->d_part, d->d_plan, s);
         CD_CUDA(ctx, cudaMemcpyAsync(H->totals, d->d_plan->totals, sizeof(uint32_t) * DIST_MAX, cudaMemcpyDeviceToHost, s));
@@ -594,7 +625,7 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
         // ---- ghosts for the higher ranks leave while the local query runs
         if (mask_higher && nlocal)
             launch_ghosts_to_peers(b->d_leaves, nlocal, &d->comm->boxes[0][0], W, DIST_K, mask_higher, b->d_peers,
-                                   reinterpret_cast<float*>(b->d_cut_scratch), b->d_block_boxes, s, b->d_ghost_list, ctx->sm_count);
+                                   reinterpret_cast<float*>(b->d_cut_scratch), b->d_block_boxes, s, b->d_ghost_list, b->ghost_list_cap, ctx->sm_count);
         CD_CUDA(ctx, cudaEventRecord(d->ev[DE_GHOST_SEND], s));
         CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
         if (nlocal >= 2) {
@@ -686,18 +717,13 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
                 d->sort_pending = false;
             }
             if (total) CD_CUDA(ctx, cudaMemcpyAsync(d->d_sorted, d->d_gather, total * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
-            cudaStream_t ss = s;
-            if (d->async_sort) {  // fork: the sort runs beside whatever this rank enqueues next on its main stream
+            if (d->async_sort) {  // fork: the sort will run beside whatever this rank enqueues next on its main stream
                 CD_CUDA(ctx, cudaEventRecord(d->ev_fork, s));
-                CD_CUDA(ctx, cudaStreamWaitEvent(d->sort_stream, d->ev_fork, 0));
-                ss = d->sort_stream;
-            }
-            rc = sort_pairs_impl(ctx, &d->d_sorted, &d->d_sorted_tmp, total, id_bits_for(d->ntris_total), &d->d_sort_hist,
-                                 &d->d_sort_status, &d->sort_status_words, ss);
-            if (rc != B200CD_OK) return rc;
-            if (d->async_sort) {
-                CD_CUDA(ctx, cudaEventRecord(d->ev_sorted, ss));
-                d->sort_pending = true;
+                d->sort_deferred = total;  // enqueued by the next step behind its first phase, or by b200cd_dist_wait_sorted
+            } else {
+                rc = sort_pairs_impl(ctx, &d->d_sorted, &d->d_sorted_tmp, total, id_bits_for(d->ntris_total), &d->d_sort_hist,
+                                     &d->d_sort_status, &d->sort_status_words, s);
+                if (rc != B200CD_OK) return rc;
             }
             d->stats.total_pairs = total;
             if (d_pairs_out) *d_pairs_out = d->d_sorted;

@@ -159,49 +159,122 @@ constexpr int GH_GROUP = 16;  // coarse boxes per super box
 // like the traversal) against that peer's coarse boxes - first the peer's overall box, then super
 // boxes of 16 consecutive coarse boxes, then the coarse boxes of the super boxes it overlaps - and,
 // on the first hit, appends the leaf's 64-byte record to the peer's ghost list (warp-aggregated atomic).
-// Pre-pass of the listed variant below: ONE THREAD per 256-leaf block tests the block's union box (left by the tree
-// build) against the overall box of every selected peer and appends (block, mask of the peers it overlaps) to a list.
-// On a Morton-range partition all blocks but those next to a range boundary drop out here - 33 k blocks are looked at
-// by 130 CTAs instead of each starting a CTA of its own to find out that it has nothing to do (0.19 ms per step on
-// rank 0 of 8, two sheets).
+// ---- ghost selection for the C++ multi-GPU step, in two kernels over a list (the tree build left the union box of
+// every 256-leaf block):
+//   ghost_block_filter_kernel   ONE WARP per block: the block's box against the overall box of every selected peer and
+//                               then, 32 at a time, against the peer's K <= 256 coarse boxes; a (block, peer) pair that
+//                               overlaps any of them becomes a list item carrying the 256-bit mask of those boxes.
+//                               On a Morton-range partition all blocks but those next to a range boundary drop out here.
+//   ghost_listed_kernel         one CTA per item: every leaf of the block against the (few) coarse boxes of the mask -
+//                               uniform loads, no shared memory, no barriers - and the hits are appended to the peer's
+//                               ghost records (one remote atomic per warp + 256-bit stores over NVLink).
+// Before: every block started a CTA, loaded 6 KB of peer boxes per overlapping peer into shared memory and mostly found
+// nothing (0.2 - 0.3 ms per step on some ranks of 8 on the two sheets, whose neighbouring ranges' overall boxes overlap
+// almost entirely); a one-thread-per-block pre-filter walking 256 boxes serially still cost 0.06 - 0.13 ms.
+struct GhostItem {
+    uint32_t block, peer;
+    uint32_t mask[8];  // bit (k & 31) of word (k >> 5): coarse box k of the peer overlaps the block's box
+};
+
 __global__ void __launch_bounds__(256)
 ghost_block_filter_kernel(const float* __restrict__ block_boxes, uint32_t nblocks, const float* __restrict__ peer_overall,
-                          uint32_t npeers, uint32_t peer_mask, uint2* __restrict__ list, uint32_t* __restrict__ list_count) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nblocks) return;
+                          const float* __restrict__ peer_boxes, uint32_t K, uint32_t npeers, uint32_t peer_mask,
+                          GhostItem* __restrict__ items, uint32_t* __restrict__ count, uint32_t cap) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= nblocks) return;  // warp-uniform
     const float4 u0 = __ldg(reinterpret_cast<const float4*>(block_boxes + 8 * (size_t)b));
     const float4 u1 = __ldg(reinterpret_cast<const float4*>(block_boxes + 8 * (size_t)b) + 1);
-    uint32_t mask = 0;
     for (uint32_t p = 0; p < npeers; ++p) {
         if (!((peer_mask >> p) & 1u)) continue;
         const float* ob = peer_overall + 6 * (size_t)p;
-        if (u0.x < __ldg(ob + 3) && __ldg(ob) < u0.w && u0.y < __ldg(ob + 4) && __ldg(ob + 1) < u1.x && u0.z < __ldg(ob + 5) &&
-            __ldg(ob + 2) < u1.y)
-            mask |= 1u << p;
+        if (!(u0.x < __ldg(ob + 3) && __ldg(ob) < u0.w && u0.y < __ldg(ob + 4) && __ldg(ob + 1) < u1.x && u0.z < __ldg(ob + 5) &&
+              __ldg(ob + 2) < u1.y))
+            continue;
+        uint32_t m[8], any = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            const uint32_t k = 32 * j + lane;
+            bool hit = false;
+            if (k < K) {
+                const float* c = peer_boxes + ((size_t)p * K + k) * 6;
+                hit = u0.x < __ldg(c + 3) && __ldg(c) < u0.w && u0.y < __ldg(c + 4) && __ldg(c + 1) < u1.x && u0.z < __ldg(c + 5) &&
+                      __ldg(c + 2) < u1.y;
+            }
+            m[j] = __ballot_sync(0xffffffffu, hit);
+            any |= m[j];
+        }
+        if (any && lane == 0) {
+            const uint32_t slot = atomicAdd(count, 1u);
+            if (slot < cap) {  // (cap = blocks x peers: cannot overflow)
+                GhostItem it;
+                it.block = b;
+                it.peer = p;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) it.mask[j] = m[j];
+                items[slot] = it;
+            }
+        }
     }
-    if (mask) list[atomicAdd(list_count, 1u)] = make_uint2(b, mask);
 }
 
-// LISTED: the grid strides over the (block, peer mask) items of ghost_block_filter_kernel instead of over all blocks
-template <bool REMOTE, bool LISTED = false>
+__global__ void __launch_bounds__(256)
+ghost_listed_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __restrict__ peer_boxes, uint32_t K,
+                    const GhostItem* __restrict__ items, const uint32_t* __restrict__ count, uint32_t cap,
+                    const PeerTable* __restrict__ peers) {
+    const uint32_t nitems = min(*count, cap);
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const GhostItem it = items[item];  // the same words for the whole CTA
+        const uint32_t j = it.block * blockDim.x + threadIdx.x;
+        const bool valid = j < n;
+        float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        float4 r0, r1, r2, r3;
+        if (valid) {
+            ld256_nc(leaves + j, r0, r1);
+            ld256_nc(reinterpret_cast<const float4*>(leaves + j) + 2, r2, r3);
+            lo[0] = fminf(fminf(r0.x, r0.w), r1.z); hi[0] = fmaxf(fmaxf(r0.x, r0.w), r1.z);
+            lo[1] = fminf(fminf(r0.y, r1.x), r1.w); hi[1] = fmaxf(fmaxf(r0.y, r1.x), r1.w);
+            lo[2] = fminf(fminf(r0.z, r1.y), r2.x); hi[2] = fmaxf(fmaxf(r0.z, r1.y), r2.x);
+        }
+        bool hit = false;
+#pragma unroll
+        for (uint32_t w = 0; w < 8; ++w) {
+            uint32_t mm = it.mask[w];
+            while (mm) {  // CTA-uniform
+                const uint32_t k = 32 * w + (uint32_t)(__ffs(mm) - 1);
+                mm &= mm - 1;
+                const float* c = peer_boxes + ((size_t)it.peer * K + k) * 6;
+                hit = hit || (valid && lo[0] < __ldg(c + 3) && __ldg(c) < hi[0] && lo[1] < __ldg(c + 4) && __ldg(c + 1) < hi[1] &&
+                              lo[2] < __ldg(c + 5) && __ldg(c + 2) < hi[2]);
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(peers->ghost_count[it.peer], (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+            if (hit && base < peers->ghost_cap) {
+                LeafRec* dst = peers->ghosts[it.peer] + base;
+                st256(dst, r0, r1);
+                st256(reinterpret_cast<float4*>(dst) + 2, r2, r3);
+            }
+        }
+    }
+}
+
+// Each thread owns one local leaf; for every selected peer it tests the leaf's box (strict overlap,
+// like the traversal) against that peer's coarse boxes - first the peer's overall box, then super
+// boxes of 16 consecutive coarse boxes, then the coarse boxes of the super boxes it overlaps - and,
+// on the first hit, appends the leaf's 64-byte record to the peer's ghost list (warp-aggregated atomic).
+template <bool REMOTE>
 __global__ void __launch_bounds__(256)
 ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __restrict__ peer_boxes, uint32_t npeers,
              uint32_t K, uint32_t peer_mask, LeafRec* __restrict__ ghosts, uint64_t cap_per_peer,
              unsigned long long* __restrict__ counts, const PeerTable* __restrict__ peers,
-             const float* __restrict__ peer_overall, const float* __restrict__ block_boxes,
-             const uint2* __restrict__ list = nullptr, const uint32_t* __restrict__ list_count = nullptr) {
+             const float* __restrict__ peer_overall, const float* __restrict__ block_boxes) {
     __shared__ float s_red[8][6];
     __shared__ float s_union[6];
-  const uint32_t nitems = LISTED ? *list_count : gridDim.x;
-  for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const uint32_t blk = LISTED ? list[item].x : item;
-    if (LISTED) {
-        peer_mask = list[item].y;
-        __syncthreads();  // the shared arrays below are reused from the previous item
-    }
-    // The tree build left the union box of every 256-leaf block (build_kernel, block_boxes): a block that
-    // overlaps no selected peer's overall box retires here, without reading a single leaf record - on a
-    // Morton-range partition that is every block except those next to a range boundary.
+    const uint32_t blk = blockIdx.x;
     if (block_boxes) {
         if (threadIdx.x < 6) s_union[threadIdx.x] = __ldg(block_boxes + 8 * (size_t)blk + threadIdx.x);
         __syncthreads();
@@ -212,7 +285,7 @@ ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __rest
             any = any || (s_union[0] < __ldg(ob + 3) && __ldg(ob) < s_union[3] && s_union[1] < __ldg(ob + 4) &&
                           __ldg(ob + 1) < s_union[4] && s_union[2] < __ldg(ob + 5) && __ldg(ob + 2) < s_union[5]);
         }
-        if (!any) continue;  // block-uniform
+        if (!any) return;  // block-uniform
     }
     __shared__ float s_box[GH_MAXK][6];
     __shared__ float s_sup[GH_MAXK / GH_GROUP + 1][6];  // super boxes; the last used slot + 1 .. : [nsup] = overall box
@@ -306,7 +379,6 @@ ghost_kernel(const LeafRec* __restrict__ leaves, uint32_t n, const float* __rest
             }
         }
     }
-  }
 }
 
 // Range plan of the partitioned build in ONE launch (one block): from the all-reduced 65536-bin histogram of the
@@ -565,17 +637,19 @@ void launch_ghosts(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxe
 
 void launch_ghosts_to_peers(const LeafRec* d_leaves, uint32_t n, const float* d_peer_boxes, uint32_t npeers, uint32_t K,
                             uint32_t peer_mask, const PeerTable* d_peers, float* d_overall, const float* d_block_boxes,
-                            cudaStream_t s, uint2* d_list, int sms) {
+                            cudaStream_t s, uint32_t* d_list, uint32_t list_cap, int sms) {
     if (!n || !npeers || !peer_mask) return;
     peer_overall_kernel<<<npeers, 32, 0, s>>>(d_peer_boxes, K, d_overall);
-    if (d_block_boxes && d_list) {  // only the blocks next to a range boundary start any work
+    if (d_block_boxes && d_list && K <= 256) {  // only the blocks next to a range boundary start any work
         const uint32_t nblocks = (n + 255) / 256;
-        uint32_t* d_count = reinterpret_cast<uint32_t*>(d_list);  // word 0 of the scratch: the list's length; items from [1]
-        uint2* items = d_list + 1;
+        uint32_t* d_count = d_list;  // word 0 of the scratch: the list's length; items behind it (16-byte aligned)
+        GhostItem* items = reinterpret_cast<GhostItem*>(d_list + 4);
         cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s);
-        ghost_block_filter_kernel<<<(nblocks + 255) / 256, 256, 0, s>>>(d_block_boxes, nblocks, d_overall, npeers, peer_mask, items, d_count);
-        ghost_kernel<true, true><<<std::min<uint32_t>(nblocks, (uint32_t)std::max(sms, 1) * 8u), 256, 0, s>>>(
-            d_leaves, n, d_peer_boxes, npeers, K, peer_mask, nullptr, 0, nullptr, d_peers, d_overall, d_block_boxes, items, d_count);
+        ghost_block_filter_kernel<<<(nblocks + 7) / 8, 256, 0, s>>>(d_block_boxes, nblocks, d_overall, d_peer_boxes, K, npeers, peer_mask,
+                                                                     items, d_count, list_cap);
+        trace_mark("ghost block pre-filter", s);
+        ghost_listed_kernel<<<std::min<uint32_t>(nblocks, (uint32_t)std::max(sms, 1) * 8u), 256, 0, s>>>(d_leaves, n, d_peer_boxes, K, items,
+                                                                                                     d_count, list_cap, d_peers);
         count_launch(3);
         trace_mark("ghost_kernel (block filter + select + send)", s);
         return;
