@@ -19,9 +19,10 @@
 //     so this halves the traversal without changing the set; the narrow phase is
 //     still called as (lower ID, higher ID) because the SAT is not symmetric in
 //     floating point.
-//   - queries do not start at the root: one thread per block of 256 consecutive sorted leaves
-//     walks the block's ancestors once (entry_kernel) and every query of the block starts at
-//     the handful of subtrees that tile "leaves after me" and overlap the block's union box.
+//   - queries do not start at the root: one thread per group of 128 consecutive sorted leaves
+//     (B200CD_QUERY_GROUP; one warp of the persistent-lane traversal works through one group)
+//     walks the group's ancestors once (entry_kernel) and every query of the group starts at
+//     the handful of subtrees that tile "leaves after me" and overlap the group's union box.
 //   - traversal only emits CANDIDATES (AABB-overlapping leaf pairs) into a compact
 //     list: per-warp staging in shared memory filled with ballots (no atomics),
 //     flushed with one global atomicAdd per >=32 candidates. The divergent fp64
@@ -174,8 +175,8 @@ entry_kernel(const NodePair* __restrict__ pairs, const float* __restrict__ root_
 // ---------------------------------------------------------------- K5b (variant 2): persistent lanes
 // Persistent lanes (after Aila & Laine 2009). With one query per thread the warp loops as long as
 // its busiest lane (measured lane utilisation on the 16 M soup: 0.40). Here a block owns 1024
-// consecutive queries (four 256-leaf groups, each with its entry list) and every warp works
-// through its own 128 of them: whenever at least BR_REFILL lanes have run out of work, the idle
+// consecutive queries (eight 128-leaf groups, each with its entry list) and every warp works
+// through its own group: whenever at least BR_REFILL lanes have run out of work, the idle
 // lanes take the warp's next queries (their records were prefetched at the previous refill), scan
 // the group's entry list and rejoin the traversal loop. Lanes of a warp still walk neighbouring
 // queries, so node fetches stay coherent. Shared memory is kept small on purpose: the unified

@@ -9,13 +9,19 @@
 //   2. rs_scan       exclusive scan of each pass's 256 bins -> global digit bases;
 //   3. rs_pass x P   one kernel per digit. Each CTA (512 threads x 8 items) takes a tile of 4096 items
 //                    (ticket from an atomic counter, so look-back never waits on a
-//                    tile that has not started), ranks its keys with a warp-level
-//                    multi-split (__match_any_sync + per-warp shared histograms),
-//                    publishes its per-digit counts and resolves its global offsets
-//                    by DECOUPLED LOOK-BACK over the previous tiles' status words,
-//                    stages the tile in shared memory in digit order and writes it
-//                    out in coalesced runs. Keys and values are read once and
-//                    written once per pass.
+//                    tile that has not started), builds the tile's digit histogram and
+//                    publishes it, resolves its global offsets by DECOUPLED LOOK-BACK over
+//                    the previous tiles' status words BEFORE the ranking (so the chain of
+//                    inclusive prefixes moves at histogram speed), ranks its keys with a
+//                    warp-level multi-split (one ballot per digit bit + per-warp shared
+//                    histograms; __match_any_sync issues far too slowly on B200), stages
+//                    the tile in shared memory in digit order and writes it out in
+//                    coalesced runs. Keys and values are read once and written once per pass.
+//   4. rs_fixup      hybrid sort: only the top digits go through passes, the low bits are
+//                    ordered per run of equal high bits (see below); conditional fallback passes.
+//   rs_pass<.., SPLIT> is also the multi-GPU range partition: digit = number of splitters <= key
+//                    (binary search in shared memory), destination = the owning rank's buffers
+//                    through peer memory.
 //
 // HBM traffic per pass: 12 B read + 12 B written per item (8+8 keys-only); the
 // histogram adds one 8 B read. Look-back words: 1 KiB per tile per pass.
@@ -493,6 +499,20 @@ constexpr size_t rs_smem_bytes(bool has_values) {
 
 }  // namespace
 
+// > 48 KiB of dynamic shared memory must be opted into, once per function and device (NOT once per launch: the
+// host calls sit in latency-bound steps)
+static void opt_in_shared_memory() {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && attr_set[dev]) return;
+    cudaFuncSetAttribute(rs_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    cudaFuncSetAttribute(rs_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false));
+    cudaFuncSetAttribute(rs_pass<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    cudaFuncSetAttribute(rs_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+}
+
 int radix_digit_bits() { return RS_BITS; }
 
 uint32_t radix_hist_words(int npass) { return (uint32_t)(npass * RS_RADIX + RS_MAX_PASS); }  // + tickets
@@ -532,15 +552,7 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
         }
     }
     const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
-    static bool attr_set[64] = {};  // > 48 KiB of dynamic shared memory must be opted into, once per function and device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaFuncSetAttribute(rs_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
-        cudaFuncSetAttribute(rs_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false));
-        cudaFuncSetAttribute(rs_pass<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
+    opt_in_shared_memory();
     const uint32_t hblocks = min((n / 2 + RH_THREADS - 1) / RH_THREADS + 1, (uint32_t)sms * 8u);
     uint32_t* d_ticket = d_hist + npass * RS_RADIX;
     cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);
@@ -604,9 +616,7 @@ void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t 
         cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * 2 * RS_RADIX, s);
         return;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaFuncSetAttribute(rs_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    opt_in_shared_memory();
     const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
     uint32_t* d_ticket = d_hist + 2 * RS_RADIX;
     cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * (2 * RS_RADIX + 1), s);
@@ -640,7 +650,7 @@ void radix_partition_to_peers(const uint64_t* keys_in, uint32_t iota_base, uint3
                               const PeerTable* d_peers, const uint32_t* d_recv_offsets, uint32_t* d_hist,
                               uint32_t* d_tile_status, cudaStream_t s) {
     if (n == 0) return;
-    cudaFuncSetAttribute(rs_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    opt_in_shared_memory();
     const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
     uint32_t* d_ticket = d_hist + 2 * RS_RADIX;
     // digit bases = where my segment starts in each destination buffer; unused digits stay 0

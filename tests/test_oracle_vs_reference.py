@@ -12,7 +12,19 @@ import pytest
 
 from oracle import refcd
 
-pytestmark = pytest.mark.skipif(not refcd.available(), reason="oracle/_ref/libref_cd.so not built")
+REFERENCE_SOURCES = "/root/reference/CollisionDetection"
+
+if not refcd.available() and os.path.isdir(REFERENCE_SOURCES):
+    # the build container: the reference is there, so its functions MUST have been compiled (make -C oracle);
+    # a silent skip here would un-pin the oracle without anybody noticing
+    raise RuntimeError("oracle/_ref/libref_cd.so is missing although /root/reference exists: run `make -C oracle` "
+                       "(or __graft_entry__.build())")
+
+# elsewhere (the GPU box normally receives the built file; a bare checkout does not): skip LOUDLY - the committed
+# vectors made by the same functions (tests/test_oracle_golden.py) then carry the pin
+pytestmark = pytest.mark.skipif(not refcd.available(),
+                                reason="PARITY PIN REDUCED: oracle/_ref/libref_cd.so absent and no /root/reference to build it "
+                                       "from - only the committed golden vectors check the oracle here")
 
 
 def compare_all_stages(co, ref_mesh, xyz, idx):
