@@ -260,37 +260,18 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
     trace_mark("build_begin", s);
     int npass = 0;
-    if (n && !keys_given) {
-        // K1
-        uint32_t* d_bbox = nullptr;
-        if (p->auto_box) {
-            d_bbox = ctx->d_scalars;
-            launch_bbox(m->d_verts, m->nverts, d_bbox, ctx->sm_count, s);
-        }
-        // face-ordered leaf records for the tree build (64 B per triangle, allocated on first use; B200CD_RECS=0 turns
-        // them off - tuning / A-B knob). Without them the build gathers indices and vertices itself.
-        // Worth it when vertices are (mostly) unshared - a triangle soup, V = 3N: -0.21 ms in the tree build for
-        // +0.11 ms in K1 at 16 M. On a mesh (V ~ N/2) the vertex gathers hit L2 anyway and the records only add traffic.
-        const bool want_recs = leaf_records_enabled() && b->unshared_verts;
-        if (!want_recs && b->d_recs) { cudaFree(b->d_recs); b->d_recs = nullptr; }
-        if (!b->d_recs && want_recs && cudaMalloc(reinterpret_cast<void**>(&b->d_recs), sizeof(LeafRec) * (size_t)n) != cudaSuccess) {
-            cudaGetLastError();
-            b->d_recs = nullptr;  // not enough memory: the gather path needs none
-        }
-        launch_morton(m->d_verts, m->d_idx, 0, n, *p, d_bbox, b->d_keys[0], s, b->d_recs);
-    }
-    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
+    // ---- the sort's plan first (host logic only): K1 can then count the digits of the passes that will run
+    RadixPass passes[8];
+    int high = 0;
     if (n) {
-        // K2: radix_digit_bits()-wide digits over the significant key bits (60 of 63: morton.h:15 masks 21 bits
+        // K2 plan: radix_digit_bits()-wide digits over the significant key bits (60 of 63: morton.h:15 masks 21 bits
         // per axis but the 2^20 scale leaves bit 20 clear for in-box meshes; we still sort all
         // 63 so out-of-box meshes order exactly like the host sort)
-        RadixPass passes[8];
         const int total_bits = (p->key_bits == 30) ? 30 : 63;
         const int db = radix_digit_bits();
         for (int sh = 0; sh < total_bits; sh += db) passes[npass++] = {sh, std::min(db, total_bits - sh)};
         // Hybrid sort for 63-bit keys: radix passes over the top b->sort_high digits only, the low bits are put in
         // order by a per-run fix-up (radix_sort.cu). The previous build's run statistics steer sort_high.
-        int high = 0;
         if (npass == 8 && b->d_fix && !sort_hybrid_disabled()) {
             const cudaError_t landed = b->fix_pending ? cudaEventQuery(b->ev_fix) : cudaErrorNotReady;
             if (landed != cudaSuccess) cudaGetLastError();  // "not ready" is an answer, not a failure: do not leave it behind
@@ -340,8 +321,43 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
             }
             high = b->sort_high < 8 ? b->sort_high : 0;
         }
+    }
+    // B200CD_FUSED_HIST=0: the sort reads the keys once more for its histograms (A/B knob, read once)
+    static int fused = -1;
+    if (fused < 0) {
+        const char* e = getenv("B200CD_FUSED_HIST");
+        fused = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool hist_in_k1 = fused && n && !keys_given;
+    RadixHistPlan hplan{};
+    if (n && !keys_given) {
+        // K1
+        uint32_t* d_bbox = nullptr;
+        if (p->auto_box) {
+            d_bbox = ctx->d_scalars;
+            launch_bbox(m->d_verts, m->nverts, d_bbox, ctx->sm_count, s);
+        }
+        // face-ordered leaf records for the tree build (64 B per triangle, allocated on first use; B200CD_RECS=0 turns
+        // them off - tuning / A-B knob). Without them the build gathers indices and vertices itself.
+        // Worth it when vertices are (mostly) unshared - a triangle soup, V = 3N: -0.21 ms in the tree build for
+        // +0.11 ms in K1 at 16 M. On a mesh (V ~ N/2) the vertex gathers hit L2 anyway and the records only add traffic.
+        const bool want_recs = leaf_records_enabled() && b->unshared_verts;
+        if (!want_recs && b->d_recs) { cudaFree(b->d_recs); b->d_recs = nullptr; }
+        if (!b->d_recs && want_recs && cudaMalloc(reinterpret_cast<void**>(&b->d_recs), sizeof(LeafRec) * (size_t)n) != cudaSuccess) {
+            cudaGetLastError();
+            b->d_recs = nullptr;  // not enough memory: the gather path needs none
+        }
+        if (hist_in_k1) {
+            radix_hist_plan(passes, npass, /*values*/ true, high, b->d_fix != nullptr, b->sort_top, &hplan);
+            CD_CUDA(ctx, cudaMemsetAsync(b->d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s));
+        }
+        launch_morton(m->d_verts, m->d_idx, 0, n, *p, d_bbox, b->d_keys[0], s, b->d_recs, hist_in_k1 ? &hplan : nullptr,
+                      hist_in_k1 ? b->d_hist : nullptr, ctx->sm_count);
+    }
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
+    if (n) {
         b->cur = radix_sort(b->d_keys, b->d_ids, n, passes, npass, /*iota*/ !keys_given, b->d_hist, b->d_tile_status,
-                            b->tile_status_words, ctx->sm_count, s, high, b->d_fix, b->sort_top, high ? b->ev_sort : nullptr);
+                            b->tile_status_words, ctx->sm_count, s, high, b->d_fix, b->sort_top, high ? b->ev_sort : nullptr, hist_in_k1);
         if (high) {
             CD_CUDA(ctx, cudaMemcpyAsync(b->h_fix, b->d_fix, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CD_CUDA(ctx, cudaEventRecord(b->ev_fix, s));

@@ -222,8 +222,17 @@ void launch_check_idx(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, ui
 void launch_check_idx_accumulate(const uint32_t* d_idx, uint32_t ntris, uint32_t nverts, uint32_t* d_flag, int sms, cudaStream_t s);
 void launch_bbox(const float4* d_verts, uint32_t nverts, uint32_t* d_bbox6 /*ordered-uint min3,max3*/, int sms, cudaStream_t s);
 // d_recs (optional): also write every triangle's LeafRec, in face order (slice-relative like d_keys)
+// The digit histograms of the radix passes that WILL run on the keys K1 is writing (radix_hist_plan): K1 holds every key
+// in a register anyway, so it counts the digits itself and the sort's separate histogram pass (one more read of the
+// keys) is skipped (radix_sort hist_done). hist: [npass][256] words, zeroed by the caller.
+struct RadixHistPlan {
+    int npass;
+    int shift[8];
+    uint32_t mask[8];
+};
 void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t first, uint32_t n, const b200cd_params& p,
-                   const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s, LeafRec* d_recs = nullptr);
+                   const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s, LeafRec* d_recs = nullptr,
+                   const RadixHistPlan* hist_plan = nullptr, uint32_t* d_hist = nullptr, int sms = 148);
 // radix_sort.cu
 struct RadixPass { int shift; int bits; };
 // sorts n (key,value) items; values may be null (keys only); if iota_values the
@@ -235,7 +244,11 @@ struct RadixPass { int shift; int bits; };
 int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
                bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words,
                int sms, cudaStream_t s, int high_passes = 0, uint32_t* d_fix = nullptr, int top_bits = 0,
-               cudaEvent_t* ev4 = nullptr /* hybrid: events recorded around the last radix pass [0,1] and the fix-up [2,3] */);
+               cudaEvent_t* ev4 = nullptr /* hybrid: events recorded around the last radix pass [0,1] and the fix-up [2,3] */,
+               bool hist_done = false /* d_hist already holds the digit histograms of radix_hist_plan (and zeroed tickets) */);
+// the passes radix_sort will run first for these arguments (hybrid: the window of high digits), for a fused histogram
+void radix_hist_plan(const RadixPass* passes, int npass, bool has_values, int high_passes, bool has_fix, int top_bits,
+                     RadixHistPlan* out);
 // stable range partition (multi-GPU): bucket = number of device-resident splitters <= key; needs
 // d_hist >= 2*256+1 words and d_tile_status >= radix_tile_status_words(n, 1); counts land in d_hist[256..]
 void radix_partition(const uint64_t* keys_in, const uint32_t* vals_in, uint32_t iota_base, uint64_t* keys_out,

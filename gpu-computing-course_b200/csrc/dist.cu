@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(32)
 dist_barrier_kernel(DistPeers P, CommBlock* mine, uint32_t rank, uint32_t world, uint32_t epoch, unsigned long long timeout_ns) {
     const uint32_t p = threadIdx.x;
     if (p >= world || p == rank) return;
+    if (*reinterpret_cast<volatile uint32_t*>(&mine->error)) return;  // a peer is gone: the step fails anyway, do not wait again
     __threadfence_system();
     st_release_sys(&P.comm[p]->flags[rank], epoch);
     const unsigned long long t0 = globaltimer_ns();
@@ -343,7 +344,7 @@ API int b200cd_dist_create(b200cd_ctx* ctx, uint32_t rank, uint32_t world, uint3
     d->cnt = (uint32_t)((uint64_t)(rank + 1) * ntris_total / world) - d->lo;
     d->cap = (uint32_t)std::min<uint64_t>(ntris_total, (uint64_t)((double)ntris_total / world * slack) + 65536);
     d->ghost_cap = std::max<uint64_t>(ntris_total / world / 2, 65536);
-    d->gather_cap = pair_capacity ? pair_capacity : (uint64_t)ntris_total / 2 + 65536;
+    d->gather_cap = pair_capacity ? pair_capacity : (uint64_t)ntris_total + 65536;
     if (const char* e = getenv("B200CD_BARRIER_TIMEOUT_MS")) {
         const long ms = atol(e);
         if (ms > 0) d->timeout_ns = (uint64_t)ms * 1000000ull;

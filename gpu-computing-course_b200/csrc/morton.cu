@@ -131,13 +131,21 @@ struct MortonBox {
     double o[3], e[3];
 };
 
-template <int KEY_BITS>
+// HIST: the grid strides over the triangles and every block also counts, in shared memory, the digits the radix sort's
+// passes will look at (plan), adding its counts to the global histograms once at the end - the sort then skips its
+// own histogram kernel, i.e. one more read of all keys (K1 is bandwidth-bound: the shared-memory atomics ride along).
+template <int KEY_BITS, bool HIST>
 __global__ void __launch_bounds__(256)
 morton_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx, uint32_t first, uint32_t n, MortonBox box,
-              const uint32_t* __restrict__ bbox6, uint64_t* __restrict__ keys, LeafRec* __restrict__ recs) {
-    // triangles first .. first+n-1 (a slice when the build is partitioned over GPUs); keys[] is slice-relative
-    const uint32_t tl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tl >= n) return;
+              const uint32_t* __restrict__ bbox6, uint64_t* __restrict__ keys, LeafRec* __restrict__ recs,
+              RadixHistPlan plan, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[HIST ? 8 * 256 : 1];
+    if (HIST) {
+        for (int i = threadIdx.x; i < plan.npass * 256; i += 256) s_hist[i] = 0;
+        __syncthreads();
+    }
+  // triangles first .. first+n-1 (a slice when the build is partitioned over GPUs); keys[] is slice-relative
+  for (uint32_t tl = blockIdx.x * blockDim.x + threadIdx.x; tl < n; tl += gridDim.x * blockDim.x) {
     const uint32_t t = first + tl;
     if (bbox6) {  // auto box: origin = bbox.lo, extent = hi - lo (1 if degenerate)
 #pragma unroll
@@ -180,10 +188,24 @@ morton_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx
         key = (xx << 2) | (yy << 1) | zz;
     }
     keys[tl] = key;
+    if (HIST) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+            if (p < plan.npass) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> plan.shift[p]) & plan.mask[p])], 1u);
+    }
+  }
+    if (HIST) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < plan.npass * 256; i += 256) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(&hist[i], c);
+        }
+    }
 }
 
 void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t first, uint32_t n, const b200cd_params& p,
-                   const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s, LeafRec* d_recs) {
+                   const uint32_t* d_bbox6_or_null, uint64_t* d_keys, cudaStream_t s, LeafRec* d_recs,
+                   const RadixHistPlan* hist_plan, uint32_t* d_hist, int sms) {
     if (!n) return;
     MortonBox box;
     for (int a = 0; a < 3; ++a) {
@@ -191,10 +213,18 @@ void launch_morton(const float4* d_verts, const uint32_t* d_idx, uint32_t first,
         box.e[a] = p.morton_extent[a];
     }
     uint32_t blocks = (n + 255) / 256;
-    if (p.key_bits == 30)
-        morton_kernel<30><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys, d_recs);
-    else
-        morton_kernel<63><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys, d_recs);
+    RadixHistPlan none{};
+    if (hist_plan && d_hist) {  // fused digit histograms: a fixed grid strides over the triangles (one flush per block)
+        blocks = std::min<uint32_t>(blocks, (uint32_t)std::max(sms, 1) * 16u);
+        if (p.key_bits == 30)
+            morton_kernel<30, true><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys, d_recs, *hist_plan, d_hist);
+        else
+            morton_kernel<63, true><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys, d_recs, *hist_plan, d_hist);
+    } else if (p.key_bits == 30) {
+        morton_kernel<30, false><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys, d_recs, none, nullptr);
+    } else {
+        morton_kernel<63, false><<<blocks, 256, 0, s>>>(d_verts, d_idx, first, n, box, d_bbox6_or_null, d_keys, d_recs, none, nullptr);
+    }
     count_launch();
     trace_mark("morton_kernel", s);
 }

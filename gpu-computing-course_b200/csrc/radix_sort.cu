@@ -522,14 +522,13 @@ uint64_t radix_tile_status_words(uint32_t n, int npass) {
     return tiles * RS_RADIX * (uint64_t)npass;
 }
 
-int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
-               bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words, int sms,
-               cudaStream_t s, int high_passes, uint32_t* d_fix, int top_bits, cudaEvent_t* ev4) {
-    (void)tile_status_words;
-    if (n == 0 || npass == 0) return 0;
-    const bool hybrid = high_passes > 0 && high_passes < npass && d_fix && vals && npass % 2 == 0;
+// which passes run first (unconditionally), and where the hybrid sort's window of digits ends
+static void make_plan(const RadixPass* passes, int npass, bool has_values, int high_passes, bool has_fix, int top_bits,
+                      PassList& pl, PassList& all, bool& hybrid, int& top) {
+    hybrid = high_passes > 0 && high_passes < npass && has_fix && has_values && npass % 2 == 0;
     const int first = hybrid ? npass - high_passes : 0;  // passes [first, npass) run unconditionally
-    PassList pl{}, all{};
+    pl = PassList{};
+    all = PassList{};
     all.npass = npass;
     for (int p = 0; p < npass; ++p) {
         all.shift[p] = passes[p].shift;
@@ -544,22 +543,48 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
     // Morton keys use 60 of the 63 bits), so all of its 8 * high_passes bits separate keys. The fix-up checks that no key
     // reaches above the window and otherwise hands over to the fallback passes.
     const int key_top = all.shift[npass - 1] + (32 - __builtin_clz(all.mask[npass - 1]));  // bits the full plan covers
-    const int top = hybrid ? std::max(8 * high_passes, std::min(top_bits > 0 ? top_bits : key_top, key_top)) : key_top;
+    top = hybrid ? std::max(8 * high_passes, std::min(top_bits > 0 ? top_bits : key_top, key_top)) : key_top;
     if (hybrid) {
         for (int p = 0; p < high_passes; ++p) {
             pl.shift[p] = top - 8 * (high_passes - p);
             pl.mask[p] = 0xffu;
         }
     }
+}
+
+void radix_hist_plan(const RadixPass* passes, int npass, bool has_values, int high_passes, bool has_fix, int top_bits,
+                     RadixHistPlan* out) {
+    PassList pl, all;
+    bool hybrid;
+    int top;
+    make_plan(passes, npass, has_values, high_passes, has_fix, top_bits, pl, all, hybrid, top);
+    out->npass = pl.npass;
+    for (int p = 0; p < RS_MAX_PASS; ++p) {
+        out->shift[p] = pl.shift[p];
+        out->mask[p] = pl.mask[p];
+    }
+}
+
+int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass* passes, int npass,
+               bool iota_values, uint32_t* d_hist, uint32_t* d_tile_status, uint64_t tile_status_words, int sms,
+               cudaStream_t s, int high_passes, uint32_t* d_fix, int top_bits, cudaEvent_t* ev4, bool hist_done) {
+    (void)tile_status_words;
+    if (n == 0 || npass == 0) return 0;
+    PassList pl, all;
+    bool hybrid;
+    int top;
+    make_plan(passes, npass, vals != nullptr, high_passes, d_fix != nullptr, top_bits, pl, all, hybrid, top);
     const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE;
     opt_in_shared_memory();
     const uint32_t hblocks = min((n / 2 + RH_THREADS - 1) / RH_THREADS + 1, (uint32_t)sms * 8u);
     uint32_t* d_ticket = d_hist + npass * RS_RADIX;
-    cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);
+    if (!hist_done) cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * radix_hist_words(npass), s);
     cudaMemsetAsync(d_tile_status, 0, sizeof(uint32_t) * (size_t)tiles * RS_RADIX * pl.npass, s);
     if (hybrid) cudaMemsetAsync(d_fix, 0, sizeof(uint32_t) * 4, s);
-    rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[0], n, pl, d_hist, nullptr, nullptr, 0);
-    count_launch();
+    if (!hist_done) {  // (otherwise K1 counted the digits while it had the keys in registers)
+        rs_histogram<<<hblocks, RH_THREADS, 0, s>>>(keys[0], n, pl, d_hist, nullptr, nullptr, 0);
+        count_launch();
+    }
     rs_scan<<<pl.npass, RS_RADIX, 0, s>>>(d_hist, nullptr);
     count_launch();
     trace_mark("rs_histogram+scan", s);

@@ -377,7 +377,9 @@ int b200cd_ghost_counter_read(b200cd_ctx* ctx, b200cd_bvh* bvh, uint64_t* count_
  *   4. a barrier of the caller's, then b200cd_dist_destroy (peers must not be inside a step any more).
  * Every rank must hold the whole mesh (same ntris, same contents). slack >= 1: room for uneven Morton ranges
  * (capacity per rank = ntris / world * slack + 65536); pair_capacity = room in rank 0's gather buffer
- * (0 = ntris / 2 + 65536). world = 1 runs the same code on one GPU. */
+ * (0 = ntris + 65536 pairs; the buffer is peer-mapped and cannot grow: a step that finds more returns
+ * B200CD_E_CAPACITY on rank 0 with the count in the error text - create the object again with more room).
+ * world = 1 runs the same code on one GPU. */
 #define B200CD_DIST_BLOB_BYTES 512
 typedef struct b200cd_dist_stats {
     uint32_t rank, world;

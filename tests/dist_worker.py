@@ -33,6 +33,18 @@ def workload(mg, cd, name):
         s = int(name[5:])
         xyz, idx = mg.cloth_fold(s, s)
         return xyz, idx, cd.default_params()
+    if name.startswith("dup"):
+        # edge case: clusters of IDENTICAL triangles (equal Morton keys, runs far longer than the sort's fix-up handles,
+        # ties ordered by triangle id) - every rank must order them exactly like one GPU does
+        k = int(name[3:])
+        bx, bi = mg.soup(max(k // 64, 4), seed=11)
+        xyz = np.tile(bx, (64, 1))
+        idx = (np.tile(bi, (64, 1)) + (np.arange(64, dtype=np.uint32).repeat(len(bi)) * np.uint32(len(bx)))[:, None]).astype(np.uint32)
+        return xyz, idx, cd.make_params(*unit)
+    if name.startswith("tiny"):
+        # edge case: fewer triangles than ranks x 2 (ranks whose Morton range is empty or a single leaf)
+        xyz, idx = mg.soup(int(name[4:]), h=0.4, seed=3)
+        return xyz, idx, cd.make_params(*unit)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -46,6 +58,8 @@ def exchange(rdv, tag, rank, world, payload, timeout=120.0):
     for r in range(world):
         p = os.path.join(rdv, f"{tag}_{r}.bin")
         while not os.path.exists(p):
+            if os.path.exists(os.path.join(rdv, "FAILED")):
+                raise SystemExit(f"rank {rank}: another rank failed")
             if time.time() - t0 > timeout:
                 raise SystemExit(f"rank {rank}: rank {r} never published {tag}")
             time.sleep(0.005)
@@ -65,7 +79,8 @@ def main():
     ctx = cd.Context(dev)
     xyz, idx, params = workload(mg, cd, name)
     mesh = ctx.mesh_from_arrays(xyz, idx)
-    dist = ctx.dist_create(rank, world, mesh.ntris, slack=float(os.environ.get("B200CD_TEST_SLACK", "1.5")))
+    dist = ctx.dist_create(rank, world, mesh.ntris, slack=float(os.environ.get("B200CD_TEST_SLACK", "1.5")),
+                           pair_capacity=int(os.environ.get("B200CD_TEST_PAIR_CAP", "0")))
     dist.connect(exchange(rdv, "blob", rank, world, dist.export()))
     exchange(rdv, "connected", rank, world, b"1")      # nobody steps before everybody has mapped everybody
     stats = []
@@ -93,4 +108,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        try:  # tell the other ranks at once (they would otherwise wait for their barrier / rendezvous timeouts)
+            open(os.path.join(sys.argv[3], "FAILED"), "w").close()
+        except Exception:
+            pass
+        raise

@@ -61,7 +61,7 @@ def test_dist_world1_in_process(cd, co, ctx, mg, name):
 
 def run_ranks(world, name, steps=2, env_extra=None, timeout=600):
     rdv = tempfile.mkdtemp(prefix="b200cd_rdv_")
-    env = dict(os.environ, **(env_extra or {}))
+    env = dict(os.environ, B200CD_BARRIER_TIMEOUT_MS="20000", **(env_extra or {}))
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), str(r), str(world), rdv, name, str(steps)],
                               env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
     outs = []
@@ -98,6 +98,27 @@ def test_dist_ranks_in_processes_equal_single_gpu(cd, co, ctx, mg, world, name):
     assert ghosts > 0                       # and the exchange really happened
 
 
+@pytest.mark.parametrize("world,name", [(2, "dup4096"), (3, "tiny5"), (2, "tiny2")])
+def test_dist_edge_cases_duplicates_and_tiny_ranges(cd, co, ctx, mg, world, name):
+    """duplicate keys across the whole mesh (the reference builds a malformed tree for them, load_obj.h:110-115 only
+    reports them; ours orders ties by id) and meshes smaller than the rank count: same list as one GPU and the oracle"""
+    want = reference_lists(cd, co, ctx, mg, name, steps=2)
+    if name.startswith("dup"):
+        # 40 pairs per triangle: more than rank 0's default gather buffer (ntris + 65536 pairs) - the step says so ...
+        with pytest.raises(AssertionError, match="gathered pair list holds"):
+            run_ranks(world, name, steps=2)
+        # ... and runs with the room it asked for
+        rdv = run_ranks(world, name, steps=2, env_extra={"B200CD_TEST_PAIR_CAP": str(len(want[0]) + len(want[0]) // 2)})
+    else:
+        rdv = run_ranks(world, name, steps=2)
+    for k in range(2):
+        got = np.load(os.path.join(rdv, f"pairs_{k}.npy"))
+        assert got.shape == want[k].shape and np.array_equal(got, want[k]), f"{name} step {k}"
+    xyz, idx, _ = dist_worker.workload(mg, cd, name)
+    total = sum(json.load(open(os.path.join(rdv, f"stats_{r}.json")))["steps"][-1]["local_triangles"] for r in range(world))
+    assert total == len(idx)
+
+
 def test_dist_retry_after_overflow_and_uneven_ranges(cd, co, ctx, mg):
     """a dense-contact mesh overflows the first guess of the pair buffers: all ranks retry together"""
     want = reference_lists(cd, co, ctx, mg, "cloth200", steps=2)
@@ -105,3 +126,46 @@ def test_dist_retry_after_overflow_and_uneven_ranges(cd, co, ctx, mg):
     for k in range(2):
         assert np.array_equal(np.load(os.path.join(rdv, f"pairs_{k}.npy")), want[k])
     assert sum(json.load(open(os.path.join(rdv, f"stats_{r}.json")))["steps"][-1]["retries"] for r in range(2)) >= 2
+
+
+def test_dist_argument_errors_and_trace(cd, ctx, mg, tmp_path):
+    """statuses, not crashes: bad rank / world, step before connect, foreign blobs; and the kernel timeline dump"""
+    import ctypes as C
+    lib = cd.lib()
+    h = C.c_void_p()
+    assert lib.b200cd_dist_create(ctx.h, C.c_uint32(2), C.c_uint32(2), C.c_uint32(1000), C.c_double(1.5), C.c_uint64(0), C.byref(h)) == cd.E_INVALID
+    assert lib.b200cd_dist_create(ctx.h, C.c_uint32(0), C.c_uint32(17), C.c_uint32(1000), C.c_double(1.5), C.c_uint64(0), C.byref(h)) == cd.E_INVALID
+    xyz, idx = mg.soup(20000, seed=9)
+    params = cd.make_params((0, 0, 0), (1, 1, 1))
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    d2 = ctx.dist_create(0, 2, mesh.ntris)                      # rank 0 of 2, never connected
+    with pytest.raises(cd.B200cdError) as e:
+        d2.step(mesh, params)
+    assert e.value.status == cd.E_INVALID
+    blob = d2.export()
+    assert len(blob) == cd.DIST_BLOB_BYTES
+    with pytest.raises(cd.B200cdError) as e:
+        d2.connect([blob, blob])                                # the second blob is not rank 1's
+    assert e.value.status == cd.E_INVALID
+    d2.destroy()
+    d1 = ctx.dist_create(0, 1, mesh.ntris)
+    other = ctx.mesh_from_arrays(xyz[:300], idx[:100])
+    with pytest.raises(cd.B200cdError) as e:
+        d1.step(other, params)                                  # not the mesh size the object was created for
+    assert e.value.status == cd.E_INVALID
+    # kernel timeline: every launch of one step, with device times
+    ctx.trace_enable(True)
+    d1.step(mesh, params)
+    d1.barrier()                                                # world = 1: a no-op, but a valid call
+    ctx.synchronize()
+    ctx.trace_enable(False)
+    out = tmp_path / "trace.csv"
+    ctx.trace_dump(str(out))
+    rows = [l.rsplit(",", 1) for l in out.read_text().splitlines()]
+    names = [r[0] for r in rows]
+    for want in ("step_begin", "morton_kernel", "key_hist16", "partition_to_peers", "rs_pass", "build_kernel", "broad_kernel", "narrow_kernel"):
+        assert want in names, (want, names)
+    assert all(float(r[1]) >= 0 for r in rows[1:])
+    d1.destroy()
+    other.destroy()
+    mesh.destroy()
