@@ -1294,6 +1294,7 @@ int grow(b200cd_ctx* ctx, uint2** buf, uint64_t* cap, uint64_t want) {
 int sort_pairs_impl(b200cd_ctx* ctx, uint2** d_pairs, uint2** d_tmp, uint64_t count, int id_bits, uint32_t** d_hist,
                     uint32_t** d_status, uint64_t* status_words, cudaStream_t s) {
     if (count < 2) return B200CD_OK;
+    if (small_pair_sort(*d_pairs, count, s)) return B200CD_OK;  // a few thousand pairs: one launch instead of ten
     if (count >= (1ull << 30)) return set_error(ctx, B200CD_E_TOOBIG, "pair list too long to sort");
     // memory word of a pair {lo_id, hi_id} read as u64 = hi_id << 32 | lo_id: LSD order = hi_id digits, then lo_id digits
     RadixPass passes[8];

@@ -271,6 +271,8 @@ void radix_partition_counts(const uint64_t* keys_in, uint32_t n, const uint64_t*
 void radix_partition_to_peers(const uint64_t* keys_in, uint32_t iota_base, uint32_t n, const uint64_t* d_splitters, int nsplit,
                               const PeerTable* d_peers, const uint32_t* d_recv_offsets, uint32_t* d_hist,
                               uint32_t* d_tile_status, cudaStream_t s);
+// lists of at most 8192 pairs: one block, bitonic network in shared memory, in place; false = too long (use radix_sort)
+bool small_pair_sort(uint2* d_pairs, uint64_t count, cudaStream_t s);
 uint64_t radix_tile_status_words(uint32_t n, int npass);
 int radix_digit_bits();  // digit width of one pass (status / histogram rows hold 1 << bits words)
 uint32_t radix_hist_words(int npass);

@@ -27,6 +27,8 @@
 // histogram adds one 8 B read. Look-back words: 1 KiB per tile per pass.
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace b200cd {
@@ -207,16 +209,15 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
 // load -> rank -> look-back -> scatter latency chain of each tile behind the other tile's.
 // COND: persistent variant for the hybrid sort's fallback - a fixed grid that does nothing when *cond == 0 and
 // otherwise works through all the tiles (ticket loop). The plain variant runs one tile per CTA.
-template <bool HAS_VALUES, bool SPLIT, bool COND = false>
-__global__ void __launch_bounds__(RS_THREADS, RS_MINB_V)
-rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
-        uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values, uint32_t iota_base,
-        const uint64_t* __restrict__ splitters, int nsplit,
-        const PeerTable* __restrict__ peers,        // non-null: bucket d is written into peer d's buffers (NVLink stores)
-        const uint32_t* __restrict__ digit_base_g,  // [256] exclusive global digit offsets of this pass
-        uint32_t* __restrict__ status,              // [ntiles][256] look-back words of this pass
-        uint32_t* __restrict__ ticket, const uint32_t* __restrict__ cond = nullptr, uint32_t ntiles = 0) {
-    if (COND && *cond == 0) return;
+template <bool HAS_VALUES, bool SPLIT, bool COND>
+__device__ __forceinline__ void
+rs_pass_body(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
+             uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values, uint32_t iota_base,
+             const uint64_t* __restrict__ splitters, int nsplit,
+             const PeerTable* __restrict__ peers,        // non-null: bucket d is written into peer d's buffers (NVLink stores)
+             const uint32_t* __restrict__ digit_base_g,  // [256] exclusive global digit offsets of this pass
+             uint32_t* __restrict__ status,              // [ntiles][256] look-back words of this pass
+             uint32_t* __restrict__ ticket, uint32_t ntiles) {
     // dynamic shared memory (> 48 KiB): [stage_k 32 KiB][stage_v 16 KiB if values][warp_hist][digit_base][warp_tot][tile][tile_hist]
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t* stage_k = reinterpret_cast<uint64_t*>(rs_smem);
@@ -414,6 +415,36 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
   }
 }
 
+template <bool HAS_VALUES, bool SPLIT>
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB_V)
+rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
+        uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, int iota_values, uint32_t iota_base,
+        const uint64_t* __restrict__ splitters, int nsplit, const PeerTable* __restrict__ peers,
+        const uint32_t* __restrict__ digit_base_g, uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+    rs_pass_body<HAS_VALUES, SPLIT, false>(keys_in, keys_out, vals_in, vals_out, n, shift, mask, iota_values, iota_base, splitters,
+                                           nsplit, peers, digit_base_g, status, ticket, 0u);
+}
+
+// The hybrid sort's fallback: ALL passes of a full sort in ONE cooperative launch (a fixed grid of co-resident CTAs
+// works through every pass's tiles by ticket, grid-wide barrier between passes). Launched behind every fix-up and
+// idle - one launch that returns at once - unless the fix-up met a run it does not handle (*cond != 0). Before: eight
+// conditional launches per build, each idle but not free (~25 us per build; 4 % of a 1.26 M-triangle step).
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB_V)
+rs_fallback_kernel(uint64_t* __restrict__ k0, uint64_t* __restrict__ k1, uint32_t* __restrict__ v0, uint32_t* __restrict__ v1, uint32_t n,
+                   PassList all, const uint32_t* __restrict__ digit_bases /* [npass][256] */, uint32_t* __restrict__ status_all,
+                   uint32_t* __restrict__ tickets, const uint32_t* __restrict__ cond, uint32_t ntiles) {
+    if (*cond == 0) return;  // (every CTA takes the same way: nobody is left waiting at a barrier)
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int p = 0; p < all.npass; ++p) {
+        const bool even = (p & 1) == 0;
+        rs_pass_body<true, false, true>(even ? k0 : k1, even ? k1 : k0, even ? v0 : v1, even ? v1 : v0, n, all.shift[p], all.mask[p], 0,
+                                        0u, nullptr, 0, nullptr, digit_bases + p * RS_RADIX, status_all + (size_t)p * ntiles * RS_RADIX,
+                                        tickets + p, ntiles);
+        __threadfence();
+        grid.sync();
+    }
+}
+
 // ---- 4. hybrid sort: fix-up of the low bits after sorting only the high digits
 // After stable passes over the digits at and above `lowbit`, the items are ordered by their high bits and every
 // run of equal high bits still has to be ordered by its low bits (ties keep their order). With lowbit chosen so
@@ -508,9 +539,66 @@ static void opt_in_shared_memory() {
     if (dev >= 0 && dev < 64 && attr_set[dev]) return;
     cudaFuncSetAttribute(rs_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
     cudaFuncSetAttribute(rs_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false));
-    cudaFuncSetAttribute(rs_pass<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    cudaFuncSetAttribute(rs_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
     cudaFuncSetAttribute(rs_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
+}
+
+// ---- 5. small lists: ONE block sorts up to SS_MAX packed pairs in shared memory (bitonic network) instead of a
+// histogram + scan + 2 x ceil(id_bits / 8) radix launches whose cost is all launch latency (a 384-pair result - the
+// flag mesh - took 10 launches, ~60 us, for 3 KB of data). Order: lexicographic by (first ID, second ID), the same as
+// the LSD passes over the two halves of the packed word give.
+namespace {
+constexpr int SS_THREADS = 1024;
+constexpr int SS_MAX = 8192;  // 64 KiB of shared memory
+__global__ void __launch_bounds__(SS_THREADS)
+small_pair_sort_kernel(uint2* __restrict__ pairs, uint32_t count, uint32_t padded /* power of two >= count */) {
+    extern __shared__ __align__(16) unsigned char ss_smem[];
+    uint64_t* key = reinterpret_cast<uint64_t*>(ss_smem);
+    for (uint32_t i = threadIdx.x; i < padded; i += SS_THREADS) {
+        uint64_t k = ~0ull;  // padding sorts last (a real pair has first ID < second ID, never both all-ones)
+        if (i < count) {
+            const uint2 p = pairs[i];
+            k = ((uint64_t)p.x << 32) | p.y;
+        }
+        key[i] = k;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= padded; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < padded / 2; t += SS_THREADS) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));  // partner pairs (lo, lo + stride)
+                const uint32_t hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t a = key[lo], b = key[hi];
+                if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < count; i += SS_THREADS) {
+        const uint64_t k = key[i];
+        pairs[i] = make_uint2((uint32_t)(k >> 32), (uint32_t)k);
+    }
+}
+}  // namespace
+
+bool small_pair_sort(uint2* d_pairs, uint64_t count, cudaStream_t s) {
+    if (count < 2) return true;
+    if (count > (uint64_t)SS_MAX) return false;
+    uint32_t padded = 2;
+    while (padded < count) padded <<= 1;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaFuncSetAttribute(small_pair_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_MAX * 8);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    small_pair_sort_kernel<<<1, SS_THREADS, (size_t)padded * 8, s>>>(d_pairs, (uint32_t)count, padded);
+    count_launch();
+    trace_mark("small_pair_sort", s);
+    return true;
 }
 
 int radix_digit_bits() { return RS_BITS; }
@@ -618,13 +706,29 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
                                                  (uint64_t)tiles * RS_RADIX * npass / 4);
     rs_scan<<<npass, RS_RADIX, 0, s>>>(d_hist, d_fix);
     count_launch(2);
-    for (int p = 0; p < npass; ++p) {  // an even number of passes: the result lands in the buffer the fix-up worked on
-        uint32_t* status = d_tile_status + (size_t)p * tiles * RS_RADIX;
-        rs_pass<true, false, true><<<2 * sms, RS_THREADS, rs_smem_bytes(true), s>>>(
-            keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, all.shift[p], all.mask[p], 0, 0u, nullptr, 0, nullptr,
-            d_hist + p * RS_RADIX, status, d_ticket + p, d_fix, tiles);
+    {   // an even number of passes: the result lands in the buffer the fix-up worked on
+        static int resident[64] = {};  // co-resident CTAs of the cooperative launch, per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) dev = 0;
+        if (!resident[dev]) {
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rs_fallback_kernel, RS_THREADS, rs_smem_bytes(true));
+            resident[dev] = std::max(1, std::min(per_sm, 2)) * std::max(sms, 1);
+        }
+        uint64_t* k0 = keys[cur];
+        uint64_t* k1 = keys[cur ^ 1];
+        uint32_t* v0 = vals[cur];
+        uint32_t* v1 = vals[cur ^ 1];
+        const uint32_t* bases = d_hist;
+        uint32_t* status_all = d_tile_status;
+        uint32_t* tickets = d_ticket;
+        const uint32_t* cond = d_fix;
+        uint32_t ntiles = tiles;
+        void* args[] = {&k0, &k1, &v0, &v1, &n, &all, &bases, &status_all, &tickets, &cond, &ntiles};
+        cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rs_fallback_kernel), dim3(resident[dev]), dim3(RS_THREADS), args,
+                                    rs_smem_bytes(true), s);
         count_launch();
-        cur ^= 1;
     }
     trace_mark("rs_fallback (idle unless a run was too long)", s);
     return cur;
