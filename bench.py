@@ -625,8 +625,14 @@ def run_gpu_arm(args, workload):
             dominant = "sort"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        traffic_note = None
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(workload, {}).get(dominant)
+            if traffic is not None and world > 1:
+                # ncu may not wrap a multi-rank run: the single-GPU capture of the same workload, divided by the ranks
+                # (each rank traverses 1/N of the leaves over 1/N of the nodes)
+                traffic = int(traffic / world)
+                traffic_note = f"single-GPU ncu capture of {workload} / {world} ranks (a multi-rank run cannot go under ncu)"
         # the same stages against SURVEY.md section 8(d)'s CONTRACT bytes (the survey's planned layout, not ours): a fatter
         # layout of ours cannot raise these fractions
         cb = contract_bytes(nloc, min(nverts, 3 * nloc) if partitioned else nverts, npairs)
@@ -639,7 +645,7 @@ def run_gpu_arm(args, workload):
         contract_stage = {"traverse": "query", "narrow": "query"}.get(dominant, dominant)
         roofline = {"bound": "hbm", "kernel": STAGE_KERNEL[dominant], "stage": dominant,
                     "achieved": stages[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": stages[dominant]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "frac": stages[dominant]["frac"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                     "launch_ms": stages[dominant]["ms"], "algorithmic_bytes": stages[dominant]["algorithmic_bytes"],
                     "stages": stages,
                     "frac_contract": contract[contract_stage]["frac"],

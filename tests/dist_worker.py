@@ -23,6 +23,10 @@ sys.path.insert(0, ROOT)
 def workload(mg, cd, name):
     """(xyz, idx, params) - small and medium meshes of the bench generators"""
     unit = ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+    if name.endswith("/30"):  # the 30-bit key variant (morton.h:31-40): many duplicate keys, 14-bit histogram shift
+        xyz, idx, params = workload(mg, cd, name[:-3])
+        params.key_bits = 30
+        return xyz, idx, params
     if name.startswith("soup"):
         xyz, idx = mg.soup(int(name[4:]), seed=5)
         return xyz, idx, cd.make_params(*unit)

@@ -24,7 +24,7 @@ import dist_worker  # noqa: E402
 def reference_lists(cd, co, ctx, mg, name, steps=2):
     """what rank 0 must produce: single-GPU b200cd_self_collide per frame, checked against the oracle"""
     xyz, idx, params = dist_worker.workload(mg, cd, name)
-    op = co.make_params(tuple(params.morton_origin), tuple(params.morton_extent))
+    op = co.make_params(tuple(params.morton_origin), tuple(params.morton_extent), int(params.key_bits))
     out = []
     for k in range(steps):
         if k == 1:
@@ -77,7 +77,7 @@ def run_ranks(world, name, steps=2, env_extra=None, timeout=600):
     return rdv
 
 
-@pytest.mark.parametrize("world,name", [(2, "soup300000"), (2, "cloth150"), (3, "sheets160")])
+@pytest.mark.parametrize("world,name", [(2, "soup300000"), (2, "cloth150"), (3, "sheets160"), (4, "soup120000/30")])
 def test_dist_ranks_in_processes_equal_single_gpu(cd, co, ctx, mg, world, name):
     want = reference_lists(cd, co, ctx, mg, name, steps=2)
     rdv = run_ranks(world, name, steps=2)
