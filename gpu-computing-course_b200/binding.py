@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200cd.so")
+# B200CD_LIB_PATH: a tuning build of the library (make ... EXTRA_NVFLAGS=-D...), for A/B runs of bench.py
+LIB_PATH = os.environ.get("B200CD_LIB_PATH") or os.path.join(_HERE, "lib", "libb200cd.so")
 _LIB = None
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_IO, E_PARSE, E_CAPACITY, E_DEPTH, E_NODEVICE, E_TOOBIG, E_PEER = range(11)
@@ -40,7 +41,7 @@ SYMBOLS = [
     "b200cd_unique_triangles", "b200cd_unique_triangles_device",
     "b200cd_dist_create", "b200cd_dist_export", "b200cd_dist_connect", "b200cd_dist_step", "b200cd_dist_barrier",
     "b200cd_dist_get_stats", "b200cd_dist_bvh", "b200cd_dist_destroy", "b200cd_dist_set_async_sort", "b200cd_dist_wait_sorted", "b200cd_nccl_unique_id", "b200cd_dist_nccl_init",
-    "b200cd_dist_broadcast_bvh", "b200cd_trace_dump", "b200cd_trace_enable",
+    "b200cd_dist_broadcast_bvh", "b200cd_trace_dump", "b200cd_trace_enable", "b200cd_device_count", "b200cd_copy_to_host",
 ]
 
 DIST_BLOB_BYTES = 512

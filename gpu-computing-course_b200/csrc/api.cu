@@ -512,6 +512,26 @@ API void b200cd_default_params(b200cd_params* p) {
     p->pair_capacity_hint = 0;
 }
 
+API int b200cd_device_count(int* count_out) {
+    if (!count_out) return B200CD_E_INVALID;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count_out = n;
+    return n > 0 ? B200CD_OK : B200CD_E_NODEVICE;
+}
+
+API int b200cd_copy_to_host(b200cd_ctx* ctx, void* dst, const void* d_src, uint64_t bytes) {
+    if (!ctx || (bytes && (!dst || !d_src))) return set_error(ctx, B200CD_E_INVALID, "NULL argument");
+    if (!bytes) return B200CD_OK;
+    DeviceGuard g(ctx->device);
+    CD_CUDA(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200CD_OK;
+}
+
 API int b200cd_host_alloc(void** out, uint64_t bytes) {
     if (!out) return B200CD_E_INVALID;
     return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? B200CD_OK : B200CD_E_NOMEM;

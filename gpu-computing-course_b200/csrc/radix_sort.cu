@@ -56,6 +56,9 @@ namespace {
 #ifndef RS_MINB_V
 #define RS_MINB_V 2
 #endif
+#ifndef RS_BULK
+#define RS_BULK 0  // 1: tile loads by cp.async.bulk + mbarrier (tuning build, see rs_pass_body)
+#endif
 constexpr int RS_THREADS = RS_THREADS_V;      // >= 256: one thread per digit publishes / looks back
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_IPT = RS_IPT_V;              // items per thread
@@ -249,16 +252,59 @@ rs_pass_body(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_o
     // load keys (and values: their latency overlaps the ranking)
     uint64_t key[RS_IPT];
     uint32_t val[RS_IPT];
+#if RS_BULK
+    // Tuning build (-DRS_BULK=1): the tile's keys (and values) arrive by ONE bulk asynchronous copy each
+    // (cp.async.bulk + mbarrier, the 1-D TMA path) into the staging buffers, and the threads pick their items up from
+    // shared memory. Measured (profiles/r02_sort_bulk.md): no faster than the coalesced loads below - the pass is bound by
+    // its look-back chain and by 2 CTAs of 64 registers per SM, not by load issue.
+    const bool full_tile = tile_items == (uint32_t)RS_TILE && !SPLIT;
+    if (full_tile) {
+        __shared__ __align__(8) unsigned long long s_mbar;
+        const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        const uint32_t bytes = RS_TILE * 8u + ((HAS_VALUES && !iota_values) ? RS_TILE * 4u : 0u);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(stage_k)),
+                         "l"(keys_in + tile_base), "r"((uint32_t)(RS_TILE * 8u)), "r"(mbar)
+                         : "memory");
+            if (HAS_VALUES && !iota_values)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(stage_v)),
+                             "l"(vals_in + tile_base), "r"((uint32_t)(RS_TILE * 4u)), "r"(mbar)
+                             : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(mbar) : "memory");
 #pragma unroll
-    for (int k = 0; k < RS_IPT; ++k) {
-        const uint32_t g = my_base + 32 * k;
-        key[k] = (g < n) ? __ldg(keys_in + g) : ~0ull;
-    }
-    if (HAS_VALUES) {
+        for (int k = 0; k < RS_IPT; ++k) {
+            const uint32_t l = warp * (32 * RS_IPT) + lane + 32 * k;
+            key[k] = stage_k[l];
+            if (HAS_VALUES) val[k] = iota_values ? iota_base + tile_base + l : stage_v[l];
+        }
+        __syncthreads();  // everybody holds its items: the staging buffers are free again (and s_mbar may be re-initialised)
+        if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
+    } else
+#endif
+    {
 #pragma unroll
         for (int k = 0; k < RS_IPT; ++k) {
             const uint32_t g = my_base + 32 * k;
-            val[k] = iota_values ? iota_base + g : ((g < n) ? __ldg(vals_in + g) : 0u);
+            key[k] = (g < n) ? __ldg(keys_in + g) : ~0ull;
+        }
+        if (HAS_VALUES) {
+#pragma unroll
+            for (int k = 0; k < RS_IPT; ++k) {
+                const uint32_t g = my_base + 32 * k;
+                val[k] = iota_values ? iota_base + g : ((g < n) ? __ldg(vals_in + g) : 0u);
+            }
         }
     }
 

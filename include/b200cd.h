@@ -145,6 +145,12 @@ void b200cd_trace_enable(int on); /* switch the recording on / off at run time (
 
 void b200cd_default_params(b200cd_params* p);
 
+/* For callers without the CUDA runtime of their own (examples/dist_main.cpp): the number of usable GPUs, and a
+ * copy of library-owned DEVICE results (b200cd_self_collide_device, b200cd_dist_step, b200cd_unique_triangles_device)
+ * to host memory, ordered behind the context's stream and complete on return. */
+int b200cd_device_count(int* count_out);
+int b200cd_copy_to_host(b200cd_ctx* ctx, void* dst, const void* d_src, uint64_t bytes);
+
 /* Page-locked host buffers for callers that want full-rate H2D/D2H. */
 int b200cd_host_alloc(void** out, uint64_t bytes);
 int b200cd_host_free(void* p);

@@ -93,3 +93,7 @@ def test_cxx_example_is_built_and_fails_loudly_without_a_gpu(cd):
         return  # GPU box: tests/test_gpu_example.py runs it for real
     out = subprocess.run([exe, "whatever.obj"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "no CPU fallback" in out.stderr
+    dexe = os.path.join(ROOT, "gpu-computing-course_b200", "lib", "b200cd_dist_run")   # examples/dist_main.cpp: forked ranks
+    assert os.path.exists(dexe) and "libb200cd.so" in subprocess.check_output(["ldd", dexe], text=True)
+    out = subprocess.run([dexe, "whatever.obj", "--ranks", "2"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and out.stderr.count("no CPU fallback") == 2
