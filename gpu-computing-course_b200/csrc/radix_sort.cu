@@ -26,6 +26,7 @@
 // HBM traffic per pass: 12 B read + 12 B written per item (8+8 keys-only); the
 // histogram adds one 8 B read. Look-back words: 1 KiB per tile per pass.
 #include <algorithm>
+#include <cstdlib>
 
 #include <cooperative_groups.h>
 
@@ -471,6 +472,16 @@ rs_pass(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, c
                                            nsplit, peers, digit_base_g, status, ticket, 0u);
 }
 
+// one conditional pass per launch: only used where the cooperative launch below is refused (e.g. a partitioned GPU)
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB_V)
+rs_pass_cond(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
+             uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t mask, const uint32_t* __restrict__ digit_base_g,
+             uint32_t* __restrict__ status, uint32_t* __restrict__ ticket, const uint32_t* __restrict__ cond, uint32_t ntiles) {
+    if (*cond == 0) return;
+    rs_pass_body<true, false, true>(keys_in, keys_out, vals_in, vals_out, n, shift, mask, 0, 0u, nullptr, 0, nullptr, digit_base_g,
+                                    status, ticket, ntiles);
+}
+
 // The hybrid sort's fallback: ALL passes of a full sort in ONE cooperative launch (a fixed grid of co-resident CTAs
 // works through every pass's tiles by ticket, grid-wide barrier between passes). Launched behind every fix-up and
 // idle - one launch that returns at once - unless the fix-up met a run it does not handle (*cond != 0). Before: eight
@@ -586,6 +597,7 @@ static void opt_in_shared_memory() {
     cudaFuncSetAttribute(rs_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
     cudaFuncSetAttribute(rs_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false));
     cudaFuncSetAttribute(rs_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
+    cudaFuncSetAttribute(rs_pass_cond, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
     cudaFuncSetAttribute(rs_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
 }
@@ -772,9 +784,27 @@ int radix_sort(uint64_t* keys[2], uint32_t* vals[2], uint32_t n, const RadixPass
         const uint32_t* cond = d_fix;
         uint32_t ntiles = tiles;
         void* args[] = {&k0, &k1, &v0, &v1, &n, &all, &bases, &status_all, &tickets, &cond, &ntiles};
-        cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rs_fallback_kernel), dim3(resident[dev]), dim3(RS_THREADS), args,
-                                    rs_smem_bytes(true), s);
+        static int coop = -1;  // B200CD_COOP=0: never use the cooperative launch (tests of the path below; read once)
+        if (coop < 0) {
+            const char* ev = getenv("B200CD_COOP");
+            coop = (ev && ev[0] == '0') ? 0 : 1;
+        }
+        const cudaError_t e = !coop ? cudaErrorCooperativeLaunchTooLarge
+                                    : cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rs_fallback_kernel), dim3(resident[dev]),
+                                                                  dim3(RS_THREADS), args, rs_smem_bytes(true), s);
         count_launch();
+        if (e != cudaSuccess) {  // refused: the same passes as eight conditional launches (the result must never depend on it)
+            cudaGetLastError();
+            int c = cur;
+            for (int p = 0; p < npass; ++p) {
+                rs_pass_cond<<<2 * sms, RS_THREADS, rs_smem_bytes(true), s>>>(keys[c], keys[c ^ 1], vals[c], vals[c ^ 1], n, all.shift[p],
+                                                                               all.mask[p], d_hist + p * RS_RADIX,
+                                                                               d_tile_status + (size_t)p * tiles * RS_RADIX, d_ticket + p,
+                                                                               d_fix, tiles);
+                count_launch();
+                c ^= 1;
+            }
+        }
     }
     trace_mark("rs_fallback (idle unless a run was too long)", s);
     return cur;

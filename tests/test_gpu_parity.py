@@ -429,3 +429,39 @@ def test_unique_triangle_set_on_device(cd, co, ctx, mg):
     assert rc == cd.E_CAPACITY and cnt.value == len(want) and not small.any()
     bvh.destroy()
     mesh.destroy()
+
+
+def test_sort_fallback_without_cooperative_launch(tmp_path):
+    """the hybrid sort's fallback (runs of equal high bits longer than the fix-up handles) is normally ONE cooperative
+    launch; where that launch is refused the same passes run as eight conditional launches - forced here with
+    B200CD_COOP=0 in a fresh process (the knob is read once): keys, tie order and pairs must equal the oracle's"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import importlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+cd = importlib.import_module("gpu-computing-course_b200.binding")
+mg = importlib.import_module("gpu-computing-course_b200.meshgen")
+from oracle import cdoracle as co
+bx, bi = mg.soup(300, seed=11)
+xyz = np.tile(bx, (64, 1))                      # 64 copies of every triangle: runs of 64 equal keys
+idx = (np.tile(bi, (64, 1)) + (np.arange(64, dtype=np.uint32).repeat(len(bi)) * np.uint32(len(bx)))[:, None]).astype(np.uint32)
+ctx = cd.Context(0)
+mesh = ctx.mesh_from_arrays(xyz, idx)
+p = cd.make_params((0, 0, 0), (1, 1, 1))
+bvh = ctx.bvh_build(mesh, p)
+for _ in range(2):
+    ctx.bvh_rebuild(bvh, mesh, p)
+_, sk, si = bvh.download(nodes=False)
+op = co.make_params((0, 0, 0), (1, 1, 1))
+rk, ri = co.sort_keys(co.morton_keys(xyz, idx, op))
+assert np.array_equal(sk, rk) and np.array_equal(si, ri), "sorted keys / tie order"
+ref, _ = co.run(xyz, idx, op)
+assert np.array_equal(ctx.self_collide(bvh, sorted=True), ref), "pairs"
+print("ok", len(ref))
+""" % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, B200CD_COOP="0"))
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok"), out.stderr[-2000:]
