@@ -302,7 +302,7 @@ struct DistPlan {
     uint32_t totals[RS_MAX_SPLIT_P1];                    // triangles each rank owns
     uint32_t counts[RS_MAX_SPLIT_P1][RS_MAX_SPLIT_P1];   // [source rank][owner rank]
 };
-// d_hists: [world][65536]; d_ghist: 65536 words; d_part: world * DIST_HIST_BLOCKS words (scratch)
+// d_hists: [world][65536]; d_ghist: 65536 words; d_part: scratch of RS_MAX_SPLIT_P1 * DIST_HIST_BLOCKS + 1024 words
 void launch_dist_plan(const uint32_t* d_hists, int world, int rank, int shift, uint32_t* d_ghist, uint32_t* d_part,
                       DistPlan* d_plan, cudaStream_t s);
 // d_scratch: K*6 + 1 words

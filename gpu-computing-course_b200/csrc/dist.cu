@@ -366,7 +366,7 @@ API int b200cd_dist_create(b200cd_ctx* ctx, uint32_t rank, uint32_t world, uint3
         A(cudaMalloc(reinterpret_cast<void**>(&d->d_keys_slice), sizeof(uint64_t) * std::max<uint32_t>(d->cnt, 1u)));
         A(cudaMalloc(reinterpret_cast<void**>(&d->d_lhist), sizeof(uint32_t) * 65536));
         A(cudaMalloc(reinterpret_cast<void**>(&d->d_ghist), sizeof(uint32_t) * 65536));
-        A(cudaMalloc(reinterpret_cast<void**>(&d->d_part), sizeof(uint32_t) * DIST_MAX * DIST_HIST_BLOCKS));
+        A(cudaMalloc(reinterpret_cast<void**>(&d->d_part), sizeof(uint32_t) * (DIST_MAX * DIST_HIST_BLOCKS + 1024)));
         A(cudaMalloc(reinterpret_cast<void**>(&d->d_plan), sizeof(DistPlan)));
         A(cudaMalloc(reinterpret_cast<void**>(&d->d_boxes), sizeof(float) * DIST_K * 6));
         A(cudaMallocHost(reinterpret_cast<void**>(&d->h_res), sizeof(HostResult)));

@@ -471,8 +471,9 @@ partition_plan_kernel(const uint32_t* __restrict__ ghist, const uint32_t* __rest
 // Stage 1 (64 blocks x 1024 bins): global histogram = sum over the ranks, plus per-rank sums of each 1024-bin block.
 __global__ void __launch_bounds__(DIST_HIST_BLOCK_BINS)
 dist_hist_reduce_kernel(const uint32_t* hists /* [world][65536], written by the peers */, int world, uint32_t* __restrict__ ghist,
-                        uint32_t* __restrict__ part /* [world][DIST_HIST_BLOCKS] */) {
+                        uint32_t* __restrict__ part /* [world][DIST_HIST_BLOCKS] */, uint32_t* __restrict__ seg /* [1024]: sums of 64 bins */) {
     __shared__ uint32_t s_part[RS_MAX_SPLIT_P1];
+    __shared__ uint32_t s_warp[DIST_HIST_BLOCK_BINS / 32];
     if (threadIdx.x < RS_MAX_SPLIT_P1) s_part[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t bin = blockIdx.x * DIST_HIST_BLOCK_BINS + threadIdx.x;
@@ -484,7 +485,13 @@ dist_hist_reduce_kernel(const uint32_t* hists /* [world][65536], written by the 
         if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_part[src], w);
     }
     ghist[bin] = sum;
+    // the plan kernel (ONE block) wants the sums of the 1024 segments of 64 bins: two warps each, computed here by 64 blocks
+    // instead of one block reading all 65536 bins again (37 us of every step's critical path)
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, sum);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = wsum;
     __syncthreads();
+    if (threadIdx.x < DIST_HIST_BLOCK_BINS / PP_PER)
+        seg[blockIdx.x * (DIST_HIST_BLOCK_BINS / PP_PER) + threadIdx.x] = s_warp[2 * threadIdx.x] + s_warp[2 * threadIdx.x + 1];
     if (threadIdx.x < (uint32_t)world) part[threadIdx.x * DIST_HIST_BLOCKS + blockIdx.x] = s_part[threadIdx.x];
 }
 
@@ -493,15 +500,13 @@ dist_hist_reduce_kernel(const uint32_t* hists /* [world][65536], written by the 
 // the remainder from the source's histogram, one warp per task - and from those the count matrix, where my segment
 // starts in every owner's receive buffer and how many triangles each rank owns.
 __global__ void __launch_bounds__(PP_THREADS)
-dist_plan_kernel(const uint32_t* __restrict__ ghist, const uint32_t* hists, const uint32_t* __restrict__ part, int shift,
-                 int world, int rank, DistPlan* __restrict__ out) {
+dist_plan_kernel(const uint32_t* __restrict__ ghist, const uint32_t* hists, const uint32_t* __restrict__ part,
+                 const uint32_t* __restrict__ seg, int shift, int world, int rank, DistPlan* __restrict__ out) {
     __shared__ uint64_t s_w[PP_THREADS / 32];
-    __shared__ uint32_t s_seg[PP_THREADS];
     __shared__ uint32_t s_bin[RS_MAX_SPLIT_P1];
     __shared__ uint32_t s_cum[RS_MAX_SPLIT_P1][RS_MAX_SPLIT_P1];  // [src][j]: src's keys in the bins [0, s_bin[j]]; j = world-1: all
     const uint32_t tid = threadIdx.x, b0 = tid * PP_PER;
-    pp_segment_sums(ghist, s_seg);
-    const uint64_t sum = s_seg[tid];
+    const uint64_t sum = seg[tid];  // bins [b0, b0 + 64), summed by dist_hist_reduce_kernel
     uint64_t total;
     const uint64_t excl = pp_block_exclusive(sum, s_w, total);
     for (int r = 1; r < world; ++r) {
@@ -579,8 +584,10 @@ void launch_partition_plan(const uint32_t* d_ghist, const uint32_t* d_lhist, int
 
 void launch_dist_plan(const uint32_t* d_hists, int world, int rank, int shift, uint32_t* d_ghist, uint32_t* d_part,
                       DistPlan* d_plan, cudaStream_t s) {
-    dist_hist_reduce_kernel<<<DIST_HIST_BLOCKS, DIST_HIST_BLOCK_BINS, 0, s>>>(d_hists, world, d_ghist, d_part);
-    dist_plan_kernel<<<1, PP_THREADS, 0, s>>>(d_ghist, d_hists, d_part, shift, world, rank, d_plan);
+    static_assert(DIST_HIST_BLOCK_BINS / PP_PER * DIST_HIST_BLOCKS == PP_THREADS && PP_PER == 64, "one segment per plan thread, two warps each");
+    uint32_t* d_seg = d_part + RS_MAX_SPLIT_P1 * DIST_HIST_BLOCKS;  // behind the per-rank block sums
+    dist_hist_reduce_kernel<<<DIST_HIST_BLOCKS, DIST_HIST_BLOCK_BINS, 0, s>>>(d_hists, world, d_ghist, d_part, d_seg);
+    dist_plan_kernel<<<1, PP_THREADS, 0, s>>>(d_ghist, d_hists, d_part, d_seg, shift, world, rank, d_plan);
     count_launch(2);
     trace_mark("dist_hist_reduce+dist_plan", s);
 }
