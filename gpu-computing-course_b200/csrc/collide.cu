@@ -397,6 +397,12 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
 }
 
 // ---------------------------------------------------------------- K5b (variant 1): one query per thread
+// STACKLESS (variant 3, B200CD_TRAVERSAL=3; north_star: "a stackless or shared-memory-stack BVH traversal"): no stack at
+// all. The node numbering makes the escape pointer implicit: a subtree that ends at leaf L is followed, in depth-first
+// order, by the RIGHT child of split node L (leaves L+1 ...), so "pop" becomes "visit node L again, right child only" -
+// one more fetch of a 64-byte line the walk has already been through (it is an ancestor), no per-thread memory, two
+// registers of state. Measured against the stack versions in DESIGN.md section 4.
+template <bool STACKLESS>
 __global__ void __launch_bounds__(BR_THREADS)
 broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, const float* __restrict__ root_box,
              uint32_t n, uint32_t shard, uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base,
@@ -508,6 +514,51 @@ broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restric
         }
     };
 
+  if (STACKLESS) {
+    int node = -1;            // split node to visit next (-1: take the next start subtree)
+    bool ronly = false;       // visit only its right child: the walk comes back from the left one ("pop")
+    int limit = -1;           // last leaf of the start subtree being walked: escapes beyond it end the subtree
+    uint32_t ecur = 0;        // this lane's cursor over the kept start subtrees
+    nkeep_sum += nkeep;
+    const bool valid = q != 0xffffffffu;
+    while (__any_sync(0xffffffffu, node >= 0 || (valid && ecur < nkeep))) {
+        bool candL = false, candR = false;
+        int leafL = 0, leafR = 0;
+        ++iters;
+        if (node >= 0) {
+            ++visits;
+            Child l, r;
+            load_children(pairs, node, l, r);
+            const int linkL = l.link(), linkR = r.link();
+            const bool hitL = !ronly && node > qcmp && overlap(qlo, qhi, l.a.x, l.a.y, l.a.z, l.a.w, l.b.x, l.b.y);
+            candL = hitL && linkL < 0; leafL = ~linkL;
+            if (hitL && linkL >= 0) {          // descend left; the right child is met again on the way back (node, ronly)
+                node = linkL;
+                ronly = false;
+            } else {
+                const bool hitR = r.ext() > qcmp && overlap(qlo, qhi, r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y);
+                candR = hitR && linkR < 0; leafR = ~linkR;
+                if (hitR && linkR >= 0) {
+                    node = linkR;
+                    ronly = false;
+                } else {                       // this subtree is done: it ends at leaf r.ext, go on behind it
+                    const int L = r.ext();
+                    ronly = true;
+                    node = L < limit ? L : -1;
+                }
+            }
+        } else if (valid) {                    // next start subtree that ends after q and overlaps q's box
+            while (ecur < nkeep) {
+                const Child c = s_entry[ecur++];
+                if (!(c.ext() > qcmp && overlap(qlo, qhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y))) continue;
+                if (c.link() >= 0) { node = c.link(); ronly = false; limit = c.ext(); }
+                else { candL = true; leafL = ~c.link(); }  // a start subtree that is a single leaf
+                break;
+            }
+        }
+        stage2(candL, leafL, candR, leafR);
+    }
+  } else {
     // start points: every kept entry that ends after q and overlaps q's box (warp-uniform loop)
     for (uint32_t e = 0; e < nkeep; ++e) {
         const Child c = s_entry[e];
@@ -550,6 +601,7 @@ broad_kernel_simple(const NodePair* __restrict__ pairs, const LeafRec* __restric
         }
         stage2(candL, leafL, candR, leafR);
     }
+  }
     if (staged) flush();
     __syncthreads();  // s_entry / s_nentry are rewritten by the next iteration
   }
@@ -739,12 +791,13 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
 
 }  // namespace
 
-// B200CD_TRAVERSAL=1: one query per thread; 2: persistent lanes (tuning knob, read once)
+// B200CD_TRAVERSAL=1: one query per thread, per-thread stack; 3: one query per thread, STACKLESS; 2 (default): persistent
+// lanes with a per-thread stack (tuning knob, read once)
 static int traversal_variant() {
     static int v = 0;
     if (!v) {
         const char* e = getenv("B200CD_TRAVERSAL");
-        v = (e && e[0] == '1') ? 1 : 2;
+        v = (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2;
     }
     return v;
 }
@@ -756,7 +809,7 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
     if (nquery == 0 || n == 0 || (!foreign && n < 2)) return;
     if (foreign && d_nquery) {  // ghost queries whose count only the device knows: a fixed grid strides over the blocks
         const uint32_t blocks = std::min<uint32_t>((nquery + BR_THREADS - 1) / BR_THREADS, (uint32_t)std::max(sms, 1) * 8u);
-        broad_kernel_simple<<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, 0, 1, BR_THREADS, nquery, 1, ghost_base,
+        broad_kernel_simple<false><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, 0, 1, BR_THREADS, nquery, 1, ghost_base,
                                                           d_entries, d_entry_count, d_cand, cand_cap, d_counters, d_nquery);
         count_launch();
         trace_mark("broad_kernel_simple (ghost queries)", s);
@@ -803,9 +856,14 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
             broad_kernel<6, false><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
                                                                  d_entries, d_entry_count, d_cand, cand_cap, d_counters);
     } else {
-        broad_kernel_simple<<<groups, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery,
-                                                          foreign, ghost_base, d_entries, d_entry_count, d_cand, cand_cap,
-                                                          d_counters, nullptr);
+        if (traversal_variant() == 3 && !foreign)
+            broad_kernel_simple<true><<<groups, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery,
+                                                                    foreign, ghost_base, d_entries, d_entry_count, d_cand, cand_cap,
+                                                                    d_counters, nullptr);
+        else
+            broad_kernel_simple<false><<<groups, BR_THREADS, 0, s>>>(d_pairs, d_leaves, d_root_box, n, shard, nshards, chunk, nquery,
+                                                                     foreign, ghost_base, d_entries, d_entry_count, d_cand, cand_cap,
+                                                                     d_counters, nullptr);
     }
     count_launch();
     trace_mark("broad_kernel", s);

@@ -465,3 +465,35 @@ print("ok", len(ref))
 """ % root
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, B200CD_COOP="0"))
     assert out.returncode == 0 and out.stdout.strip().startswith("ok"), out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("variant", ["1", "3"])
+def test_traversal_variants_give_the_same_pairs(variant):
+    """B200CD_TRAVERSAL=1 (one query per thread, per-thread stack) and =3 (one query per thread, STACKLESS: the escape
+    pointer is implicit in the node numbering) against the oracle, in a fresh process (the knob is read once); the
+    default (=2, persistent lanes) is what every other test runs"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import importlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+cd = importlib.import_module("gpu-computing-course_b200.binding")
+mg = importlib.import_module("gpu-computing-course_b200.meshgen")
+from oracle import cdoracle as co
+ctx = cd.Context(0)
+for (xyz, idx), box in ((mg.soup(60000, seed=2), ((0, 0, 0), (1, 1, 1))), (mg.cloth_fold(90, 90), None), (mg.two_sheets(64), ((0, 0, 0), (1, 1, 1))),
+                        (mg.soup(3, h=0.4, seed=1), ((0, 0, 0), (1, 1, 1)))):
+    p = cd.make_params(*box) if box else cd.default_params()
+    op = co.make_params(*box) if box else co.default_params()
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, p)
+    ref, _ = co.run(xyz, idx, op)
+    assert np.array_equal(ctx.self_collide(bvh, sorted=True), ref), len(idx)
+    bvh.destroy(); mesh.destroy()
+print("ok")
+""" % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, B200CD_TRAVERSAL=variant))
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
