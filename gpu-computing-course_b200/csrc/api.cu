@@ -127,6 +127,8 @@ void free_bvh_buffers(b200cd_bvh* b) {
     cudaFree(b->d_flags);
     cudaFree(b->d_build_scratch);
     cudaFree(b->d_pairs);
+    cudaFree(b->d_qpairs);
+    cudaFree(b->d_qframe);
     cudaFree(b->d_leaves);
     cudaFree(b->d_recs);
     cudaFree(b->d_block_boxes);
@@ -186,6 +188,7 @@ int alloc_bvh(b200cd_ctx* ctx, uint32_t n, uint32_t nverts, bool with_sort, b200
             if (cudaEventCreate(&b->ev_sort[i]) != cudaSuccess) rc = set_error(ctx, B200CD_E_NOMEM, "cudaEventCreate failed");
     }
     A(dev_alloc(ctx, &b->d_pairs, n));
+    A(dev_alloc(ctx, &b->d_qframe, 8));  // (d_qpairs: on the first build that wants them, run_build)
     A(dev_alloc(ctx, &b->d_leaves, (uint64_t)n + ghost_cap));  // ghost records of a partitioned build live after the local leaves
     if (max_peers) {
         b->ghost_out_cap = ghost_cap;
@@ -255,8 +258,16 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     const uint32_t n = b->n;
     if (m->pending) return set_error(ctx, B200CD_E_INVALID, "mesh has an asynchronous upload in flight: call b200cd_mesh_wait first");
     b->params = *p;
+    const QFrame qframe = make_qframe(*p);  // the traversal's 15-bit grid lies over the Morton box
     b->built = false;
     b->unshared_verts = 2ull * m->nverts >= 3ull * m->ntris;
+    b->qvalid = broad_uses_quantised_nodes(!b->unshared_verts);
+    if (b->qvalid && !b->d_qpairs && b->cap > 1 &&  // (sized like d_pairs: a partitioned build's n changes from step to step)
+        cudaMalloc(reinterpret_cast<void**>(&b->d_qpairs), sizeof(QNodePair) * (size_t)b->cap) != cudaSuccess) {
+        cudaGetLastError();  // no room for the second node array: walk the exact nodes, not an error
+        b->d_qpairs = nullptr;
+    }
+    if (!b->d_qpairs) b->qvalid = false;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B0], s));
     trace_mark("build_begin", s);
     int npass = 0;
@@ -368,7 +379,8 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));  // (K3 is fused into K4: ms_hierarchy stays ~0)
     launch_build_tree(m->d_verts, m->d_idx, b->d_ids[b->cur], b->d_keys[b->cur], n, b->d_flags, b->d_pairs, b->d_leaves,
-                      b->d_root_box, b->d_build_scratch, s, keys_given ? nullptr : b->d_recs, b->d_block_boxes);  // K3+K4
+                      b->d_root_box, b->d_build_scratch, s, keys_given ? nullptr : b->d_recs, b->d_block_boxes,
+                      b->qvalid ? b->d_qpairs : nullptr, b->d_qframe, &qframe);  // K3+K4
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, mark_consumed(m, s));  // nothing after this point reads the mesh
     CD_CUDA(ctx, cudaGetLastError());
@@ -848,9 +860,11 @@ API int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* me
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B1], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B2], s));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));
+    const QFrame qframe = make_qframe(bvh->params);
     // the sorted keys are kept, so the same climb reproduces the same topology around the new boxes
     launch_build_tree(mesh->d_verts, mesh->d_idx, bvh->d_ids[bvh->cur], bvh->d_keys[bvh->cur], bvh->n, bvh->d_flags,
-                      bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, bvh->d_build_scratch, s, nullptr, bvh->d_block_boxes);
+                      bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, bvh->d_build_scratch, s, nullptr, bvh->d_block_boxes,
+                      bvh->qvalid ? bvh->d_qpairs : nullptr, bvh->d_qframe, &qframe);
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, mark_consumed(mesh, s));
     CD_CUDA(ctx, cudaGetLastError());
@@ -1395,7 +1409,8 @@ int run_query(b200cd_ctx* ctx, b200cd_bvh* b, uint32_t shard, uint32_t nshards, 
         if (need_broad) {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), s));
             launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, n, shard, nshards, chunk, nquery, /*foreign*/ 0, 0u, b->d_entries,
-                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s, nullptr, ctx->sm_count, !b->unshared_verts);
+                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s, nullptr, ctx->sm_count, !b->unshared_verts,
+                         b->qvalid ? b->d_qpairs : nullptr, b->d_qframe);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
         } else {
             CD_CUDA(ctx, cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), s));

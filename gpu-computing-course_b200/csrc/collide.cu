@@ -396,6 +396,272 @@ broad_kernel(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ lea
     }
 }
 
+// ---------------------------------------------------------------- K5b (variant 2q): persistent lanes on quantised nodes
+#ifndef BR_STEPS
+#define BR_STEPS 2  // walk steps per refill check
+#endif
+// QUANT: the walk reads the 32-byte quantised nodes (common.cuh QNodePair) - one sector and one LDG.256 per visit instead
+// of two, three packed query words per lane instead of six floats, seven integer instructions per child box instead of
+// six float compares - and emits a SUPERSET of the exact candidates (15-bit cells are conservative); the narrow phase
+// drops the extras with the exact box test before anything else. The start subtrees are still tested exactly.
+template <int MIN_BLOCKS, bool FILTER>  // MIN_BLOCKS: resident CTAs per SM the register allocation is bounded for
+__global__ void __launch_bounds__(BR_THREADS, MIN_BLOCKS)
+broad_kernel_q(const NodePair* __restrict__ pairs, const LeafRec* __restrict__ leaves, uint32_t n, uint32_t shard,
+             uint32_t nshards, uint32_t chunk, uint32_t nquery, uint32_t ngroups, int refill, const Node32* __restrict__ entries,
+             const uint32_t* __restrict__ entry_count, uint2* __restrict__ cand, uint64_t cand_cap,
+             unsigned long long* __restrict__ counters, const QNodePair* __restrict__ qpairs, const float* __restrict__ qframe) {
+    constexpr bool QUANT = true;                        // (the exact walk of this kernel is kept for A/B builds)
+    __shared__ uint2 s_cq[BR_WARPS][BR_CQ];
+    __shared__ Child s_entry[BR_WARPS][BR_KEEP];        // the warp's current group: start subtrees that overlap its union box
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint2* wq = s_cq[warp];
+    Child* we = s_entry[warp];
+    uint32_t staged = 0;  // warp-uniform: candidates waiting in wq (< 128)
+    const float inf = __int_as_float(0x7f800000);
+
+    // query slot t -> sorted leaf position
+    auto slot_position = [&](uint32_t t) -> uint32_t {
+        if (t >= nquery) return 0xffffffffu;
+        const uint64_t qq = query_position(t, shard, nshards, chunk);
+        return qq + 1 < n ? (uint32_t)qq : 0xffffffffu;  // the last leaf has no partner with a larger position
+    };
+
+    // Per-thread stack with a sentinel: entries live in stack[1 .. MAX], stack[0] = -1 is what an empty stack pops ("no
+    // node"), sp = index of the top entry, stack[MAX + 1] is written by an overflowing push only (links are >= 0, so the
+    // -1 put there now tells at the end whether one happened) - push and pop are straight-line code, no "is it empty /
+    // is it full" branch and no flag register in the walk.
+    int stack[B200CD_MAX_STACK + 2];
+    int sp = 0;
+    stack[0] = -1;
+    stack[B200CD_MAX_STACK + 1] = -1;
+    auto push = [&](int link) {
+        sp = min(sp + 1, B200CD_MAX_STACK + 1);
+        stack[sp] = link;
+    };
+    auto pop = [&]() -> int {
+        const int v = stack[sp];
+        sp = max(sp - 1, 0);
+        return v;
+    };
+
+    // drop the staged candidates whose triangles share a vertex index (compaction in place, warp-wide)
+    auto filter = [&]() {
+        uint32_t kept = 0;
+        for (uint32_t i0 = 0; i0 < staged; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            bool keep = false;
+            uint2 c = make_uint2(0, 0);
+            if (i < staged) {
+                c = wq[i];
+                // second half of a leaf record: v2.z, vi[0], vi[1], vi[2] (16 bytes at offset 32)
+                const float4 a = __ldg(reinterpret_cast<const float4*>(leaves + c.x) + 2);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(leaves + c.y) + 2);
+                const uint32_t a0 = __float_as_uint(a.y), a1 = __float_as_uint(a.z), a2 = __float_as_uint(a.w);
+                const uint32_t b0 = __float_as_uint(b.y), b1 = __float_as_uint(b.z), b2 = __float_as_uint(b.w);
+                keep = !(a0 == b0 || a0 == b1 || a0 == b2 || a1 == b0 || a1 == b1 || a1 == b2 || a2 == b0 || a2 == b1 || a2 == b2);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);  // (every lane has read its slot: slots below are free to overwrite)
+            if (keep) wq[kept + __popc(m & lt)] = c;
+            kept += __popc(m);
+            __syncwarp();
+        }
+        staged = kept;
+    };
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counters + 0, (unsigned long long)staged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < staged; i += 32)
+            if (base + i < cand_cap) __stcs(cand + base + i, wq[i]);
+        staged = 0;
+        __syncwarp();
+    };
+    // stage (q, leaf) candidates of the whole warp: positions by ballot, no atomics
+    auto stage2 = [&](uint32_t q, bool candL, int leafL, bool candR, int leafR) {
+        const uint32_t bL = __ballot_sync(0xffffffffu, candL), bR = __ballot_sync(0xffffffffu, candR);
+        if (bL | bR) {
+            const uint32_t nL = __popc(bL);
+            if (candL) wq[staged + __popc(bL & lt)] = make_uint2(q, (uint32_t)leafL);
+            if (candR) wq[staged + nL + __popc(bR & lt)] = make_uint2(q, (uint32_t)leafR);
+            staged += nL + __popc(bR);
+            __syncwarp();
+            if (staged >= BR_FLUSH) {
+                if (FILTER) {
+                    filter();
+                    if (staged >= 32) flush();  // the few survivors wait for company (< 32 carried + <= 64 new < BR_CQ)
+                } else {
+                    flush();
+                }
+            }
+        }
+    };
+
+    // ---- the warp's groups: first, first + stride, ... A warp never drains between two of them: lanes that are still
+    // walking queries of one group keep going (they only need their own stack) while the idle lanes start on the next.
+    // cur = (current group << 8) | queries of it already handed out; "before the first group" = first - stride, all 128 out.
+    int cur = (int)(((int)(blockIdx.x * BR_WARPS + warp) - (int)(gridDim.x * BR_WARPS)) * 256 + BR_PER_WARP);
+    // nk = start subtrees of the current group to scan (bits 0-6), bit 7: more than BR_KEEP of them overlap the union box -
+    // scan the global list; bits 8-31: walk steps of this warp since the group was opened (b200cd_stats::warp_steps).
+    // visits = lane-steps with a node (b200cd_stats::nodes_visited): both warp-uniform, both flushed per group.
+    uint32_t nk = 0, visits = 0;
+    // warp-wide: keep the entries of group g that overlap the group's union box, in list order
+    auto open_group = [&](uint32_t g) {
+        __syncwarp();                                    // the previous group's entries have been read by every lane
+        const uint32_t cnt = __ldg(entry_count + g);
+        float4 u0, u1;
+        ld256_nc(reinterpret_cast<const float4*>(entry_count + ((ngroups + 7u) & ~7u)) + 2 * (size_t)g, u0, u1);
+        const float ulo[3] = {u0.x, u0.y, u0.z}, uhi[3] = {u0.w, u1.x, u1.y};
+        uint32_t kept = 0;
+#pragma unroll 1
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            bool keep = false;
+            Child c;
+            if (e < cnt) {
+                ld256_nc(entries + (size_t)g * BR_ENTRIES + e, c.a, c.b);
+                keep = overlap(ulo, uhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            const uint32_t at = kept + __popc(m & lt);
+            if (keep && at < (uint32_t)BR_KEEP) we[at] = c;
+            kept += __popc(m);
+        }
+        const uint32_t nkeep = kept > (uint32_t)BR_KEEP ? (cnt | 0x80u) : kept;  // cnt <= BR_ENTRIES = 64
+        if (lane == 0) {
+            atomicAdd(counters + 3, (unsigned long long)visits);
+            atomicAdd(counters + 4, (unsigned long long)(nk >> 8));
+            atomicAdd(counters + 5, (unsigned long long)(nkeep & 0x7fu));  // b200cd_stats::start_entries
+        }
+        visits = 0;
+        nk = nkeep;
+        __syncwarp();
+        // the first refill's records
+        const uint32_t t0 = g * BR_PER_WARP + lane;
+        const uint32_t p0 = slot_position(t0);
+        if (p0 != 0xffffffffu) asm volatile("prefetch.global.L2 [%0];" ::"l"(leaves + p0));
+    };
+
+    int q = 0x7fffffff;                                  // this lane's query position ("none": nothing ends after it)
+    float qlo[3] = {inf, inf, inf}, qhi[3] = {-inf, -inf, -inf};  // the query box (!QUANT)
+    uint32_t qx = 0, qy = 0, qz = 0;                     // QUANT: the query box as packed grid words (common.cuh)
+    int node = -1;
+
+    while (true) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, node < 0);
+        if (__popc(idle) >= refill || idle == 0xffffffffu) {
+            int grp = cur >> 8;
+            uint32_t rel = (uint32_t)cur & 255u;
+            uint32_t wrel = grp >= 0 ? min((uint32_t)BR_PER_WARP, nquery - (uint32_t)grp * BR_PER_WARP) : 0u;  // queries in the group
+            if (rel >= wrel) {                            // this group is handed out: on to the warp's next one
+                const uint32_t g2 = (uint32_t)(grp + (int)(gridDim.x * BR_WARPS));
+                if (g2 < ngroups) {
+                    open_group(g2);
+                    grp = (int)g2;
+                    rel = 0;
+                    wrel = min((uint32_t)BR_PER_WARP, nquery - g2 * BR_PER_WARP);
+                }
+            }
+            if (rel < wrel) {
+            // ---- refill: idle lanes take the group's next queries and collect their start subtrees
+            const uint32_t mine = rel + __popc(idle & lt);
+            bool take = node < 0 && mine < wrel;
+            rel = min(wrel, rel + (uint32_t)__popc(idle));
+            cur = grp * 256 + (int)rel;
+            float blo[3] = {0.f, 0.f, 0.f}, bhi[3] = {0.f, 0.f, 0.f};  // the exact box of the query taken in THIS refill
+            if (take) {
+                const uint32_t p = slot_position((uint32_t)grp * BR_PER_WARP + mine);
+                take = p != 0xffffffffu;
+                if (take) {
+                    float4 r0, r1, r2, r3;
+                    ld256_nc(leaves + p, r0, r1);
+                    ld256_nc(reinterpret_cast<const float4*>(leaves + p) + 2, r2, r3);
+                    // v0 = r0.xyz, v1 = (r0.w, r1.x, r1.y), v2 = (r1.z, r1.w, r2.x); box.cuh:13-22
+                    blo[0] = min3_ref(r0.x, r0.w, r1.z); bhi[0] = max3_ref(r0.x, r0.w, r1.z);
+                    blo[1] = min3_ref(r0.y, r1.x, r1.w); bhi[1] = max3_ref(r0.y, r1.x, r1.w);
+                    blo[2] = min3_ref(r0.z, r1.y, r2.x); bhi[2] = max3_ref(r0.z, r1.y, r2.x);
+                    q = (int)p;
+                    if (QUANT) {
+                        qx = qquery_word(blo[0], bhi[0], __ldg(qframe + 0), __ldg(qframe + 3));
+                        qy = qquery_word(blo[1], bhi[1], __ldg(qframe + 1), __ldg(qframe + 4));
+                        qz = qquery_word(blo[2], bhi[2], __ldg(qframe + 2), __ldg(qframe + 5));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { qlo[k] = blo[k]; qhi[k] = bhi[k]; }
+                    }
+                }
+            }
+            if (rel + lane < wrel) {   // records of the NEXT refill (it takes at most 32 slots starting at rel)
+                const uint32_t pn = slot_position((uint32_t)grp * BR_PER_WARP + rel + lane);
+                if (pn != 0xffffffffu) asm volatile("prefetch.global.L2 [%0];" ::"l"(leaves + pn));
+            }
+            const uint32_t nscan = nk & 0x7fu;
+#pragma unroll 1
+            for (uint32_t e = 0; e < nscan; ++e) {
+                Child c;
+                if (!(nk & 0x80u)) c = we[e];
+                else ld256_nc(entries + (size_t)grp * BR_ENTRIES + e, c.a, c.b);
+                const bool hit = take && c.ext() > q && overlap(blo, bhi, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y);
+                const int link = c.link();  // the same entry for every lane: the branch below is warp-uniform
+                if (link >= 0) {
+                    if (hit) push(link);
+                } else {
+                    stage2((uint32_t)q, hit, ~link, false, 0);  // a start subtree that is a single leaf (rare)
+                }
+            }
+            if (take) node = pop();
+            continue;
+            }
+            if (idle == 0xffffffffu) break;  // nothing left to take, nobody working
+        }
+#pragma unroll
+        for (int rep = 0; rep < BR_STEPS; ++rep) {  // walk steps per refill check
+            nk += 256u;
+            visits += BR_STEPS == 1 ? 32u - (uint32_t)__popc(idle) : (uint32_t)__popc(__ballot_sync(0xffffffffu, node >= 0));
+            bool candL = false, candR = false;
+            int leafL = 0, leafR = 0;
+            if (node >= 0) {
+                int linkL, linkR;
+                bool hitL, hitR;
+                // left child = leaves [.., node], right child = leaves [node+1, last leaf of this node]: skip what ends at
+                // or before q. Every visited subtree ends after q (start subtrees: checked in the scan; a right child ends
+                // where its parent does; a left child is entered only if node > q), so the right child needs no test.
+                if (QUANT) {
+                    float4 a, b;
+                    ld256_nc(qpairs + node, a, b);
+                    linkL = __float_as_int(a.w);
+                    linkR = __float_as_int(b.w);
+                    hitL = node > q && qoverlap(qx, qy, qz, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z));
+                    hitR = qoverlap(qx, qy, qz, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z));
+                } else {
+                    Child l, r;
+                    load_children(pairs, node, l, r);
+                    linkL = l.link();
+                    linkR = r.link();
+                    hitL = node > q && overlap(qlo, qhi, l.a.x, l.a.y, l.a.z, l.a.w, l.b.x, l.b.y);
+                    hitR = r.ext() > q && overlap(qlo, qhi, r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y);
+                }
+                candL = hitL && linkL < 0; leafL = ~linkL;
+                candR = hitR && linkR < 0; leafR = ~linkR;
+                const bool goL = hitL && linkL >= 0, goR = hitR && linkR >= 0;
+                // straight-line (predicated) successor selection: descend left first, park the right child, pop when neither
+                int nxt = goL ? linkL : linkR;
+                if (goL && goR) push(linkR);
+                if (!(goL || goR)) nxt = pop();
+                node = nxt;
+            }
+            stage2((uint32_t)q, candL, leafL, candR, leafR);
+        }
+    }
+    if (FILTER && staged) filter();
+    if (staged) flush();
+    if (stack[B200CD_MAX_STACK + 1] != -1) atomicOr(counters + 2, ERR_STACK);
+    if (lane == 0) {
+        atomicAdd(counters + 3, (unsigned long long)visits);
+        atomicAdd(counters + 4, (unsigned long long)(nk >> 8));
+    }
+}
+
 // ---------------------------------------------------------------- K5b (variant 1): one query per thread
 // STACKLESS (variant 3, B200CD_TRAVERSAL=3; north_star: "a stackless or shared-memory-stack BVH traversal"): no stack at
 // all. The node numbering makes the escape pointer implicit: a subtree that ends at leaf L is followed, in depth-first
@@ -767,6 +1033,13 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
                 float4 a0, a1, b0, b1;
                 ld256_nc(leaves + c.x, a0, a1);
                 ld256_nc(leaves + c.y, b0, b1);
+                // box.cuh:13-22 + 40-43 on the exact vertices: the quantised traversal admits a few box pairs that only
+                // touch or just miss (collision.cuh:36 tests the boxes before anything else)
+                const float alo[3] = {min3_ref(a0.x, a0.w, a1.z), min3_ref(a0.y, a1.x, a1.w), min3_ref(a0.z, a1.y, a2.x)};
+                const float ahi[3] = {max3_ref(a0.x, a0.w, a1.z), max3_ref(a0.y, a1.x, a1.w), max3_ref(a0.z, a1.y, a2.x)};
+                const bool boxes = overlap(alo, ahi, min3_ref(b0.x, b0.w, b1.z), min3_ref(b0.y, b1.x, b1.w), min3_ref(b0.z, b1.y, b2.x),
+                                           max3_ref(b0.x, b0.w, b1.z), max3_ref(b0.y, b1.x, b1.w), max3_ref(b0.z, b1.y, b2.x));
+                if (boxes) {
                 const D3 av0 = {(double)a0.x, (double)a0.y, (double)a0.z}, av1 = {(double)a0.w, (double)a1.x, (double)a1.y},
                          av2 = {(double)a1.z, (double)a1.w, (double)a2.x};
                 const D3 bv0 = {(double)b0.x, (double)b0.y, (double)b0.z}, bv1 = {(double)b0.w, (double)b1.x, (double)b1.y},
@@ -774,6 +1047,7 @@ narrow_kernel(const LeafRec* __restrict__ leaves, const uint2* __restrict__ cand
                 // tri_contact.cuh:81-86: P is the lower-ID triangle
                 if (aid < bid) { alive = sat_stage_a(sat_input(av0, av1, av2, bv0, bv1, bv2)); entry = make_uint2(c.x, c.y); }
                 else           { alive = sat_stage_a(sat_input(bv0, bv1, bv2, av0, av1, av2)); entry = make_uint2(c.y, c.x); }
+                }
             }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, alive);
@@ -802,10 +1076,24 @@ static int traversal_variant() {
     return v;
 }
 
+// Which builds write (and which traversals read) the quantised nodes: triangle soups by default - on a mesh of flat
+// sheets the fixed 15-bit grid over the Morton box is too coarse ACROSS the sheets and the extra candidates cost more than
+// the halved node fetches save (measured). B200CD_BROAD_QUANT=0 never, =1 always.
+bool broad_uses_quantised_nodes(bool shared_vertices) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("B200CD_BROAD_QUANT");
+        mode = !e ? 2 : (e[0] == '0' ? 0 : 1);
+    }
+    if (traversal_variant() != 2) return false;
+    return mode == 1 || (mode == 2 && !shared_vertices);
+}
+
 void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float* d_root_box, uint32_t n, uint32_t shard,
                   uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries,
                   uint32_t* d_entry_count, uint2* d_cand, uint64_t cand_cap, unsigned long long* d_counters,
-                  cudaStream_t s, const unsigned long long* d_nquery, int sms, bool shared_vertices) {
+                  cudaStream_t s, const unsigned long long* d_nquery, int sms, bool shared_vertices, const QNodePair* d_qpairs,
+                  const float* d_qframe) {
     if (nquery == 0 || n == 0 || (!foreign && n < 2)) return;
     if (foreign && d_nquery) {  // ghost queries whose count only the device knows: a fixed grid strides over the blocks
         const uint32_t blocks = std::min<uint32_t>((nquery + BR_THREADS - 1) / BR_THREADS, (uint32_t)std::max(sms, 1) * 8u);
@@ -843,7 +1131,22 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
             filt = (e && e[0] == '0') ? 0 : 1;
         }
         const bool filter = filt && shared_vertices;
-        if (filter && occ == 5)
+        if (d_qpairs && d_qframe) {  // the build wrote the quantised nodes (broad_uses_quantised_nodes): walk those
+            // B200CD_BROAD_GRID=persist: one resident wave of blocks, every warp works through groups w, w + all warps, ...
+            // without draining in between (lane utilisation 0.53 -> 0.61, measured SLOWER: DESIGN.md section 4)
+            static int persist = -1;
+            if (persist < 0) {
+                const char* e = getenv("B200CD_BROAD_GRID");
+                persist = (e && e[0] == 'p') ? 1 : 0;
+            }
+            const uint32_t qblocks = persist ? std::min<uint32_t>(blocks, (uint32_t)(sms > 0 ? sms : 148) * (uint32_t)occ) : blocks;
+#define B200CD_BROAD_Q(OCC, F)                                                                                                     \
+    broad_kernel_q<OCC, F><<<qblocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill, d_entries, \
+                                                          d_entry_count, d_cand, cand_cap, d_counters, d_qpairs, d_qframe)
+            if (occ == 5) { if (filter) B200CD_BROAD_Q(5, true); else B200CD_BROAD_Q(5, false); }
+            else          { if (filter) B200CD_BROAD_Q(6, true); else B200CD_BROAD_Q(6, false); }
+#undef B200CD_BROAD_Q
+        } else if (filter && occ == 5)
             broad_kernel<5, true><<<blocks, BR_THREADS, 0, s>>>(d_pairs, d_leaves, n, shard, nshards, chunk, nquery, groups, refill,
                                                                 d_entries, d_entry_count, d_cand, cand_cap, d_counters);
         else if (filter)

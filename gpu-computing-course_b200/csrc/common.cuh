@@ -49,6 +49,59 @@ struct __align__(64) LeafRec {
 };
 static_assert(sizeof(Node32) == 32 && sizeof(NodePair) == 64 && sizeof(LeafRec) == 64, "layout");
 
+// Quantised traversal node (round 2): the same two children in HALF the bytes - one 32-byte sector, one LDG.256 per
+// node visit instead of two (the traversal is bound by the L1 data pipe: 92 % of its peak wavefront rate, profiles/
+// r02_ncu_broad_l1.md). c[k] = {x, y, z, link}; an axis word holds the child's box on a 15-bit grid over the Morton box
+// (b200cd_params): lo cell in bits 0-14, (32767 - hi cell) in bits 16-30, bits 15 and 31 zero. Cells are CONSERVATIVE:
+// lo = floor(u), hi = floor(u) + 1 with u = (x - origin) * scale, clamped to [0, 32766] / [1, 32767]; rounding is
+// monotone, so a.lo < b.hi in floats implies cell_lo(a) < cell_hi(b) - a quantised test never misses an overlap, it
+// only admits a few more candidates, and the narrow phase re-tests the exact boxes (box.cuh:40-43) first.
+// With the query packed as ((hi | 0x8000) | ((32767 - lo) | 0x8000) << 16) - 0x00010001 per axis, BOTH strict
+// comparisons of an axis are the two guard bits of ONE subtraction: t = query - node, bit 15 = node.lo < query.hi,
+// bit 31 = query.lo < node.hi (neither half can borrow), and the three axes AND together.
+struct __align__(32) QNodePair {
+    uint4 c[2];
+};
+struct QFrame {
+    float o[3], s[3];  // cell = floor((x - o) * s)
+};
+constexpr uint32_t Q_CELLS = 32767u;
+constexpr uint32_t Q_GUARD = 0x80008000u;
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t qcell_lo(float x, float o, float s) {
+    const float u = floorf((x - o) * s);
+    return (uint32_t)(int)fminf(fmaxf(u, 0.f), (float)(Q_CELLS - 1u));
+}
+__device__ __forceinline__ uint32_t qcell_hi(float x, float o, float s) {
+    const float u = floorf((x - o) * s) + 1.f;
+    return (uint32_t)(int)fminf(fmaxf(u, 1.f), (float)Q_CELLS);
+}
+__device__ __forceinline__ uint32_t qnode_word(float lo, float hi, float o, float s) {
+    return qcell_lo(lo, o, s) | ((Q_CELLS - qcell_hi(hi, o, s)) << 16);
+}
+__device__ __forceinline__ uint32_t qquery_word(float lo, float hi, float o, float s) {
+    return ((qcell_hi(hi, o, s) | 0x8000u) | (((Q_CELLS - qcell_lo(lo, o, s)) | 0x8000u) << 16)) - 0x00010001u;
+}
+__device__ __forceinline__ bool qoverlap(uint32_t qx, uint32_t qy, uint32_t qz, uint32_t nx, uint32_t ny, uint32_t nz) {
+    return (((qx - nx) & (qy - ny) & (qz - nz)) & Q_GUARD) == Q_GUARD;
+}
+// a child as stored in a NodePair half (a = lo.xyz hi.x, b = hi.yz link ext) -> its quantised half
+__device__ __forceinline__ uint4 qnode_half(const float4& a, const float4& b, const QFrame& f) {
+    return make_uint4(qnode_word(a.x, a.w, f.o[0], f.s[0]), qnode_word(a.y, b.x, f.o[1], f.s[1]),
+                      qnode_word(a.z, b.y, f.o[2], f.s[2]), __float_as_uint(b.z));
+}
+#endif
+inline QFrame make_qframe(const b200cd_params& p) {
+    QFrame f;
+    for (int k = 0; k < 3; ++k) {
+        f.o[k] = (float)p.morton_origin[k];
+        const double e = p.morton_extent[k];
+        f.s[k] = (e > 0.0 && e < 1e300) ? (float)((double)Q_CELLS / e) : 0.f;
+        if (!(f.s[k] > 0.f) || !(f.s[k] < 3.0e38f) || !(f.o[k] == f.o[k])) { f.o[k] = 0.f; f.s[k] = 0.f; }  // degenerate box: one cell
+    }
+    return f;
+}
+
 // ---------------------------------------------------------------- host-side objects
 
 }  // namespace b200cd
@@ -143,6 +196,9 @@ struct b200cd_bvh {
     uint32_t* d_flags = nullptr;       // n-1 arrival counters of the splits merged through global memory
     void* d_build_scratch = nullptr;   // pending-subtree list of the tree build (lbvh.cu)
     b200cd::NodePair* d_pairs = nullptr;  // n-1
+    b200cd::QNodePair* d_qpairs = nullptr;  // n-1: the same nodes on the 15-bit grid (what the traversal reads)
+    float* d_qframe = nullptr;         // 8 floats: QFrame of d_qpairs
+    bool qvalid = false;               // the last build wrote d_qpairs (soups; B200CD_BROAD_QUANT): the traversal walks them
     b200cd::LeafRec* d_leaves = nullptr;  // n
     b200cd::LeafRec* d_recs = nullptr;    // n, face order: written by K1, moved into sorted order by the tree build (full builds only)
     float* d_root_box = nullptr;       // 6 floats + [6] = index of the root node (int)
@@ -283,7 +339,8 @@ uint64_t build_tree_scratch_bytes(uint32_t n);
 // (one 64-byte gather per leaf) instead of being assembled from d_idx / d_verts
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
-                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs = nullptr, float* d_block_boxes = nullptr);
+                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs = nullptr, float* d_block_boxes = nullptr,
+                       QNodePair* d_qpairs = nullptr, float* d_qframe = nullptr, const QFrame* frame = nullptr);
 // d_scratch: 2 * (2n-1) words
 void launch_export_nodes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t* d_scratch,
                          b200cd_node32* d_nodes_out, cudaStream_t s);
@@ -332,7 +389,9 @@ void launch_broad(const NodePair* d_pairs, const LeafRec* d_leaves, const float*
                   uint32_t nshards, uint32_t chunk, uint32_t nquery, int foreign, uint32_t ghost_base, Node32* d_entries, uint32_t* d_entry_count, uint2* d_cand,
                   uint64_t cand_cap, unsigned long long* d_counters, cudaStream_t s,
                   const unsigned long long* d_nquery = nullptr /* foreign only: device-side query count (nquery = cap) */, int sms = 148,
-                  bool shared_vertices = false /* a mesh (V < 1.5 N): drop vertex-sharing candidates in the traversal */);
+                  bool shared_vertices = false /* a mesh (V < 1.5 N): drop vertex-sharing candidates in the traversal */,
+                  const QNodePair* d_qpairs = nullptr, const float* d_qframe = nullptr /* quantised nodes + their frame */);
+bool broad_uses_quantised_nodes(bool shared_vertices);  // whether a build should write d_qpairs for the traversal
 void launch_narrow(const LeafRec* d_leaves, const uint2* d_cand, uint64_t cand_cap, uint2* d_out, uint64_t out_cap,
                    unsigned long long* d_counters, int sms, cudaStream_t s, bool unshared_vertices = false);
 

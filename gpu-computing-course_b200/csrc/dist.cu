@@ -633,7 +633,8 @@ API int b200cd_dist_step(b200cd_dist* d, const b200cd_mesh* mesh, const b200cd_p
             const uint32_t chunk = (nlocal + B200CD_QUERY_BLOCK - 1) / B200CD_QUERY_BLOCK * B200CD_QUERY_BLOCK;
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q0], s));
             launch_broad(b->d_pairs, b->d_leaves, b->d_root_box, nlocal, 0, 1, chunk, chunk, /*foreign*/ 0, 0u, b->d_entries,
-                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s, nullptr, ctx->sm_count, !b->unshared_verts);
+                         b->d_entry_count, b->d_cand, b->cand_cap, b->d_counters, s, nullptr, ctx->sm_count, !b->unshared_verts,
+                         b->qvalid ? b->d_qpairs : nullptr, b->d_qframe);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q1], s));
             launch_narrow(b->d_leaves, b->d_cand, b->cand_cap, b->d_out, b->out_cap, b->d_counters, ctx->sm_count, s, b->unshared_verts);
             CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_Q2], s));
@@ -816,5 +817,6 @@ API int b200cd_dist_broadcast_bvh(b200cd_dist* d, b200cd_bvh* bvh, uint32_t root
     }
     bvh->built = true;
     bvh->id_space = n;
+    if (d->rank != root) bvh->qvalid = false;  // the quantised nodes do not travel: a received BVH is walked on the exact ones
     return B200CD_OK;
 }

@@ -114,7 +114,8 @@ __device__ __forceinline__ void write_root(const Carry& c, float* __restrict__ r
 // + fences). `have_slot`: the first arrival's split/side are already known (conversion of a deposit
 // left in shared memory).
 __device__ void climb_global(Carry c, bool have_slot, int s, int side, const uint64_t* __restrict__ keys, int n,
-                             uint32_t* __restrict__ flags, NodePair* __restrict__ pairs, float* __restrict__ root_box) {
+                             uint32_t* __restrict__ flags, NodePair* __restrict__ pairs, float* __restrict__ root_box,
+                             QNodePair* __restrict__ qpairs, const QFrame& qf) {
     while (true) {
         if (!have_slot) {
             const int dl = similarity_at(keys, n, c.F - 1), dr = similarity_at(keys, n, c.L);
@@ -130,6 +131,7 @@ __device__ void climb_global(Carry c, bool have_slot, int s, int side, const uin
         float4 a, b;
         pack(c, side ? c.L : c.F, a, b);
         st256_cg(&pairs[s].c[side], a, b);
+        if (qpairs) qpairs[s].c[side] = qnode_half(a, b, qf);  // read by later kernels only: no ordering needed
         // arrival counter with release (my half is visible before the count) and acquire (the sibling's half is
         // read after it) semantics in ONE instruction instead of two device-wide fences around a relaxed atomic
         unsigned int old;
@@ -154,7 +156,7 @@ struct __align__(16) Pending {
 __global__ void __launch_bounds__(128)
 upper_kernel(const Pending* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t capacity,
              const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
-             float* __restrict__ root_box) {
+             float* __restrict__ root_box, QNodePair* __restrict__ qpairs, const QFrame qf) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= min(__ldg(list_count), capacity)) return;
     const Pending p = list[i];
@@ -162,7 +164,7 @@ upper_kernel(const Pending* __restrict__ list, const uint32_t* __restrict__ list
     c.lo[0] = p.a.x; c.lo[1] = p.a.y; c.lo[2] = p.a.z; c.hi[0] = p.a.w; c.hi[1] = p.b.x; c.hi[2] = p.b.y;
     c.link = __float_as_int(p.b.z);
     c.F = p.F; c.L = p.L;
-    climb_global(c, p.side >= 0, p.slot, p.side, keys, n, flags, pairs, root_box);
+    climb_global(c, p.side >= 0, p.slot, p.side, keys, n, flags, pairs, root_box, qpairs, qf);
 }
 
 template <bool RECS>  // leaf records come from the face-ordered copies K1 wrote (recs) instead of idx / verts
@@ -171,7 +173,8 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
              const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
              LeafRec* __restrict__ leaves, float* __restrict__ root_box, Pending* __restrict__ list,
              uint32_t* __restrict__ list_count, uint32_t capacity, const LeafRec* __restrict__ recs,
-             float* __restrict__ block_boxes /* optional: [blocks][8], union box of each block's 256 leaves */) {
+             float* __restrict__ block_boxes /* optional: [blocks][8], union box of each block's 256 leaves */,
+             QNodePair* __restrict__ qpairs, float* __restrict__ qframe_out, const QFrame qf) {
     __shared__ float s_bb[BL / 32][6];
     __shared__ int s_sim[BL + 1];          // s_sim[i] = similarity of sorted positions (B0-1+i, B0+i); -1 outside
     __shared__ uint32_t s_flag[BL];        // per split B0+i: bit 0 = left child arrived, bit 1 = right child arrived
@@ -221,6 +224,7 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     }
     s_flag[tid] = 0;
     if (tid == 0) s_npend = 0;
+    if (qframe_out && blockIdx.x == 0 && tid < 6) qframe_out[tid] = tid < 3 ? qf.o[tid] : qf.s[tid - 3];
     if (block_boxes) {  // (partitioned builds) the ghost selection tests whole blocks against the peers' boxes first
         const float inf = __int_as_float(0x7f800000);
         float v[6] = {j < n ? c.lo[0] : inf, j < n ? c.lo[1] : inf, j < n ? c.lo[2] : inf,
@@ -287,7 +291,11 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     // written with full 32-byte sectors, two threads per node
     for (int i = tid; i < 2 * (BL - 1); i += BL) {
         const int ls = i >> 1, half = i & 1;
-        if (B0 + ls < Bend && s_flag[ls] == 3u) st256(&pairs[B0 + ls].c[half], s_dep[ls][half][0], s_dep[ls][half][1]);
+        if (B0 + ls < Bend && s_flag[ls] == 3u) {
+            const float4 a = s_dep[ls][half][0], b = s_dep[ls][half][1];
+            st256(&pairs[B0 + ls].c[half], a, b);
+            if (qpairs) qpairs[B0 + ls].c[half] = qnode_half(a, b, qf);  // neighbouring threads fill the two halves of a sector
+        }
     }
     // ---- leftovers are parked for upper_kernel: (1) my own subtree if its parent split lies outside the
     // block, (2) split B0+tid if only one child arrived (the sibling reaches beyond the block)
@@ -313,7 +321,7 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
             p.F = c.F; p.L = c.L; p.slot = 0; p.side = -1;
             list[at] = p;
         } else {
-            climb_global(c, false, 0, 0, keys, n, flags, pairs, root_box);  // list full: climb here
+            climb_global(c, false, 0, 0, keys, n, flags, pairs, root_box, qpairs, qf);  // list full: climb here
         }
         ++at;
     }
@@ -332,7 +340,7 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
             d.lo[0] = a.x; d.lo[1] = a.y; d.lo[2] = a.z; d.hi[0] = a.w; d.hi[1] = b.x; d.hi[2] = b.y;
             d.link = __float_as_int(b.z);
             d.F = p.F; d.L = p.L;
-            climb_global(d, true, s, side, keys, n, flags, pairs, root_box);
+            climb_global(d, true, s, side, keys, n, flags, pairs, root_box, qpairs, qf);
         }
     }
 }
@@ -467,8 +475,11 @@ uint32_t build_tree_pending_capacity(uint32_t n) { return n / 8 + 4096; }
 
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
-                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs, float* d_block_boxes) {
+                       void* d_scratch, cudaStream_t s, const LeafRec* d_recs, float* d_block_boxes, QNodePair* d_qpairs,
+                       float* d_qframe, const QFrame* frame) {
     if (!n) return;
+    QFrame qf{};
+    if (frame) qf = *frame; else d_qpairs = nullptr;
     uint32_t* list_count = static_cast<uint32_t*>(d_scratch);
     Pending* list = reinterpret_cast<Pending*>(static_cast<char*>(d_scratch) + 16);
     const uint32_t capacity = build_tree_pending_capacity(n);
@@ -476,15 +487,17 @@ void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint3
     cudaMemsetAsync(list_count, 0, sizeof(uint32_t), s);
     if (d_recs)
         build_kernel<true><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs, d_leaves,
-                                                            d_root_box, list, list_count, capacity, d_recs, d_block_boxes);
+                                                            d_root_box, list, list_count, capacity, d_recs, d_block_boxes, d_qpairs,
+                                                            d_qpairs ? d_qframe : nullptr, qf);
     else
         build_kernel<false><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs,
-                                                             d_leaves, d_root_box, list, list_count, capacity, nullptr, d_block_boxes);
+                                                             d_leaves, d_root_box, list, list_count, capacity, nullptr, d_block_boxes,
+                                                             d_qpairs, d_qpairs ? d_qframe : nullptr, qf);
     count_launch();
     trace_mark("build_kernel", s);
     {
         upper_kernel<<<(capacity + 127) / 128, 128, 0, s>>>(list, list_count, capacity, d_keys, (int)n, d_flags, d_pairs,
-                                                            d_root_box);
+                                                            d_root_box, d_qpairs, qf);
         count_launch();
         trace_mark("upper_kernel", s);
     }
