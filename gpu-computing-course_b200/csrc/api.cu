@@ -258,7 +258,8 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     const uint32_t n = b->n;
     if (m->pending) return set_error(ctx, B200CD_E_INVALID, "mesh has an asynchronous upload in flight: call b200cd_mesh_wait first");
     b->params = *p;
-    const QFrame qframe = make_qframe(*p);  // the traversal's 15-bit grid lies over the Morton box
+    const QFrame qframe = make_qframe(*p);  // the traversal's 15-bit grid: over the previous root box, else over the Morton box
+    const bool have_root = b->built && b->root_valid;
     b->built = false;
     b->unshared_verts = 2ull * m->nverts >= 3ull * m->ntris;
     b->qvalid = broad_uses_quantised_nodes(!b->unshared_verts);
@@ -380,7 +381,8 @@ int run_build(b200cd_ctx* ctx, b200cd_bvh* b, const b200cd_mesh* m, const b200cd
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B3], s));  // (K3 is fused into K4: ms_hierarchy stays ~0)
     launch_build_tree(m->d_verts, m->d_idx, b->d_ids[b->cur], b->d_keys[b->cur], n, b->d_flags, b->d_pairs, b->d_leaves,
                       b->d_root_box, b->d_build_scratch, s, keys_given ? nullptr : b->d_recs, b->d_block_boxes,
-                      b->qvalid ? b->d_qpairs : nullptr, b->d_qframe, &qframe);  // K3+K4
+                      b->qvalid ? b->d_qpairs : nullptr, b->d_qframe, &qframe, have_root);  // K3+K4
+    b->root_valid = n > 0;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, mark_consumed(m, s));  // nothing after this point reads the mesh
     CD_CUDA(ctx, cudaGetLastError());
@@ -864,7 +866,7 @@ API int b200cd_bvh_refit(b200cd_ctx* ctx, b200cd_bvh* bvh, const b200cd_mesh* me
     // the sorted keys are kept, so the same climb reproduces the same topology around the new boxes
     launch_build_tree(mesh->d_verts, mesh->d_idx, bvh->d_ids[bvh->cur], bvh->d_keys[bvh->cur], bvh->n, bvh->d_flags,
                       bvh->d_pairs, bvh->d_leaves, bvh->d_root_box, bvh->d_build_scratch, s, nullptr, bvh->d_block_boxes,
-                      bvh->qvalid ? bvh->d_qpairs : nullptr, bvh->d_qframe, &qframe);
+                      bvh->qvalid ? bvh->d_qpairs : nullptr, bvh->d_qframe, &qframe, bvh->root_valid);
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[EV_B4], s));
     CD_CUDA(ctx, mark_consumed(mesh, s));
     CD_CUDA(ctx, cudaGetLastError());

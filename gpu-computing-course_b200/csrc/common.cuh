@@ -198,6 +198,7 @@ struct b200cd_bvh {
     b200cd::NodePair* d_pairs = nullptr;  // n-1
     b200cd::QNodePair* d_qpairs = nullptr;  // n-1: the same nodes on the 15-bit grid (what the traversal reads)
     float* d_qframe = nullptr;         // 8 floats: QFrame of d_qpairs
+    bool root_valid = false;           // d_root_box holds the root box of a build of THIS handle (frame of the next build's grid)
     bool qvalid = false;               // the last build wrote d_qpairs (soups; B200CD_BROAD_QUANT): the traversal walks them
     b200cd::LeafRec* d_leaves = nullptr;  // n
     b200cd::LeafRec* d_recs = nullptr;    // n, face order: written by K1, moved into sorted order by the tree build (full builds only)
@@ -340,7 +341,8 @@ uint64_t build_tree_scratch_bytes(uint32_t n);
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
                        void* d_scratch, cudaStream_t s, const LeafRec* d_recs = nullptr, float* d_block_boxes = nullptr,
-                       QNodePair* d_qpairs = nullptr, float* d_qframe = nullptr, const QFrame* frame = nullptr);
+                       QNodePair* d_qpairs = nullptr, float* d_qframe = nullptr, const QFrame* frame = nullptr,
+                       bool frame_from_root = false /* d_root_box holds the previous build's root box: lay the grid over it */);
 // d_scratch: 2 * (2n-1) words
 void launch_export_nodes(const NodePair* d_pairs, const float* d_root_box, uint32_t n, uint32_t* d_scratch,
                          b200cd_node32* d_nodes_out, cudaStream_t s);

@@ -110,12 +110,42 @@ __device__ __forceinline__ void write_root(const Carry& c, float* __restrict__ r
     reinterpret_cast<int*>(root_box)[6] = c.link;  // index of the root node (or ~0 when n == 1)
 }
 
+__device__ __forceinline__ QFrame load_qframe(const float* __restrict__ qframe) {
+    QFrame f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        f.o[k] = qframe ? __ldg(qframe + k) : 0.f;
+        f.s[k] = qframe ? __ldg(qframe + 3 + k) : 0.f;
+    }
+    return f;
+}
+
+// The 15-bit grid of the quantised nodes (common.cuh QFrame). A rebuild lays it over the root box of the PREVIOUS build
+// (the mesh of a simulation moves little from frame to frame; whatever leaves the box lands in the border cells, still
+// conservative) - tight on every axis, where the Morton box of b200cd_params can be far larger than the mesh along one
+// of them (two flat sheets in a unit cube: 46 % more candidates on the cube-wide grid). First build: the Morton box.
+__global__ void qframe_kernel(const float* __restrict__ root_box, int have_root, const QFrame fallback, float* __restrict__ qframe) {
+    const int k = threadIdx.x;
+    if (k >= 3) return;
+    float o = fallback.o[k], s = fallback.s[k];
+    if (have_root) {
+        const float lo = root_box[k], hi = root_box[3 + k];
+        const float ext = hi - lo;
+        if (ext > 0.f && ext < 3.0e38f) {
+            const float sc = (float)Q_CELLS / ext;
+            if (sc > 0.f && sc < 3.0e38f) { o = lo; s = sc; }
+        }
+    }
+    qframe[k] = o;
+    qframe[3 + k] = s;
+}
+
 // Global-memory climb for the few subtrees that straddle block boundaries (bvh.cuh:269-283 protocol
 // + fences). `have_slot`: the first arrival's split/side are already known (conversion of a deposit
 // left in shared memory).
 __device__ void climb_global(Carry c, bool have_slot, int s, int side, const uint64_t* __restrict__ keys, int n,
                              uint32_t* __restrict__ flags, NodePair* __restrict__ pairs, float* __restrict__ root_box,
-                             QNodePair* __restrict__ qpairs, const QFrame& qf) {
+                             QNodePair* __restrict__ qpairs, const QFrame& qf) {  // qf: loaded by the caller iff qpairs
     while (true) {
         if (!have_slot) {
             const int dl = similarity_at(keys, n, c.F - 1), dr = similarity_at(keys, n, c.L);
@@ -156,9 +186,10 @@ struct __align__(16) Pending {
 __global__ void __launch_bounds__(128)
 upper_kernel(const Pending* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t capacity,
              const uint64_t* __restrict__ keys, int n, uint32_t* __restrict__ flags, NodePair* __restrict__ pairs,
-             float* __restrict__ root_box, QNodePair* __restrict__ qpairs, const QFrame qf) {
+             float* __restrict__ root_box, QNodePair* __restrict__ qpairs, const float* __restrict__ qframe) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= min(__ldg(list_count), capacity)) return;
+    const QFrame qf = load_qframe(qpairs ? qframe : nullptr);
     const Pending p = list[i];
     Carry c;
     c.lo[0] = p.a.x; c.lo[1] = p.a.y; c.lo[2] = p.a.z; c.hi[0] = p.a.w; c.hi[1] = p.b.x; c.hi[2] = p.b.y;
@@ -174,7 +205,7 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
              LeafRec* __restrict__ leaves, float* __restrict__ root_box, Pending* __restrict__ list,
              uint32_t* __restrict__ list_count, uint32_t capacity, const LeafRec* __restrict__ recs,
              float* __restrict__ block_boxes /* optional: [blocks][8], union box of each block's 256 leaves */,
-             QNodePair* __restrict__ qpairs, float* __restrict__ qframe_out, const QFrame qf) {
+             QNodePair* __restrict__ qpairs, const float* __restrict__ qframe) {
     __shared__ float s_bb[BL / 32][6];
     __shared__ int s_sim[BL + 1];          // s_sim[i] = similarity of sorted positions (B0-1+i, B0+i); -1 outside
     __shared__ uint32_t s_flag[BL];        // per split B0+i: bit 0 = left child arrived, bit 1 = right child arrived
@@ -184,6 +215,7 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     const int B0 = blockIdx.x * BL;
     const int j = B0 + tid;
     const int Bend = min(B0 + BL, n) - 1;  // last leaf of this block
+    const QFrame qf = load_qframe(qpairs ? qframe : nullptr);
 #ifdef BT_PROFILE
     long long t_prev = clock64();
 #endif
@@ -224,7 +256,6 @@ build_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ idx,
     }
     s_flag[tid] = 0;
     if (tid == 0) s_npend = 0;
-    if (qframe_out && blockIdx.x == 0 && tid < 6) qframe_out[tid] = tid < 3 ? qf.o[tid] : qf.s[tid - 3];
     if (block_boxes) {  // (partitioned builds) the ghost selection tests whole blocks against the peers' boxes first
         const float inf = __int_as_float(0x7f800000);
         float v[6] = {j < n ? c.lo[0] : inf, j < n ? c.lo[1] : inf, j < n ? c.lo[2] : inf,
@@ -476,10 +507,13 @@ uint32_t build_tree_pending_capacity(uint32_t n) { return n / 8 + 4096; }
 void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint32_t* d_sorted_ids, const uint64_t* d_keys,
                        uint32_t n, uint32_t* d_flags, NodePair* d_pairs, LeafRec* d_leaves, float* d_root_box,
                        void* d_scratch, cudaStream_t s, const LeafRec* d_recs, float* d_block_boxes, QNodePair* d_qpairs,
-                       float* d_qframe, const QFrame* frame) {
+                       float* d_qframe, const QFrame* frame, bool frame_from_root) {
     if (!n) return;
-    QFrame qf{};
-    if (frame) qf = *frame; else d_qpairs = nullptr;
+    if (!frame || !d_qframe) d_qpairs = nullptr;
+    if (d_qpairs) {  // the grid of the quantised nodes: over the PREVIOUS build's root box when there is one, else over `frame`
+        qframe_kernel<<<1, 32, 0, s>>>(d_root_box, frame_from_root ? 1 : 0, *frame, d_qframe);
+        count_launch();
+    }
     uint32_t* list_count = static_cast<uint32_t*>(d_scratch);
     Pending* list = reinterpret_cast<Pending*>(static_cast<char*>(d_scratch) + 16);
     const uint32_t capacity = build_tree_pending_capacity(n);
@@ -488,16 +522,16 @@ void launch_build_tree(const float4* d_verts, const uint32_t* d_idx, const uint3
     if (d_recs)
         build_kernel<true><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs, d_leaves,
                                                             d_root_box, list, list_count, capacity, d_recs, d_block_boxes, d_qpairs,
-                                                            d_qpairs ? d_qframe : nullptr, qf);
+                                                            d_qframe);
     else
         build_kernel<false><<<(n + BL - 1) / BL, BL, 0, s>>>(d_verts, d_idx, d_sorted_ids, d_keys, (int)n, d_flags, d_pairs,
                                                              d_leaves, d_root_box, list, list_count, capacity, nullptr, d_block_boxes,
-                                                             d_qpairs, d_qpairs ? d_qframe : nullptr, qf);
+                                                             d_qpairs, d_qframe);
     count_launch();
     trace_mark("build_kernel", s);
     {
         upper_kernel<<<(capacity + 127) / 128, 128, 0, s>>>(list, list_count, capacity, d_keys, (int)n, d_flags, d_pairs,
-                                                            d_root_box, d_qpairs, qf);
+                                                            d_root_box, d_qpairs, d_qframe);
         count_launch();
         trace_mark("upper_kernel", s);
     }

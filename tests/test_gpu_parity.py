@@ -497,3 +497,50 @@ print("ok")
 """ % root
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, B200CD_TRAVERSAL=variant))
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("knobs", [{"B200CD_BROAD_QUANT": "1"}, {"B200CD_BROAD_QUANT": "0"},
+                                   {"B200CD_BROAD_QUANT": "1", "B200CD_BROAD_GRID": "persist"}])
+def test_quantised_node_traversal_gives_the_same_pairs(knobs):
+    """The traversal on 32-byte quantised nodes (default on soups) forced on for meshes too (=1: shared-vertex filter +
+    quantised walk, touching boxes everywhere), off everywhere (=0), and with persistent warps - against the oracle, in a
+    fresh process. Covers: Morton boxes much larger and much smaller than the mesh (cells clamp at the border), rebuilds
+    (the grid moves to the previous root box), refits after the vertices moved out of that box, a degenerate flat mesh."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import importlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+cd = importlib.import_module("gpu-computing-course_b200.binding")
+mg = importlib.import_module("gpu-computing-course_b200.meshgen")
+from oracle import cdoracle as co
+ctx = cd.Context(0)
+flat = mg.soup(4000, seed=9)
+flat[0][:, 2] = 0.5                                   # every vertex in one plane: zero extent along z
+cases = ((mg.soup(60000, seed=2), ((0, 0, 0), (1, 1, 1))), (mg.cloth_fold(90, 90), None), (mg.two_sheets(64), ((0, 0, 0), (1, 1, 1))),
+         (mg.soup(20000, seed=3), ((-40, -40, -40), (100, 100, 100))),      # grid far coarser than the triangles
+         (mg.soup(20000, seed=4), ((0.4, 0.4, 0.4), (0.2, 0.2, 0.2))),      # most of the mesh outside the box
+         (flat, ((0, 0, 0), (1, 1, 1))), (mg.soup(3, h=0.4, seed=1), ((0, 0, 0), (1, 1, 1))))
+for (xyz, idx), box in cases:
+    p = cd.make_params(*box) if box else cd.default_params()
+    op = co.make_params(*box) if box else co.default_params()
+    mesh = ctx.mesh_from_arrays(xyz, idx)
+    bvh = ctx.bvh_build(mesh, p)
+    ref, _ = co.run(xyz, idx, op)
+    assert np.array_equal(ctx.self_collide(bvh, sorted=True), ref), ("build", len(idx))
+    ctx.bvh_rebuild(bvh, mesh, p)                     # grid over the first build's root box
+    assert np.array_equal(ctx.self_collide(bvh, sorted=True), ref), ("rebuild", len(idx))
+    moved = (xyz * np.float32(1.5) + np.float32(0.25)).astype(np.float32)   # leaves the previous root box
+    mesh.update(moved)
+    ctx.bvh_refit(bvh, mesh)
+    ref2, _ = co.run(moved, idx, op)
+    got = ctx.self_collide(bvh, sorted=True)
+    assert np.array_equal(got, ref2), ("refit", len(idx))
+    bvh.destroy(); mesh.destroy()
+print("ok")
+""" % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, **knobs))
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
