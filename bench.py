@@ -71,10 +71,12 @@ def generate(mg, name, out=None):
     return getattr(mg, kind)(**kw, out=out)
 
 
-def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes, recs=True):
+def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes, recs=True, quant=False):
     """Compulsory HBM bytes per stage for OUR data layout, each array read or
     written once per pass. n triangles, nverts vertices. recs: K1 also writes the face-ordered 64 B leaf
-    records and the tree build moves those (single-GPU full builds) instead of gathering indices + vertices."""
+    records and the tree build moves those (single-GPU full builds) instead of gathering indices + vertices.
+    quant: the tree build also writes the 32 B quantised node pairs and the traversal reads those instead of the
+    64 B exact ones (triangle soups, csrc/collide.cu broad_uses_quantised_nodes)."""
     return {
         # K1: 12 B indices + one 16 B float4 per vertex (each vertex is read at least once) + 8 B key out (+ 64 B record)
         "morton": 12 * n + 16 * nverts + 8 * n + (64 * n if recs else 0),
@@ -83,13 +85,23 @@ def algorithmic_bytes(n, nverts, ncand, npairs, sort_passes, recs=True):
         #     hybrid sort (< 8 passes): the fix-up reads the keys once more
         "sort": 8 * n + sort_passes * 24 * n - 4 * n + (8 * n if sort_passes < 8 else 0),
         # K3+K4 (fused): sorted ids + keys + indices + vertices in, 64 B leaf record + 64 B node pair out
-        "tree": 4 * n + 8 * n + (64 * n if recs else 12 * n + 16 * nverts) + 64 * n + 64 * n,
-        # K5: every node pair (64 B) and every query record (64 B) once, 8 B per candidate out
-        "traverse": 64 * n + 64 * n + 8 * ncand,
+        "tree": 4 * n + 8 * n + (64 * n if recs else 12 * n + 16 * nverts) + 64 * n + 64 * n + (32 * n if quant else 0),
+        # K5: every node pair (64 B, or 32 B quantised) and every query record (64 B) once, 8 B per candidate out
+        "traverse": (32 if quant else 64) * n + 64 * n + 8 * ncand,
         # K6: candidate list in, every leaf record it names at most once from HBM (compulsory traffic; repeats are
         #     cache hits), 8 B per pair out
         "narrow": 8 * ncand + 64 * min(2 * ncand, n) + 8 * npairs,
     }
+
+
+def uses_quantised_nodes(ntris, nverts):
+    """mirror of csrc/collide.cu broad_uses_quantised_nodes: soups (V >= 1.5 N) unless B200CD_BROAD_QUANT says otherwise"""
+    e = os.environ.get("B200CD_BROAD_QUANT")
+    if os.environ.get("B200CD_TRAVERSAL", "2")[:1] != "2":
+        return False
+    if e is not None:
+        return e[:1] != "0"
+    return 2 * nverts >= 3 * ntris
 
 
 def contract_bytes(n, nverts, npairs):
@@ -602,19 +614,21 @@ def run_gpu_arm(args, workload):
         ncand, npairs = int(last.get("candidates", 0)), int(last.get("pairs", 0))
         recs = os.environ.get("B200CD_RECS", "1") != "0"
         recs = recs and 2 * nverts >= 3 * ntris  # api.cu run_build: only for (mostly) unshared vertices
-        abytes = algorithmic_bytes(ntris, nverts, ncand, npairs, int(last.get("sort_passes", 8)), recs)
+        quant = uses_quantised_nodes(ntris, nverts)
+        abytes = algorithmic_bytes(ntris, nverts, ncand, npairs, int(last.get("sort_passes", 8)), recs, quant)
         nloc = ntris
         if partitioned:  # rank 0's own Morton range (keys arrive from the exchange: no face-ordered records)
             nloc = int(pstats.get("local_triangles", ntris // world))
-            abytes = algorithmic_bytes(nloc, min(nverts, 3 * nloc), ncand, npairs, int(last.get("sort_passes", 8)), False)
+            abytes = algorithmic_bytes(nloc, min(nverts, 3 * nloc), ncand, npairs, int(last.get("sort_passes", 8)), False, quant)
         elif world > 1:  # per-rank share of the query stages
-            abytes["traverse"] = 64 * ntris + 64 * ntris // world + 8 * ncand
+            abytes["traverse"] = (32 if quant else 64) * ntris + 64 * ntris // world + 8 * ncand
         stages = {}
         for s, key in (("morton", "ms_morton"), ("sort", "ms_sort"), ("tree", "ms_refit"),
                        ("traverse", "ms_traverse"), ("narrow", "ms_narrow")):
             ms = acc[key] / K
             gbs = abytes[s] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-            stages[s] = {"kernel": STAGE_KERNEL[s], "ms": round(ms, 4), "algorithmic_bytes": int(abytes[s]),
+            kname = "broad_kernel_q (quantised nodes) (+ entry_kernel)" if (s == "traverse" and quant) else STAGE_KERNEL[s]
+            stages[s] = {"kernel": kname, "ms": round(ms, 4), "algorithmic_bytes": int(abytes[s]),
                          "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
         if partitioned:  # K1 ran on the rank's input slice before the exchange: not part of the local build's events
             stages["morton"] = {"kernel": STAGE_KERNEL["morton"], "ms": None, "note": "runs before the key exchange (phase_ms: keys+hist+allreduce)"}
@@ -626,8 +640,9 @@ def run_gpu_arm(args, workload):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         traffic_note = None
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(workload, {}).get(dominant)
+        traffic_file = json.load(open(tpath)) if os.path.exists(tpath) else {}
+        if traffic_file:
+            traffic = traffic_file.get(workload, {}).get(dominant)
             if traffic is not None and world > 1:
                 # ncu may not wrap a multi-rank run: the single-GPU capture of the same workload, divided by the ranks
                 # (each rank traverses 1/N of the leaves over 1/N of the nodes)
@@ -643,7 +658,7 @@ def run_gpu_arm(args, workload):
             gbs = cb[st_] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             contract[st_] = {"bytes": int(cb[st_]), "ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
         contract_stage = {"traverse": "query", "narrow": "query"}.get(dominant, dominant)
-        roofline = {"bound": "hbm", "kernel": STAGE_KERNEL[dominant], "stage": dominant,
+        roofline = {"bound": "hbm", "kernel": stages[dominant]["kernel"], "stage": dominant,
                     "achieved": stages[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": stages[dominant]["frac"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                     "launch_ms": stages[dominant]["ms"], "algorithmic_bytes": stages[dominant]["algorithmic_bytes"],
@@ -652,6 +667,8 @@ def run_gpu_arm(args, workload):
                     "contract": dict(contract, note="SURVEY.md 8(d) bytes: K1 48N+16V, K2 200N, K3+K4 132N, K5 (traverse+narrow) "
                                                     "100N+16V+8*pairs, e2e 480N+32V+8*pairs; `frac_contract` is the dominant "
                                                     "kernel's stage (traverse and narrow share K5)"),
+                    # what actually bounds the traversal (ncu, profiles/r02_ncu_broad_l1.md): the L1 data pipe, not HBM
+                    "traverse_l1_data_pipe": traffic_file.get("_l1_data_pipe", {}).get(workload) if dominant == "traverse" else None,
                     "e2e_frac_contract": contract["e2e"]["frac"],
                     "e2e_algorithmic_bytes": int(sum(abytes.values())),
                     "e2e_frac": round(sum(abytes.values()) / ((acc["ms_build"] + acc["ms_query"]) / K * 1e-3) / 1e9 / peak, 4)
