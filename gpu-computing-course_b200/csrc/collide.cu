@@ -23,6 +23,10 @@
 //     (B200CD_QUERY_GROUP; one warp of the persistent-lane traversal works through one group)
 //     walks the group's ancestors once (entry_kernel) and every query of the group starts at
 //     the handful of subtrees that tile "leaves after me" and overlap the group's union box.
+//   - on triangle soups the walk reads QUANTISED nodes (common.cuh QNodePair: both children in one 32-byte sector,
+//     conservative 15-bit cells) - the traversal is bound by the L1 data pipe, i.e. by sectors per node visit - and
+//     emits a superset of the exact candidates; the narrow phase applies the exact strict box test first
+//     (broad_kernel_q; meshes keep the exact 64-byte nodes: touching boxes defeat a quantiser).
 //   - traversal only emits CANDIDATES (AABB-overlapping leaf pairs) into a compact
 //     list: per-warp staging in shared memory filled with ballots (no atomics),
 //     flushed with one global atomicAdd per >=32 candidates. The divergent fp64

@@ -95,7 +95,8 @@ typedef struct b200cd_stats {
     float ms_query;       /* K5 + K6 (+ sort) end to end */
     float ms_download;    /* D2H of the pair list */
     uint32_t ntris, nverts;
-    uint64_t candidates;  /* AABB-overlapping leaf pairs handed to the narrow phase */
+    uint64_t candidates;  /* leaf pairs handed to the narrow phase: the AABB-overlapping ones (collision.cuh:36), on a triangle soup a
+                             few per cent more - its traversal walks 15-bit quantised boxes and the narrow phase re-tests the exact ones */
     uint64_t pairs;       /* colliding pairs found */
     uint32_t sort_passes; /* radix passes actually run */
     uint32_t query_retries; /* times a stage was re-run after growing a buffer */
