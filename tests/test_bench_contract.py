@@ -40,3 +40,27 @@ def test_non_zero_ranks_of_the_reference_arm_print_nothing():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          cwd=ROOT, capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_stage_bytes_follow_the_layout_the_library_uses(monkeypatch):
+    """bench.py's per-stage algorithmic bytes: a soup walks the 32-byte quantised nodes (and its build writes them), a
+    mesh the exact 64-byte ones; the knob that overrides the library's choice overrides bench.py's too"""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    n = 1 << 20
+    for var in ("B200CD_BROAD_QUANT", "B200CD_TRAVERSAL"):
+        monkeypatch.delenv(var, raising=False)
+    assert bench.uses_quantised_nodes(n, 3 * n) and not bench.uses_quantised_nodes(n, n // 2)
+    exact = bench.algorithmic_bytes(n, 3 * n, 5 * n, n // 8, 4, recs=True, quant=False)
+    quant = bench.algorithmic_bytes(n, 3 * n, 5 * n, n // 8, 4, recs=True, quant=True)
+    assert exact["traverse"] - quant["traverse"] == 32 * n and quant["tree"] - exact["tree"] == 32 * n
+    assert all(exact[k] == quant[k] for k in ("morton", "sort", "narrow"))
+    monkeypatch.setenv("B200CD_BROAD_QUANT", "0")
+    assert not bench.uses_quantised_nodes(n, 3 * n)
+    monkeypatch.setenv("B200CD_BROAD_QUANT", "1")
+    assert bench.uses_quantised_nodes(n, n // 2)
+    monkeypatch.setenv("B200CD_TRAVERSAL", "1")
+    assert not bench.uses_quantised_nodes(n, 3 * n)
+    # the survey's contract bytes do not depend on our layout
+    assert bench.contract_bytes(n, 3 * n, 7)["query"] == 100 * n + 16 * 3 * n + 8 * 7
